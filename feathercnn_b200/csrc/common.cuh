@@ -1,0 +1,46 @@
+// Shared helpers for the fcuda kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+// Error convention mirrors the reference booster: 0 ok, negative int on failure
+// (/root/reference/src/booster/avx/booster.cpp:306-307,349-353).  CUDA failures map to -700.
+#define FCUDA_ERR_CUDA (-700)
+
+#define FCUDA_CHECK(expr)                                                              \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            fprintf(stderr, "fcuda: %s failed at %s:%d: %s\n", #expr, __FILE__,        \
+                    __LINE__, cudaGetErrorString(_e));                                 \
+            return FCUDA_ERR_CUDA;                                                     \
+        }                                                                              \
+    } while (0)
+
+#define FCUDA_CHECK_LAUNCH() FCUDA_CHECK(cudaGetLastError())
+
+namespace fcuda {
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
+static inline size_t round_up_sz(size_t a, size_t b) { return ceil_div_sz(a, b) * b; }
+
+// Number of SMs of the current device (148 on B200); cached per process.
+int sm_count();
+
+// Split an fp32 value into a TF32-representable "hi" (round-to-nearest on the 13 dropped
+// mantissa bits) and the exact fp32 remainder "lo".  hi + lo == v exactly; the tensor
+// core then truncates lo to TF32, leaving a relative error of ~2^-22 per operand.
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+    uint32_t u = __float_as_uint(v);
+    // round to nearest (ties away) on bit 13, then clear the low 13 bits
+    uint32_t r = (u + 0x1000u) & 0xFFFFE000u;
+    // Inf/NaN: keep as is (exponent all ones) — adding could overflow the exponent field.
+    if ((u & 0x7F800000u) == 0x7F800000u) r = u & 0xFFFFE000u;
+    hi = __uint_as_float(r);
+    lo = v - hi;
+}
+
+}  // namespace fcuda

@@ -1,0 +1,587 @@
+// TensorGEMM on tcgen05 (sm_100a).  See tensor_gemm.cuh for the contract.
+//
+// Kernel anatomy (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 3D boxes (K=32 fp32 = one 128B swizzle atom)
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma kind::tf32, accumulators in TMEM
+//   warps 2..5  epilogue       : tcgen05.ld 32x32b -> registers -> fused store (row-major / NCHW+bias+ReLU / FC)
+// Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring
+// (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "tensor_gemm.cuh"
+#include "common.cuh"
+
+#include <mutex>
+
+namespace fcuda {
+
+// --------------------------------------------------------------------------------------------
+// PTX wrappers
+// --------------------------------------------------------------------------------------------
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must fail the launch (trap) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+            printf("fcuda tensor_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, single CTA.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrives on `bar` once all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> lane base+i).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace ptx
+
+// --------------------------------------------------------------------------------------------
+// Descriptors
+// --------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor for a K-major tile whose rows are 128 bytes (32 fp32) wide,
+// laid out by TMA with CU_TENSOR_MAP_SWIZZLE_128B: 8-row groups of 1024 B (SBO = 1024),
+// LBO unused for swizzled K-major layouts (set to 1 as CUTLASS does), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);  // start address, 16-byte units
+    d |= static_cast<uint64_t>(1) << 16;                    // leading byte offset (ignored)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;            // stride byte offset between 8-row groups
+    d |= static_cast<uint64_t>(1) << 46;                    // descriptor version (Blackwell)
+    d |= static_cast<uint64_t>(2) << 61;                    // layout type: SWIZZLE_128B
+    return d;
+}
+
+// Instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int bn) {
+    return (1u << 4)                               // c_format = F32
+           | (2u << 7)                             // a_format = TF32
+           | (2u << 10)                            // b_format = TF32
+           | (static_cast<uint32_t>(bn >> 3) << 17)  // N / 8
+           | (static_cast<uint32_t>(128 >> 4) << 24);  // M / 16
+}
+
+// --------------------------------------------------------------------------------------------
+// Kernel
+// --------------------------------------------------------------------------------------------
+constexpr int kBM = 128;
+constexpr int kBK = 32;  // fp32 elements per k-block = 128 bytes = one swizzle atom
+constexpr int kThreads = 192;
+
+struct GemmKernelArgs {
+    float* D;
+    const float* bias;
+    int M, N, K, G;
+    int epilogue, ldd, P, relu, split_k;
+    int num_m, num_n, k_blocks_total;
+};
+
+template <int BN, int PLANES>
+struct SmemLayout {
+    static constexpr int kATile = kBM * kBK * 4;  // 16 KB
+    static constexpr int kBTile = BN * kBK * 4;
+    static constexpr int kStage = PLANES * (kATile + kBTile);
+};
+
+template <int BN, int PLANES, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tensor_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                   const GemmKernelArgs args) {
+    using L = SmemLayout<BN, PLANES>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    __shared__ uint64_t full_bar[STAGES];
+    __shared__ uint64_t empty_bar[STAGES];
+    __shared__ uint64_t tmem_full_bar[2];
+    __shared__ uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int tiles_per_g = args.num_m * args.num_n;
+    const int total_tiles = tiles_per_g * args.G * args.split_k;
+    const int kb_per_split = (args.k_blocks_total + args.split_k - 1) / args.split_k;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tmem_full_bar[s], 1);
+            ptx::mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+        if (PLANES == 2) {
+            ptx::prefetch_tensormap(&tmAlo);
+            ptx::prefetch_tensormap(&tmBlo);
+        }
+    }
+    constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    if (warp == 1) {
+        ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ks = tile / (tiles_per_g * args.G);
+                const int rem = tile - ks * (tiles_per_g * args.G);
+                const int g = rem / tiles_per_g;
+                const int mn = rem - g * tiles_per_g;
+                const int m_blk = mn / args.num_n;
+                const int n_blk = mn - m_blk * args.num_n;
+                const int kb0 = ks * kb_per_split;
+                const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * L::kStage;
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStage);
+                    ptx::tma_load_3d(st, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM, g);
+                    ptx::tma_load_3d(st + L::kATile, &tmB, &full_bar[stage], kb * kBK, n_blk * BN, g);
+                    if (PLANES == 2) {
+                        ptx::tma_load_3d(st + L::kATile + L::kBTile, &tmAlo, &full_bar[stage], kb * kBK, m_blk * kBM, g);
+                        ptx::tma_load_3d(st + 2 * L::kATile + L::kBTile, &tmBlo, &full_bar[stage], kb * kBK, n_blk * BN, g);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int ks = tile / (tiles_per_g * args.G);
+                const int kb0 = ks * kb_per_split;
+                const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + stage * L::kStage);
+                    const uint64_t dA = make_smem_desc_sw128(st);
+                    const uint64_t dB = make_smem_desc_sw128(st + L::kATile);
+                    const uint64_t dAlo = make_smem_desc_sw128(st + L::kATile + L::kBTile);
+                    const uint64_t dBlo = make_smem_desc_sw128(st + 2 * L::kATile + L::kBTile);
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k) {
+                        // advance 8 tf32 = 32 bytes inside the 128-byte swizzle atom: +2 in 16-byte units
+                        const uint64_t koff = static_cast<uint64_t>(k * 2);
+                        const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
+                        if (PLANES == 2) {
+                            ptx::umma_tf32(tmem_d, dAlo + koff, dB + koff, idesc, first);
+                            ptx::umma_tf32(tmem_d, dA + koff, dBlo + koff, idesc, 1u);
+                            ptx::umma_tf32(tmem_d, dA + koff, dB + koff, idesc, 1u);
+                        } else {
+                            ptx::umma_tf32(tmem_d, dA + koff, dB + koff, idesc, first);
+                        }
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int ks = tile / (tiles_per_g * args.G);
+            const int rem = tile - ks * (tiles_per_g * args.G);
+            const int g = rem / tiles_per_g;
+            const int mn = rem - g * tiles_per_g;
+            const int m_blk = mn / args.num_n;
+            const int n_blk = mn - m_blk * args.num_n;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(&tmem_full_bar[as], aphase);
+            ptx::tc_fence_after();
+
+            const int m = m_blk * kBM + q * 32 + lane;
+            const bool m_ok = m < args.M;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+
+            // per-row output bases
+            size_t row_base = 0;
+            int img = 0, pix = 0;
+            if (args.epilogue == EPI_ROWMAJOR) {
+                row_base = (static_cast<size_t>(g) * args.M + (m_ok ? m : 0)) * args.ldd;
+            } else if (args.epilogue == EPI_NCHW) {
+                img = (m_ok ? m : 0) / args.P;
+                pix = (m_ok ? m : 0) - img * args.P;
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int n0 = n_blk * BN + c0;
+                if (n0 >= args.N) break;  // warp-uniform
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(taddr0 + c0, r);
+                ptx::tmem_ld_wait();
+                if (m_ok) {
+                    if (args.epilogue == EPI_ROWMAJOR) {
+                        float* dst = args.D + row_base + n0;
+                        if (n0 + 32 <= args.N && (args.ldd & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                                *reinterpret_cast<float4*>(dst + j) = v;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + j < args.N) dst[j] = __uint_as_float(r[j]);
+                        }
+                    } else if (args.epilogue == EPI_NCHW) {
+                        // lanes hold consecutive pixels -> each column store is a coalesced 128-byte line
+                        float* dst = args.D + (static_cast<size_t>(img) * args.N + n0) * args.P + pix;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (n0 + j < args.N) {
+                                float v = __uint_as_float(r[j]);
+                                if (args.bias) v += __ldg(args.bias + n0 + j);
+                                if (args.relu) v = fmaxf(v, 0.f);
+                                dst[static_cast<size_t>(j) * args.P] = v;
+                            }
+                        }
+                    } else {  // EPI_COLMAJOR_ATOMIC
+                        float* dst = args.D + static_cast<size_t>(n0) * args.ldd + m;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (n0 + j < args.N) {
+                                if (args.split_k > 1)
+                                    atomicAdd(dst + static_cast<size_t>(j) * args.ldd, __uint_as_float(r[j]));
+                                else
+                                    dst[static_cast<size_t>(j) * args.ldd] += __uint_as_float(r[j]);
+                            }
+                        }
+                    }
+                }
+            }
+            // hand the accumulator stage back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Host side
+// --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        // Resolve through the runtime so the library does not link libcuda directly.
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+        n = prop.multiProcessorCount;
+    }
+    return n;
+}
+
+// 3D map over [G][rows][K] fp32 with a (32 x box_rows x 1) box and 128B swizzle.
+static int make_map(CUtensorMap* map, const float* base, int K, int rows, int G, long long batch_stride,
+                    int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        fprintf(stderr, "fcuda: cuTensorMapEncodeTiled unavailable (no CUDA driver?)\n");
+        return FCUDA_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(G)};
+    const cuuint64_t bstride = batch_stride > 0 ? static_cast<cuuint64_t>(batch_stride)
+                                                : static_cast<cuuint64_t>(K) * static_cast<cuuint64_t>(rows);
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 4, bstride * 4};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "fcuda: cuTensorMapEncodeTiled failed (%d) K=%d rows=%d G=%d\n", static_cast<int>(r), K, rows, G);
+        return FCUDA_ERR_CUDA;
+    }
+    return 0;
+}
+
+bool tensor_gemm_supported(const GemmProblem& p) {
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.G <= 0) return false;
+    if (p.K % 4 != 0) return false;
+    auto aligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!aligned(p.A_hi) || !aligned(p.B_hi)) return false;
+    if (p.planes == 2 && (!p.A_lo || !p.B_lo || !aligned(p.A_lo) || !aligned(p.B_lo))) return false;
+    if (p.a_batch_stride % 4 != 0 || p.b_batch_stride % 4 != 0) return false;
+    return true;
+}
+
+template <int BN, int PLANES, int STAGES>
+static int launch(const GemmProblem& p, cudaStream_t stream) {
+    using L = SmemLayout<BN, PLANES>;
+    static_assert(STAGES * L::kStage + 1024 <= 227 * 1024, "smem budget");
+    CUtensorMap tmA, tmAlo, tmB, tmBlo;
+    const long long as = p.a_batch_stride ? p.a_batch_stride : static_cast<long long>(p.M) * p.K;
+    const long long bs = p.b_batch_stride ? p.b_batch_stride : static_cast<long long>(p.N) * p.K;
+    int rc;
+    if ((rc = make_map(&tmA, p.A_hi, p.K, p.M, p.G, as, kBM))) return rc;
+    if ((rc = make_map(&tmB, p.B_hi, p.K, p.N, p.G, bs, BN))) return rc;
+    if (PLANES == 2) {
+        if ((rc = make_map(&tmAlo, p.A_lo, p.K, p.M, p.G, as, kBM))) return rc;
+        if ((rc = make_map(&tmBlo, p.B_lo, p.K, p.N, p.G, bs, BN))) return rc;
+    } else {
+        tmAlo = tmA;
+        tmBlo = tmB;
+    }
+    GemmKernelArgs a;
+    a.D = p.D; a.bias = p.bias;
+    a.M = p.M; a.N = p.N; a.K = p.K; a.G = p.G;
+    a.epilogue = p.epilogue; a.ldd = p.ldd; a.P = p.P > 0 ? p.P : 1; a.relu = p.relu;
+    a.split_k = p.split_k > 0 ? p.split_k : 1;
+    a.num_m = ceil_div(p.M, kBM);
+    a.num_n = ceil_div(p.N, BN);
+    a.k_blocks_total = ceil_div(p.K, kBK);
+    if (a.split_k > a.k_blocks_total) a.split_k = a.k_blocks_total;
+    // every k-split must own at least one k-block, otherwise its accumulator is never written
+    while (a.split_k > 1 && ceil_div(a.k_blocks_total, a.split_k) * (a.split_k - 1) >= a.k_blocks_total) --a.split_k;
+    const long long total = static_cast<long long>(a.num_m) * a.num_n * a.G * a.split_k;
+    if (total > 0x7fffffffLL) return -1;
+    const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+    const int smem = STAGES * L::kStage + 1024;
+    auto kern = tensor_gemm_kernel<BN, PLANES, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmAlo, tmB, tmBlo, a);
+    FCUDA_CHECK_LAUNCH();
+    return 0;
+}
+
+int tensor_gemm(const GemmProblem& p, cudaStream_t stream) {
+    if (!tensor_gemm_supported(p)) return -1;
+    if (p.split_k > 1 && p.epilogue != EPI_COLMAJOR_ATOMIC) return -1;
+    const bool x3 = p.planes == 2;
+    // N tile: smallest supported tile that covers N (fewer wasted MMA columns), capped at 128/256.
+    if (p.N <= 32) return x3 ? launch<32, 2, 4>(p, stream) : launch<32, 1, 8>(p, stream);
+    if (p.N <= 64) return x3 ? launch<64, 2, 4>(p, stream) : launch<64, 1, 8>(p, stream);
+    if (p.N <= 128 || x3) return x3 ? launch<128, 2, 3>(p, stream) : launch<128, 1, 6>(p, stream);
+    return launch<256, 1, 4>(p, stream);
+}
+
+// --------------------------------------------------------------------------------------------
+// CUDA-core reference GEMM (same contract).  64x64 tile, 4x4 micro-tile per thread.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+simt_gemm_kernel(const float* __restrict__ A_hi, const float* __restrict__ A_lo, const float* __restrict__ B_hi,
+                 const float* __restrict__ B_lo, long long a_stride, long long b_stride, GemmKernelArgs args) {
+    __shared__ float sA[16][64 + 4];
+    __shared__ float sB[16][64 + 4];
+    const int g = blockIdx.z;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const float* Ah = A_hi + g * a_stride;
+    const float* Al = A_lo ? A_lo + g * a_stride : nullptr;
+    const float* Bh = B_hi + g * b_stride;
+    const float* Bl = B_lo ? B_lo + g * b_stride : nullptr;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < args.K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int r = i >> 4, c = i & 15;
+            const int k = k0 + c;
+            float a = 0.f, b = 0.f;
+            if (m0 + r < args.M && k < args.K) {
+                a = Ah[static_cast<size_t>(m0 + r) * args.K + k];
+                if (Al) a += Al[static_cast<size_t>(m0 + r) * args.K + k];
+            }
+            if (n0 + r < args.N && k < args.K) {
+                b = Bh[static_cast<size_t>(n0 + r) * args.K + k];
+                if (Bl) b += Bl[static_cast<size_t>(n0 + r) * args.K + k];
+            }
+            sA[c][r] = a;
+            sB[c][r] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sA[c][ty * 4 + i]; b[i] = sB[c][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= args.M) continue;
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= args.N) continue;
+            float v = acc[i][j];
+            if (args.epilogue == EPI_ROWMAJOR) {
+                args.D[(static_cast<size_t>(g) * args.M + m) * args.ldd + n] = v;
+            } else if (args.epilogue == EPI_NCHW) {
+                const int img = m / args.P, pix = m - img * args.P;
+                if (args.bias) v += args.bias[n];
+                if (args.relu) v = fmaxf(v, 0.f);
+                args.D[(static_cast<size_t>(img) * args.N + n) * args.P + pix] = v;
+            } else {
+                args.D[static_cast<size_t>(n) * args.ldd + m] += v;
+            }
+        }
+    }
+}
+
+int simt_gemm(const GemmProblem& p, cudaStream_t stream) {
+    GemmKernelArgs a;
+    a.D = p.D; a.bias = p.bias;
+    a.M = p.M; a.N = p.N; a.K = p.K; a.G = p.G;
+    a.epilogue = p.epilogue; a.ldd = p.ldd; a.P = p.P > 0 ? p.P : 1; a.relu = p.relu; a.split_k = 1;
+    a.num_m = ceil_div(p.M, 64); a.num_n = ceil_div(p.N, 64); a.k_blocks_total = 0;
+    const long long as = p.a_batch_stride ? p.a_batch_stride : static_cast<long long>(p.M) * p.K;
+    const long long bs = p.b_batch_stride ? p.b_batch_stride : static_cast<long long>(p.N) * p.K;
+    dim3 grid(a.num_n, a.num_m, p.G);
+    simt_gemm_kernel<<<grid, 256, 0, stream>>>(p.A_hi, p.planes == 2 ? p.A_lo : nullptr, p.B_hi,
+                                               p.planes == 2 ? p.B_lo : nullptr, as, bs, a);
+    FCUDA_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace fcuda

@@ -1,0 +1,59 @@
+// TensorGEMM on tcgen05 — the B200 replacement for the reference's 64-way batched
+// "TensorGEMM" (/root/reference/src/booster/avx/winograd_kernels_F63.cpp:518-757) and for its
+// packed SGEMM (/root/reference/src/booster/avx/sgemm.cpp:377-433).
+//
+//   for g in [0,G):   D_g[M x N] = A_g[M x K] * B_g[N x K]^T        (fp32 in, fp32 out)
+//
+// Both operands are K-major ("TN").  The contraction runs on the 5th-gen tensor cores as
+// kind::tf32 UMMA with fp32 accumulation in TMEM.  fp32 semantics are recovered with the
+// 3xTF32 split: every operand is stored as a TF32-exact "hi" plane plus an fp32 remainder
+// "lo" plane (hi + lo == x exactly), and each k-step issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
+// PLANES == 1 runs plain TF32 (one MMA per k-step) on the hi planes only.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fcuda {
+
+enum GemmEpilogue : int {
+    // D[g][m][n], n contiguous, row stride = ldd floats, batch stride = M*ldd.
+    // Used for the Winograd product buffer M_e[tile][oc].
+    EPI_ROWMAJOR = 0,
+    // m = img * P + pix ;  out[(img * N + n) * P + pix] = act(acc + bias[n])      (NCHW conv output)
+    EPI_NCHW = 1,
+    // out[n * ldd + m] (+)= acc   — m = output feature, n = batch row (InnerProduct).
+    // With split_k > 1 partial sums are combined with fp32 atomics into a pre-initialised out.
+    EPI_COLMAJOR_ATOMIC = 2,
+};
+
+struct GemmProblem {
+    // operands (device pointers).  *_lo may be null when planes == 1.
+    const float* A_hi; const float* A_lo;   // [G][M][K]
+    const float* B_hi; const float* B_lo;   // [G][N][K]
+    float* D;
+    int M, N, K, G;
+    int planes;        // 1 = TF32, 2 = 3xTF32 (hi/lo split)
+    int epilogue;      // GemmEpilogue
+    int ldd;           // EPI_ROWMAJOR / EPI_COLMAJOR_ATOMIC leading dimension (floats)
+    int P;             // EPI_NCHW: pixels per image
+    const float* bias; // EPI_NCHW: per-n bias or null
+    int relu;          // EPI_NCHW: fuse max(0, .)
+    int split_k;       // >=1; only with EPI_COLMAJOR_ATOMIC
+    long long a_batch_stride;  // floats between consecutive g in A; 0 => dense (M*K)
+    long long b_batch_stride;  // floats between consecutive g in B; 0 => dense (N*K)
+};
+
+// Launches the persistent tcgen05 kernel on `stream`.  Returns 0 or a negative fcuda error.
+// Requirements: K % 4 == 0, 16-byte aligned operand pointers.  M/N/K tails are zero-filled by TMA.
+int tensor_gemm(const GemmProblem& p, cudaStream_t stream);
+
+// True when the problem satisfies the TMA alignment rules above.
+bool tensor_gemm_supported(const GemmProblem& p);
+
+// Reference CUDA-core fp32 GEMM with identical semantics (used by the self-test and as
+// the fallback for shapes TMA cannot describe).
+int simt_gemm(const GemmProblem& p, cudaStream_t stream);
+
+}  // namespace fcuda
