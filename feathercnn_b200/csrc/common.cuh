@@ -27,6 +27,11 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
 static inline size_t round_up_sz(size_t a, size_t b) { return ceil_div_sz(a, b) * b; }
 
+// Launch accounting for bench.py's gpu_launches (fcuda_launch_count).
+void count_launch(int n = 1);
+unsigned long long launch_count();
+void reset_launch_count();
+
 // Number of SMs of the current device (148 on B200); cached per process.
 int sm_count();
 

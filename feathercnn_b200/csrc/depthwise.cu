@@ -1,0 +1,146 @@
+// Depthwise convolution (group == channels).
+//
+// Replaces DEPTHWISE_Forward (/root/reference/src/booster/avx/booster.cpp:136-160) -> dwConv_template /
+// globalDwConv (avx/depthwise.cpp:161-207, 30-55) and the hand-unrolled NEON dwConvs1/dwConvs2
+// (arm/depthwise.cpp:166,803).  The op is HBM-bound (18 FLOP per 8 bytes): the 3x3 kernels keep a 3-row
+// sliding window in registers, read every input element once per warp with coalesced row loads and fetch
+// the horizontal neighbours with warp shuffles (only the two edge lanes issue an extra halo load).
+// Zero padding comes from the bounds checks — no padded copy (the reference's pad_input) is made.
+// Stride semantics are the geometric ones; the reference swaps stride_w/stride_h in its index
+// (depthwise.cpp:184), which is identical whenever stride_h == stride_w (all models in scope).
+#include "depthwise.cuh"
+#include "common.cuh"
+
+namespace fcuda {
+
+constexpr int kDwRows = 16;  // output rows marched by one warp
+
+template <int STRIDE>
+__global__ void __launch_bounds__(128)
+dw3x3_shuffle_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                     float* __restrict__ out, int C, int H, int W, int OH, int OW, int relu, long long items,
+                     int xstrips, int ystrips) {
+    const long long item = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+    if (item >= items) return;
+    const int lane = threadIdx.x & 31;
+    const int xs = static_cast<int>(item % xstrips);
+    const long long t = item / xstrips;
+    const int ys = static_cast<int>(t % ystrips);
+    const long long plane = t / ystrips;  // n * C + c
+    const int c = static_cast<int>(plane % C);
+    const float* ip = in + plane * H * W;
+    float* op = out + plane * OH * OW;
+
+    float k[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
+    const float bv = bias ? __ldg(bias + c) : 0.f;
+
+    const int ox = xs * 32 + lane;
+    const int oy0 = ys * kDwRows;
+    const int oy1 = min(oy0 + kDwRows, OH);
+
+    // returns the three horizontally adjacent inputs (left, centre, right) of this lane for input row iy
+    auto load_row = [&](int iy, float& l, float& m, float& r) {
+        const bool row_ok = iy >= 0 && iy < H;
+        const float* rp = ip + static_cast<long long>(iy) * W;
+        if (STRIDE == 1) {
+            const int ix = ox;  // centre column (pad_left == 1)
+            m = (row_ok && ix < W) ? __ldg(rp + ix) : 0.f;
+            l = __shfl_up_sync(0xffffffffu, m, 1);
+            r = __shfl_down_sync(0xffffffffu, m, 1);
+            if (lane == 0) l = (row_ok && ix - 1 >= 0 && ix - 1 < W) ? __ldg(rp + ix - 1) : 0.f;
+            if (lane == 31) r = (row_ok && ix + 1 < W) ? __ldg(rp + ix + 1) : 0.f;
+        } else {
+            const int ix = 2 * ox;  // centre column 2*ox - 1 + 1
+            m = (row_ok && ix < W) ? __ldg(rp + ix) : 0.f;
+            r = (row_ok && ix + 1 < W) ? __ldg(rp + ix + 1) : 0.f;
+            l = __shfl_up_sync(0xffffffffu, r, 1);
+            if (lane == 0) l = (row_ok && ix - 1 >= 0 && ix - 1 < W) ? __ldg(rp + ix - 1) : 0.f;
+        }
+    };
+
+    if (STRIDE == 1) {
+        float a0, a1, a2, b0, b1, b2, c0, c1, c2;
+        load_row(oy0 - 1, a0, a1, a2);
+        load_row(oy0, b0, b1, b2);
+        for (int oy = oy0; oy < oy1; ++oy) {
+            load_row(oy + 1, c0, c1, c2);
+            float v = bv;
+            v = fmaf(k[0], a0, v); v = fmaf(k[1], a1, v); v = fmaf(k[2], a2, v);
+            v = fmaf(k[3], b0, v); v = fmaf(k[4], b1, v); v = fmaf(k[5], b2, v);
+            v = fmaf(k[6], c0, v); v = fmaf(k[7], c1, v); v = fmaf(k[8], c2, v);
+            if (relu) v = fmaxf(v, 0.f);
+            if (ox < OW) op[static_cast<long long>(oy) * OW + ox] = v;
+            a0 = b0; a1 = b1; a2 = b2;
+            b0 = c0; b1 = c1; b2 = c2;
+        }
+    } else {
+        float a0, a1, a2, b0, b1, b2, c0, c1, c2;
+        load_row(2 * oy0 - 1, a0, a1, a2);
+        for (int oy = oy0; oy < oy1; ++oy) {
+            load_row(2 * oy, b0, b1, b2);
+            load_row(2 * oy + 1, c0, c1, c2);
+            float v = bv;
+            v = fmaf(k[0], a0, v); v = fmaf(k[1], a1, v); v = fmaf(k[2], a2, v);
+            v = fmaf(k[3], b0, v); v = fmaf(k[4], b1, v); v = fmaf(k[5], b2, v);
+            v = fmaf(k[6], c0, v); v = fmaf(k[7], c1, v); v = fmaf(k[8], c2, v);
+            if (relu) v = fmaxf(v, 0.f);
+            if (ox < OW) op[static_cast<long long>(oy) * OW + ox] = v;
+            a0 = c0; a1 = c1; a2 = c2;
+        }
+    }
+}
+
+// Generic k x k / any stride / any padding depthwise: one thread per output element.
+__global__ void __launch_bounds__(256)
+dw_generic_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ out, DwGeom g, int relu, long long total) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ox = static_cast<int>(idx % g.OW);
+    long long t = idx / g.OW;
+    const int oy = static_cast<int>(t % g.OH);
+    const long long plane = t / g.OH;
+    const int c = static_cast<int>(plane % g.C);
+    const float* ip = in + plane * g.H * g.W;
+    const float* kp = w + static_cast<size_t>(c) * g.KH * g.KW;
+    float v = 0.f;
+    for (int u = 0; u < g.KH; ++u) {
+        const int iy = oy * g.stride_h - g.pad_top + u;
+        if (iy < 0 || iy >= g.H) continue;
+        for (int x = 0; x < g.KW; ++x) {
+            const int ix = ox * g.stride_w - g.pad_left + x;
+            if (ix < 0 || ix >= g.W) continue;
+            v = fmaf(__ldg(ip + static_cast<long long>(iy) * g.W + ix), __ldg(kp + u * g.KW + x), v);
+        }
+    }
+    if (bias) v += __ldg(bias + c);
+    if (relu) v = fmaxf(v, 0.f);
+    out[idx] = v;
+}
+
+int depthwise_forward(const float* in, const float* w, const float* bias, float* out, const DwGeom& g, int relu,
+                      int batch, cudaStream_t s) {
+    const bool k3 = g.KH == 3 && g.KW == 3 && g.pad_top == 1 && g.pad_left == 1 && g.stride_h == g.stride_w &&
+                    (g.stride_h == 1 || g.stride_h == 2) && g.OW >= 24;
+    if (k3) {
+        const int xstrips = ceil_div(g.OW, 32), ystrips = ceil_div(g.OH, kDwRows);
+        const long long items = static_cast<long long>(batch) * g.C * xstrips * ystrips;
+        const unsigned blocks = static_cast<unsigned>((items + 3) / 4);
+        if (g.stride_h == 1)
+            dw3x3_shuffle_kernel<1><<<blocks, 128, 0, s>>>(in, w, bias, out, g.C, g.H, g.W, g.OH, g.OW, relu, items,
+                                                            xstrips, ystrips);
+        else
+            dw3x3_shuffle_kernel<2><<<blocks, 128, 0, s>>>(in, w, bias, out, g.C, g.H, g.W, g.OH, g.OW, relu, items,
+                                                            xstrips, ystrips);
+    } else {
+        const long long total = static_cast<long long>(batch) * g.C * g.OH * g.OW;
+        dw_generic_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, w, bias, out, g, relu, total);
+    }
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+}  // namespace fcuda

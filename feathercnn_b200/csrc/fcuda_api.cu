@@ -1,0 +1,484 @@
+// extern "C" surface of libfcuda.so (include/fcuda.h): algorithm selection, workspace planning and the
+// per-layer dispatch that stands where booster::ConvBooster's function table stood
+// (/root/reference/src/booster/avx/booster.cpp:283-355).
+#include "fcuda.h"
+
+#include "common.cuh"
+#include "conv_direct.cuh"
+#include "depthwise.cuh"
+#include "layers.cuh"
+#include "pack.cuh"
+#include "tensor_gemm.cuh"
+#include "winograd.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+using namespace fcuda;
+
+namespace {
+
+int env_precision() {
+    const char* e = getenv("FCUDA_PRECISION");
+    if (e && (!strcmp(e, "tf32") || !strcmp(e, "TF32") || !strcmp(e, "1"))) return FCUDA_PRECISION_TF32;
+    return FCUDA_PRECISION_TF32X3;
+}
+size_t env_chunk() {
+    const char* e = getenv("FCUDA_L2_CHUNK_MB");
+    if (e) return static_cast<size_t>(atof(e) * 1024.0 * 1024.0);
+    return static_cast<size_t>(48) << 20;
+}
+
+int g_precision = env_precision();
+size_t g_l2_chunk = env_chunk();
+
+inline int planes() { return g_precision == FCUDA_PRECISION_TF32X3 ? 2 : 1; }
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+struct ConvPlan {
+    int algo = -1;
+    int np = 1;  // operand planes (1 = TF32, 2 = 3xTF32)
+    // Winograd
+    int tile = 0, TT = 0;
+    WinoGeom wg{};
+    int total_tile_rows = 0, rows_per_chunk = 0;
+    size_t Tc_max = 0;
+    // im2col / direct
+    PackGeom pg{};
+    long long total_pixels = 0;
+    int pixels_per_chunk = 0;
+    bool im2col_tc = false;  // false => fall back to the CUDA-core direct kernel
+    // depthwise
+    DwGeom dg{};
+    size_t scratch_floats = 0, packed_floats = 0;
+};
+
+PackGeom pack_geom(const FcudaConvParam* p) {
+    PackGeom g;
+    g.IC = p->input_channels; g.H = p->input_h; g.W = p->input_w;
+    g.KH = p->kernel_h; g.KW = p->kernel_w; g.OH = p->output_h; g.OW = p->output_w;
+    g.stride_h = p->stride_h; g.stride_w = p->stride_w; g.pad_top = p->pad_top; g.pad_left = p->pad_left;
+    g.K = p->input_channels * p->kernel_h * p->kernel_w;
+    g.Kp = (g.K + 3) & ~3;
+    return g;
+}
+
+int make_plan(const FcudaConvParam* p, int algo, int batch, ConvPlan* plan) {
+    if (!p || batch < 1) return -100;
+    if (p->output_channels <= 0 || p->input_channels <= 0 || p->input_h <= 0 || p->input_w <= 0 ||
+        p->kernel_h <= 0 || p->kernel_w <= 0 || p->stride_h <= 0 || p->stride_w <= 0 || p->output_h <= 0 ||
+        p->output_w <= 0)
+        return -100;
+    ConvPlan& pl = *plan;
+    pl.algo = algo;
+    pl.np = planes();
+    const int IC = p->input_channels, OC = p->output_channels;
+    switch (algo) {
+        case FCUDA_WINOGRADF63:
+        case FCUDA_WINOGRADF23: {
+            if (p->group != 1 || p->kernel_h != 3 || p->kernel_w != 3 || p->stride_h != 1 || p->stride_w != 1) return -1;
+            if (IC % 4 != 0) return -1;  // TMA needs 16-byte rows (the reference's rule is IC%4 && OC%4 too)
+            pl.tile = algo == FCUDA_WINOGRADF63 ? 8 : 4;
+            pl.TT = pl.tile * pl.tile;
+            const int ot = pl.tile - 2;
+            WinoGeom& g = pl.wg;
+            g.C_in = IC; g.C_out = OC; g.H = p->input_h; g.W = p->input_w; g.OH = p->output_h; g.OW = p->output_w;
+            g.pad_top = p->pad_top; g.pad_left = p->pad_left;
+            g.tilesX = ceil_div(g.OW, ot);  // == (Wp + 3) / 6 for F(6,3), winograd_kernels_F63.cpp:2320
+            g.tilesY = ceil_div(g.OH, ot);
+            pl.total_tile_rows = batch * g.tilesY;
+            const size_t bytes_per_row = static_cast<size_t>(g.tilesX) * pl.TT * (static_cast<size_t>(pl.np) * IC + OC) * 4;
+            const size_t u_bytes = static_cast<size_t>(pl.np) * pl.TT * IC * OC * 4;
+            size_t budget = g_l2_chunk;
+            if (budget && budget < 2 * u_bytes) budget = 2 * u_bytes;  // do not re-stream U more than the data it multiplies
+            long long rows = budget ? static_cast<long long>(budget / bytes_per_row) : pl.total_tile_rows;
+            if (rows < 1) rows = 1;
+            if (rows > pl.total_tile_rows) rows = pl.total_tile_rows;
+            const int nchunks = ceil_div(pl.total_tile_rows, static_cast<int>(rows));
+            pl.rows_per_chunk = ceil_div(pl.total_tile_rows, nchunks);
+            pl.Tc_max = static_cast<size_t>(pl.rows_per_chunk) * g.tilesX;
+            if (pl.Tc_max > 0x7fffffffULL / 64) return -100;
+            pl.scratch_floats = pl.TT * pl.Tc_max * (static_cast<size_t>(pl.np) * IC + OC);
+            pl.packed_floats = static_cast<size_t>(pl.np) * pl.TT * IC * OC;
+            return 0;
+        }
+        case FCUDA_IM2COL:
+        case FCUDA_NAIVE: {
+            if (p->group != 1) return -1;
+            pl.pg = pack_geom(p);
+            pl.total_pixels = static_cast<long long>(batch) * p->output_h * p->output_w;
+            if (algo == FCUDA_NAIVE) {
+                pl.scratch_floats = 0;
+                pl.packed_floats = static_cast<size_t>(OC) * pl.pg.K;
+                return 0;
+            }
+            pl.im2col_tc = true;
+            const size_t bytes_per_pixel = static_cast<size_t>(pl.np) * pl.pg.Kp * 4;
+            long long pix = g_l2_chunk ? static_cast<long long>(g_l2_chunk / bytes_per_pixel) : pl.total_pixels;
+            pix = pix / 128 * 128;
+            if (pix < 128) pix = 128;
+            if (pix > pl.total_pixels) pix = pl.total_pixels;
+            if (pix > 0x7fffff00LL) pix = 0x7fffff00LL;
+            const long long nchunks = (pl.total_pixels + pix - 1) / pix;
+            pix = ((pl.total_pixels + nchunks - 1) / nchunks + 127) / 128 * 128;
+            pl.pixels_per_chunk = static_cast<int>(pix);
+            pl.scratch_floats = static_cast<size_t>(pl.np) * pix * pl.pg.Kp;
+            pl.packed_floats = static_cast<size_t>(pl.np) * OC * pl.pg.Kp;
+            return 0;
+        }
+        case FCUDA_DEPTHWISE: {
+            if (p->group != IC || OC != IC) return -1;
+            DwGeom& g = pl.dg;
+            g.C = IC; g.H = p->input_h; g.W = p->input_w; g.KH = p->kernel_h; g.KW = p->kernel_w;
+            g.OH = p->output_h; g.OW = p->output_w; g.stride_h = p->stride_h; g.stride_w = p->stride_w;
+            g.pad_top = p->pad_top; g.pad_left = p->pad_left;
+            pl.scratch_floats = 0;
+            pl.packed_floats = static_cast<size_t>(IC) * p->kernel_h * p->kernel_w;
+            return 0;
+        }
+        default:
+            // SGECONV / WINOGRADF63FUSED: stubs or unselected in the reference's AVX dispatcher
+            // (avx/booster.cpp:105-118, 291-292); "This algo is not supported" => -1 (booster.cpp:349-353).
+            return -1;
+    }
+}
+
+// Stage a possibly-host pointer on the device.  Returns the device pointer to use and, when a temporary
+// was allocated, stores it in *tmp (caller frees after the consuming kernels are enqueued + synchronised).
+int stage_to_device(const float* src, size_t n, const float** dev, float** tmp, cudaStream_t s) {
+    *tmp = nullptr;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, src);
+    if (e == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+        *dev = src;
+        return 0;
+    }
+    cudaGetLastError();
+    FCUDA_CHECK(cudaMalloc(tmp, n * sizeof(float)));
+    FCUDA_CHECK(cudaMemcpyAsync(*tmp, src, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    *dev = *tmp;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fcuda_set_precision(int precision) {
+    if (precision != FCUDA_PRECISION_TF32X3 && precision != FCUDA_PRECISION_TF32) return -200;
+    g_precision = precision;
+    return 0;
+}
+int fcuda_get_precision(void) { return g_precision; }
+int fcuda_set_l2_chunk_bytes(size_t bytes) { g_l2_chunk = bytes; return 0; }
+size_t fcuda_get_l2_chunk_bytes(void) { return g_l2_chunk; }
+
+int fcuda_conv_assign_output_dim(FcudaConvParam* p) {
+    if (!p) return -100;
+    if (p->group == 0) p->group = 1;
+    if (p->stride_h == 0) p->stride_h = 1;
+    if (p->stride_w == 0) p->stride_w = 1;
+    p->output_h = (p->input_h + p->pad_top + p->pad_bottom - p->kernel_h) / p->stride_h + 1;
+    p->output_w = (p->input_w + p->pad_left + p->pad_right - p->kernel_w) / p->stride_w + 1;
+    if (p->group == p->input_channels) p->output_channels = p->input_channels;
+    return 0;
+}
+
+int fcuda_conv_select_algo(const FcudaConvParam* p, int* algo) {
+    if (!p || !algo) return -100;
+    if (p->group == p->input_channels) {
+        *algo = FCUDA_DEPTHWISE;
+    } else if (p->group == 1 && p->kernel_h == 3 && p->kernel_w == 3 && p->stride_h == 1 && p->stride_w == 1 &&
+               p->input_h > 8 && p->input_w > 8 && p->output_channels % 4 == 0 && p->input_channels % 4 == 0) {
+        *algo = FCUDA_WINOGRADF63;
+    } else if (p->group == 1) {
+        *algo = FCUDA_IM2COL;
+    } else {
+        *algo = -1;
+        return -1;  // partial group conv, avx/booster.cpp:304-308
+    }
+    return 0;
+}
+
+int fcuda_conv_get_buffer_size(const FcudaConvParam* p, int algo, int batch, size_t* scratch_floats,
+                               size_t* packed_kernel_floats) {
+    ConvPlan pl;
+    const int rc = make_plan(p, algo, batch, &pl);
+    if (rc) return rc;
+    if (scratch_floats) *scratch_floats = pl.scratch_floats;
+    if (packed_kernel_floats) *packed_kernel_floats = pl.packed_floats;
+    return 0;
+}
+
+int fcuda_conv_init(const FcudaConvParam* p, int algo, float* packed, const float* raw, void* stream) {
+    ConvPlan pl;
+    int rc = make_plan(p, algo, 1, &pl);
+    if (rc) return rc;
+    if (!packed || !raw) return -100;
+    cudaStream_t s = as_stream(stream);
+    const int IC = p->input_channels, OC = p->output_channels;
+    const size_t raw_n = algo == FCUDA_DEPTHWISE ? static_cast<size_t>(IC) * p->kernel_h * p->kernel_w
+                                                 : static_cast<size_t>(OC) * IC * p->kernel_h * p->kernel_w;
+    const float* d_raw;
+    float* tmp;
+    if ((rc = stage_to_device(raw, raw_n, &d_raw, &tmp, s))) return rc;
+    switch (algo) {
+        case FCUDA_WINOGRADF63:
+        case FCUDA_WINOGRADF23: {
+            const size_t plane = static_cast<size_t>(pl.TT) * IC * OC;
+            rc = wino_filter_transform(pl.tile, d_raw, packed, pl.np == 2 ? packed + plane : nullptr, OC, IC, s);
+            break;
+        }
+        case FCUDA_IM2COL: {
+            const size_t plane = static_cast<size_t>(OC) * pl.pg.Kp;
+            rc = pack_weights(d_raw, packed, pl.np == 2 ? packed + plane : nullptr, OC, pl.pg.K, pl.pg.Kp, s);
+            break;
+        }
+        case FCUDA_NAIVE:
+        case FCUDA_DEPTHWISE:
+            if (cudaMemcpyAsync(packed, d_raw, raw_n * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+                rc = FCUDA_ERR_CUDA;
+            break;
+        default:
+            rc = -1;
+    }
+    if (tmp) {
+        cudaStreamSynchronize(s);
+        cudaFree(tmp);
+    }
+    return rc;
+}
+
+int fcuda_conv_forward(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
+                       float* scratch, const float* bias, int batch, void* stream) {
+    ConvPlan pl;
+    int rc = make_plan(p, algo, batch, &pl);
+    if (rc) return rc;
+    if (!output || !input || !packed) return -100;
+    if (pl.scratch_floats && !scratch) return -100;
+    cudaStream_t s = as_stream(stream);
+    const int IC = p->input_channels, OC = p->output_channels;
+    const float* b = p->bias_term ? bias : nullptr;
+    const int relu = p->activation == FCUDA_ACT_RELU;
+    switch (algo) {
+        case FCUDA_WINOGRADF63:
+        case FCUDA_WINOGRADF23: {
+            const size_t v_plane = static_cast<size_t>(pl.TT) * pl.Tc_max * IC;
+            const size_t u_plane = static_cast<size_t>(pl.TT) * IC * OC;
+            float* V_hi = scratch;
+            float* V_lo = pl.np == 2 ? scratch + v_plane : nullptr;
+            float* Mbuf = scratch + static_cast<size_t>(pl.np) * v_plane;
+            for (int R0 = 0; R0 < pl.total_tile_rows; R0 += pl.rows_per_chunk) {
+                const int R1 = R0 + pl.rows_per_chunk < pl.total_tile_rows ? R0 + pl.rows_per_chunk : pl.total_tile_rows;
+                const int Tc = (R1 - R0) * pl.wg.tilesX;
+                if ((rc = wino_input_transform(pl.tile, input, V_hi, V_lo, pl.wg, R0, R1, s))) return rc;
+                GemmProblem g{};
+                g.A_hi = V_hi; g.A_lo = V_lo;
+                g.B_hi = packed; g.B_lo = pl.np == 2 ? packed + u_plane : nullptr;
+                g.D = Mbuf;
+                g.M = Tc; g.N = OC; g.K = IC; g.G = pl.TT;
+                g.planes = pl.np; g.epilogue = EPI_ROWMAJOR; g.ldd = OC; g.split_k = 1;
+                // algorithmic (direct-conv, booster.h:145-148) FLOPs of the output rows this chunk covers
+                g.algo_flops = 2.0 * OC * IC * 9.0 * p->output_h * p->output_w * batch *
+                               (static_cast<double>(R1 - R0) / pl.total_tile_rows);
+                if ((rc = tensor_gemm(g, s))) return rc;
+                if ((rc = wino_output_transform(pl.tile, Mbuf, output, b, pl.wg, R0, R1, relu, s))) return rc;
+            }
+            return 0;
+        }
+        case FCUDA_IM2COL: {
+            const size_t p_plane = static_cast<size_t>(pl.pixels_per_chunk) * pl.pg.Kp;
+            const size_t w_plane = static_cast<size_t>(OC) * pl.pg.Kp;
+            float* P_hi = scratch;
+            float* P_lo = pl.np == 2 ? scratch + p_plane : nullptr;
+            for (long long m0 = 0; m0 < pl.total_pixels; m0 += pl.pixels_per_chunk) {
+                const int rows = static_cast<int>(m0 + pl.pixels_per_chunk < pl.total_pixels ? pl.pixels_per_chunk
+                                                                                               : pl.total_pixels - m0);
+                if ((rc = im2col_pack(input, P_hi, P_lo, pl.pg, m0, rows, s))) return rc;
+                GemmProblem g{};
+                g.A_hi = P_hi; g.A_lo = P_lo;
+                g.B_hi = packed; g.B_lo = pl.np == 2 ? packed + w_plane : nullptr;
+                g.D = output;
+                g.M = rows; g.N = OC; g.K = pl.pg.Kp; g.G = 1;
+                g.planes = pl.np; g.epilogue = EPI_NCHW; g.P = p->output_h * p->output_w; g.m_offset = m0;
+                g.bias = b; g.relu = relu; g.split_k = 1;
+                g.algo_flops = 2.0 * OC * pl.pg.K * static_cast<double>(rows);
+                if ((rc = tensor_gemm(g, s))) return rc;
+            }
+            return 0;
+        }
+        case FCUDA_NAIVE:
+            return conv_direct(input, packed, b, output, pl.pg, OC, relu, batch, s);
+        case FCUDA_DEPTHWISE:
+            return depthwise_forward(input, packed, b, output, pl.dg, relu, batch, s);
+        default:
+            return -1;
+    }
+}
+
+int fcuda_tensor_gemm(float* d, const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int m,
+                      int n, int k, int g, void* stream) {
+    GemmProblem p{};
+    p.A_hi = a_hi; p.A_lo = a_lo; p.B_hi = b_hi; p.B_lo = b_lo; p.D = d;
+    p.M = m; p.N = n; p.K = k; p.G = g;
+    p.planes = (a_lo && b_lo) ? 2 : 1;
+    p.epilogue = EPI_ROWMAJOR; p.ldd = n; p.split_k = 1;
+    return tensor_gemm(p, as_stream(stream));
+}
+
+int fcuda_split_tf32(float* hi, float* lo, const float* x, size_t n, void* stream) {
+    return split_tf32_planes(x, hi, lo, n, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// InnerProduct
+// ---------------------------------------------------------------------------------------------
+static bool fc_tensor_path(int input_size) { return input_size % 4 == 0; }
+
+int fcuda_inner_product_get_buffer_size(int input_size, int output_size, int batch, size_t* scratch_floats,
+                                        size_t* packed_kernel_floats) {
+    if (input_size <= 0 || output_size <= 0 || batch < 1) return -100;
+    const int np = fc_tensor_path(input_size) ? planes() : 1;
+    if (packed_kernel_floats) *packed_kernel_floats = static_cast<size_t>(np) * output_size * input_size;
+    if (scratch_floats) *scratch_floats = np == 2 ? 2 * static_cast<size_t>(batch) * input_size : 0;
+    return 0;
+}
+
+int fcuda_inner_product_init(int input_size, int output_size, float* packed, const float* raw, void* stream) {
+    if (input_size <= 0 || output_size <= 0 || !packed || !raw) return -100;
+    cudaStream_t s = as_stream(stream);
+    const size_t n = static_cast<size_t>(output_size) * input_size;
+    const float* d_raw;
+    float* tmp;
+    int rc = stage_to_device(raw, n, &d_raw, &tmp, s);
+    if (rc) return rc;
+    const int np = fc_tensor_path(input_size) ? planes() : 1;
+    if (np == 2) {
+        rc = split_tf32_planes(d_raw, packed, packed + n, n, s);
+    } else if (cudaMemcpyAsync(packed, d_raw, n * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+        rc = FCUDA_ERR_CUDA;
+    }
+    if (tmp) {
+        cudaStreamSynchronize(s);
+        cudaFree(tmp);
+    }
+    return rc;
+}
+
+int fcuda_inner_product_forward(int input_size, int output_size, float* output, const float* input,
+                                const float* packed, const float* bias, float* scratch, int relu, int batch,
+                                void* stream) {
+    if (input_size <= 0 || output_size <= 0 || batch < 1 || !output || !input || !packed) return -100;
+    cudaStream_t s = as_stream(stream);
+    const bool tc = fc_tensor_path(input_size);
+    const int np = tc ? planes() : 1;
+    if (np == 2 && !scratch) return -100;
+    const size_t wn = static_cast<size_t>(output_size) * input_size;
+    const size_t xn = static_cast<size_t>(batch) * input_size;
+    int rc = fill_rows(output, bias, output_size, batch, s);  // out[b][o] = bias[o]; the GEMM accumulates on top
+    if (rc) return rc;
+    GemmProblem g{};
+    g.A_hi = packed; g.A_lo = np == 2 ? packed + wn : nullptr;  // A = W (out x in): output features on the 128-row M side
+    g.B_hi = input; g.B_lo = nullptr;                           // B = X (batch x in)
+    if (np == 2) {
+        if ((rc = split_tf32_planes(input, scratch, scratch + xn, xn, s))) return rc;
+        g.B_hi = scratch; g.B_lo = scratch + xn;
+    }
+    g.D = output;
+    g.M = output_size; g.N = batch; g.K = input_size; g.G = 1;
+    g.planes = np; g.epilogue = EPI_COLMAJOR_ATOMIC; g.ldd = output_size;
+    // weight streaming is HBM-bound: split K until there are ~2 CTAs per SM
+    const int num_m = ceil_div(output_size, 128) * ceil_div(batch, 128);
+    int split = ceil_div(2 * sm_count(), num_m);
+    const int kb = ceil_div(input_size, 32);
+    if (split > kb / 8) split = kb / 8;
+    if (split > 64) split = 64;
+    if (split < 1) split = 1;
+    g.split_k = split;
+    g.algo_flops = 2.0 * output_size * static_cast<double>(input_size) * batch;
+    if (tc && tensor_gemm_supported(g)) rc = tensor_gemm(g, s);
+    else { g.split_k = 1; rc = simt_gemm(g, s); count_launch(); }
+    if (rc) return rc;
+    if (relu) rc = scale_relu(output, output, static_cast<size_t>(batch) * output_size, 1.f, 1, s);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Remaining layers
+// ---------------------------------------------------------------------------------------------
+int fcuda_pooling_out_dim(int in, int pad_a, int pad_b, int kernel, int stride) {
+    // pooling_layer.h:129-130
+    return static_cast<int>(ceilf(static_cast<float>(in + pad_a + pad_b - kernel) / static_cast<float>(stride))) + 1;
+}
+
+int fcuda_pooling_forward(float* output, const float* input, int channels, int in_h, int in_w, int type, int kernel_h,
+                          int kernel_w, int stride_h, int stride_w, int pad_left, int pad_right, int pad_top,
+                          int pad_bottom, int global_pooling, int batch, void* stream) {
+    if (!output || !input || channels <= 0 || in_h <= 0 || in_w <= 0 || batch < 1) return -100;
+    PoolGeom g;
+    g.H = in_h; g.W = in_w; g.type = type;
+    g.stride_h = stride_h > 0 ? stride_h : 1; g.stride_w = stride_w > 0 ? stride_w : 1;
+    g.pad_left = pad_left; g.pad_right = pad_right; g.pad_top = pad_top; g.pad_bottom = pad_bottom;
+    if (global_pooling) {  // pooling_layer.h:114-121
+        g.KH = in_h; g.KW = in_w; g.OH = 1; g.OW = 1;
+    } else {
+        if (kernel_h <= 0 || kernel_w <= 0) return -100;
+        g.KH = kernel_h; g.KW = kernel_w;
+        g.OH = fcuda_pooling_out_dim(in_h, pad_top, pad_bottom, kernel_h, g.stride_h);
+        g.OW = fcuda_pooling_out_dim(in_w, pad_left, pad_right, kernel_w, g.stride_w);
+    }
+    return pooling_forward(input, output, g, channels, batch, as_stream(stream));
+}
+
+int fcuda_batchnorm_forward(float* output, const float* input, int channels, size_t stride, const float* alpha,
+                            const float* beta, const float* scale, const float* scale_bias, int relu, int batch,
+                            void* stream) {
+    if (!output || !input || !alpha || !beta || channels <= 0) return -100;
+    return channel_affine(input, output, channels, stride, beta, alpha, scale, scale_bias, relu, batch, as_stream(stream));
+}
+
+int fcuda_scale_forward(float* output, const float* input, int channels, size_t stride, const float* scale,
+                        const float* bias, int batch, void* stream) {
+    if (!output || !input || !scale || channels <= 0) return -100;
+    return channel_affine(input, output, channels, stride, scale, bias, nullptr, nullptr, 0, batch, as_stream(stream));
+}
+
+int fcuda_eltwise_add_forward(float* output, const float* a, const float* b, size_t n, int relu, void* stream) {
+    if (!output || !a || !b) return -100;
+    return add_relu(a, b, output, n, relu, as_stream(stream));
+}
+
+int fcuda_relu_forward(float* output, const float* input, size_t n, void* stream) {
+    if (!output || !input) return -100;
+    return scale_relu(input, output, n, 1.f, 1, as_stream(stream));
+}
+
+int fcuda_softmax_forward(float* output, const float* input, size_t n_per_image, int batch, void* stream) {
+    if (!output || !input || batch < 1) return -100;
+    return softmax_forward(input, output, n_per_image, batch, as_stream(stream));
+}
+
+int fcuda_dropout_forward(float* output, const float* input, size_t n, float scale, void* stream) {
+    if (!output || !input) return -100;
+    return scale_relu(input, output, n, scale, 0, as_stream(stream));
+}
+
+int fcuda_copy_channels(float* dst, int dst_channels, int dst_channel_offset, const float* src, int channels,
+                        size_t stride, int batch, void* stream) {
+    if (!dst || !src || channels <= 0 || dst_channel_offset < 0 || dst_channel_offset + channels > dst_channels)
+        return -100;
+    return copy_channels(src, dst, static_cast<size_t>(channels) * stride, static_cast<size_t>(dst_channels) * stride,
+                         static_cast<size_t>(dst_channel_offset) * stride, batch, as_stream(stream));
+}
+
+void fcuda_profile_tensor_gemm(int enable) { gemm_profile_enable(enable != 0); }
+int fcuda_profile_collect(double* total_ms, double* algo_flops, double* mma_flops, long long* launches) {
+    gemm_profile_collect(total_ms, algo_flops, mma_flops, launches);
+    return 0;
+}
+
+unsigned long long fcuda_launch_count(void) { return launch_count(); }
+void fcuda_reset_launch_count(void) { reset_launch_count(); }
+
+}  // extern "C"

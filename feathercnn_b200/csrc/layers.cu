@@ -1,0 +1,258 @@
+// Bandwidth-bound layer kernels: pooling, BN/Scale, eltwise add, ReLU, softmax, dropout, channel copies.
+// Each replaces an inline CPU loop of the reference (citations at each kernel).  All are single-pass,
+// coalesced along the innermost (W / flattened) dimension; grid-stride loops sized from the SM count.
+#include "layers.cuh"
+#include "common.cuh"
+
+#include <float.h>
+
+namespace fcuda {
+
+static inline unsigned grid_for(size_t n, int block) {
+    size_t blocks = ceil_div_sz(n, block);
+    const size_t cap = static_cast<size_t>(sm_count()) * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return static_cast<unsigned>(blocks);
+}
+
+// PoolingLayer::Forward, /root/reference/src/layers/pooling_layer.h:38-91.  Window start subtracts BOTH pads
+// of an axis (:56, :67) — reproduced as is; max pooling starts from -FLT_MAX (:53), average divides by the
+// number of in-bounds elements (:84).
+__global__ void __launch_bounds__(256)
+pooling_kernel(const float* __restrict__ in, float* __restrict__ out, PoolGeom g, size_t total) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int ox = static_cast<int>(idx % g.OW);
+        size_t t = idx / g.OW;
+        const int oy = static_cast<int>(t % g.OH);
+        const size_t plane = t / g.OH;
+        const float* ip = in + plane * g.H * g.W;
+        const int ys = oy * g.stride_h - g.pad_top - g.pad_bottom;
+        const int xs = ox * g.stride_w - g.pad_left - g.pad_right;
+        const int y0 = max(ys, 0), y1 = min(ys + g.KH, g.H);
+        const int x0 = max(xs, 0), x1 = min(xs + g.KW, g.W);
+        if (g.type == 0) {
+            float m = -FLT_MAX;
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) m = fmaxf(m, __ldg(ip + static_cast<size_t>(y) * g.W + x));
+            out[idx] = m;
+        } else {
+            float s = 0.f;
+            int cnt = 0;
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) { s += __ldg(ip + static_cast<size_t>(y) * g.W + x); ++cnt; }
+            out[idx] = s / static_cast<float>(cnt);
+        }
+    }
+}
+
+// Global average / max pooling (kernel == whole plane): one warp per plane, shuffle reduction.
+__global__ void __launch_bounds__(256)
+global_pool_kernel(const float* __restrict__ in, float* __restrict__ out, int HW, int type, size_t planes) {
+    const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= planes) return;
+    const float* ip = in + warp * HW;
+    float acc = type == 0 ? -FLT_MAX : 0.f;
+    for (int i = lane; i < HW; i += 32) {
+        const float v = __ldg(ip + i);
+        acc = type == 0 ? fmaxf(acc, v) : acc + v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float other = __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = type == 0 ? fmaxf(acc, other) : acc + other;
+    }
+    if (lane == 0) out[warp] = type == 0 ? acc : acc / static_cast<float>(HW);
+}
+
+// booster::batchnorm<has_bias, has_scale, has_relu>, avx/generic_kernels.cpp:237-279 and
+// booster::scale<has_bias>, :203-233, as one per-channel affine kernel:  y = act((a*x + b) * s + t).
+__global__ void __launch_bounds__(256)
+channel_affine_kernel(const float* __restrict__ in, float* __restrict__ out, int channels, size_t hw,
+                      const float* __restrict__ mul, const float* __restrict__ add, const float* __restrict__ mul2,
+                      const float* __restrict__ add2, int relu, size_t total) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int c = static_cast<int>((idx / hw) % channels);
+        float v = in[idx];
+        v = mul ? fmaf(__ldg(mul + c), v, add ? __ldg(add + c) : 0.f) : (add ? v + __ldg(add + c) : v);
+        if (mul2) v *= __ldg(mul2 + c);
+        if (add2) v += __ldg(add2 + c);
+        if (relu) v = fmaxf(v, 0.f);
+        out[idx] = v;
+    }
+}
+
+// booster::add_relu<fuse_relu>, avx/generic_kernels.cpp:138-169.
+__global__ void __launch_bounds__(256)
+add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n, int relu) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t n4 = n >> 2;
+    const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (vec) {
+        for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+            float4 r = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+            if (relu) r = make_float4(fmaxf(r.x, 0.f), fmaxf(r.y, 0.f), fmaxf(r.z, 0.f), fmaxf(r.w, 0.f));
+            reinterpret_cast<float4*>(out)[i] = r;
+        }
+        for (size_t i = (n4 << 2) + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const float r = a[i] + b[i];
+            out[i] = relu ? fmaxf(r, 0.f) : r;
+        }
+    } else {
+        for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const float r = a[i] + b[i];
+            out[i] = relu ? fmaxf(r, 0.f) : r;
+        }
+    }
+}
+
+// ReluLayer::Forward (relu_layer.h:29-41) and DropoutLayer::Forward (dropout_layer.h:36-57): y = act(x * scale).
+__global__ void __launch_bounds__(256)
+scale_relu_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, float scale, int relu) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t n4 = n >> 2;
+    const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const size_t nv = vec ? n4 : 0;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        float4 x = reinterpret_cast<const float4*>(in)[i];
+        if (scale != 1.f) x = make_float4(x.x * scale, x.y * scale, x.z * scale, x.w * scale);
+        if (relu) x = make_float4(x.x > 0 ? x.x : 0.f, x.y > 0 ? x.y : 0.f, x.z > 0 ? x.z : 0.f, x.w > 0 ? x.w : 0.f);
+        reinterpret_cast<float4*>(out)[i] = x;
+    }
+    for (size_t i = (nv << 2) + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float x = in[i];
+        if (scale != 1.f) x *= scale;
+        if (relu) x = x > 0 ? x : 0.f;
+        out[i] = x;
+    }
+}
+
+// SoftmaxLayer::Forward, softmax_layer.h:32-55: max-subtracted softmax over the whole blob of one image.
+// One block per image.
+__global__ void __launch_bounds__(256)
+softmax_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
+    __shared__ float red[8];
+    __shared__ float bcast;
+    const float* ip = in + static_cast<size_t>(blockIdx.x) * n;
+    float* op = out + static_cast<size_t>(blockIdx.x) * n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float m = -FLT_MAX;
+    for (size_t i = threadIdx.x; i < n; i += 256) m = fmaxf(m, ip[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = red[0];
+        for (int i = 1; i < 8; ++i) r = fmaxf(r, red[i]);
+        bcast = r;
+    }
+    __syncthreads();
+    m = bcast;
+    float s = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += 256) {
+        const float e = expf(ip[i] - m);
+        op[i] = e;
+        s += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = 0.f;
+        for (int i = 0; i < 8; ++i) r += red[i];
+        bcast = r;
+    }
+    __syncthreads();
+    s = bcast;
+    for (size_t i = threadIdx.x; i < n; i += 256) op[i] = op[i] / s;
+}
+
+// ConcatLayer::Forward (concat_layer.h:37-47) / SplitLayer::Forward (split_layer.h:43-53) per image.
+__global__ void __launch_bounds__(256)
+copy_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t per_image, size_t dst_image,
+                     size_t dst_offset, size_t total) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const size_t n = idx / per_image, r = idx - n * per_image;
+        dst[n * dst_image + dst_offset + r] = src[idx];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fill_rows_kernel(float* __restrict__ out, const float* __restrict__ row, int row_len, size_t total) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride)
+        out[idx] = row ? __ldg(row + idx % row_len) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+int pooling_forward(const float* in, float* out, const PoolGeom& g, int channels, int batch, cudaStream_t s) {
+    const size_t planes = static_cast<size_t>(batch) * channels;
+    if (g.OH == 1 && g.OW == 1 && g.KH >= g.H && g.KW >= g.W && g.pad_top + g.pad_bottom == 0 &&
+        g.pad_left + g.pad_right == 0) {
+        global_pool_kernel<<<static_cast<unsigned>(ceil_div_sz(planes * 32, 256)), 256, 0, s>>>(in, out, g.H * g.W,
+                                                                                              g.type, planes);
+    } else {
+        const size_t total = planes * g.OH * g.OW;
+        pooling_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, g, total);
+    }
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+int channel_affine(const float* in, float* out, int channels, size_t hw, const float* mul, const float* add,
+                   const float* mul2, const float* add2, int relu, int batch, cudaStream_t s) {
+    const size_t total = static_cast<size_t>(batch) * channels * hw;
+    channel_affine_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, channels, hw, mul, add, mul2, add2, relu, total);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+int add_relu(const float* a, const float* b, float* out, size_t n, int relu, cudaStream_t s) {
+    add_relu_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(a, b, out, n, relu);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+int scale_relu(const float* in, float* out, size_t n, float scale, int relu, cudaStream_t s) {
+    scale_relu_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(in, out, n, scale, relu);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+int softmax_forward(const float* in, float* out, size_t n_per_image, int batch, cudaStream_t s) {
+    softmax_kernel<<<batch, 256, 0, s>>>(in, out, n_per_image);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+int copy_channels(const float* src, float* dst, size_t per_image, size_t dst_image, size_t dst_offset, int batch,
+                  cudaStream_t s) {
+    const size_t total = per_image * batch;
+    copy_channels_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, per_image, dst_image, dst_offset, total);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+int fill_rows(float* out, const float* row, int row_len, int rows, cudaStream_t s) {
+    const size_t total = static_cast<size_t>(row_len) * rows;
+    fill_rows_kernel<<<grid_for(total, 256), 256, 0, s>>>(out, row, row_len, total);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+}  // namespace fcuda

@@ -9,7 +9,9 @@
 #include "tensor_gemm.cuh"
 #include "common.cuh"
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace fcuda {
 
@@ -158,6 +160,7 @@ struct GemmKernelArgs {
     int M, N, K, G;
     int epilogue, ldd, P, relu, split_k;
     int num_m, num_n, k_blocks_total;
+    long long m_offset;
 };
 
 template <int BN, int PLANES>
@@ -316,8 +319,9 @@ tensor_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (args.epilogue == EPI_ROWMAJOR) {
                 row_base = (static_cast<size_t>(g) * args.M + (m_ok ? m : 0)) * args.ldd;
             } else if (args.epilogue == EPI_NCHW) {
-                img = (m_ok ? m : 0) / args.P;
-                pix = (m_ok ? m : 0) - img * args.P;
+                const long long mg = args.m_offset + (m_ok ? m : 0);
+                img = static_cast<int>(mg / args.P);
+                pix = static_cast<int>(mg - static_cast<long long>(img) * args.P);
             }
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -403,6 +407,38 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void reset_launch_count() { g_launches.store(0, std::memory_order_relaxed); }
+
+// ---- per-launch profiling ------------------------------------------------------------------------
+struct ProfRec { cudaEvent_t e0, e1; double algo_flops, mma_flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+void gemm_profile_enable(bool on) {
+    if (on) {
+        for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        g_prof.clear();
+    }
+    g_prof_on = on;
+}
+
+void gemm_profile_collect(double* total_ms, double* algo_flops, double* mma_flops, long long* launches) {
+    double ms = 0, af = 0, mf = 0;
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) ms += t;
+        af += r.algo_flops;
+        mf += r.mma_flops;
+    }
+    if (total_ms) *total_ms = ms;
+    if (algo_flops) *algo_flops = af;
+    if (mma_flops) *mma_flops = mf;
+    if (launches) *launches = static_cast<long long>(g_prof.size());
+}
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -471,6 +507,7 @@ static int launch(const GemmProblem& p, cudaStream_t stream) {
     a.M = p.M; a.N = p.N; a.K = p.K; a.G = p.G;
     a.epilogue = p.epilogue; a.ldd = p.ldd; a.P = p.P > 0 ? p.P : 1; a.relu = p.relu;
     a.split_k = p.split_k > 0 ? p.split_k : 1;
+    a.m_offset = p.m_offset;
     a.num_m = ceil_div(p.M, kBM);
     a.num_n = ceil_div(p.N, BN);
     a.k_blocks_total = ceil_div(p.K, kBK);
@@ -487,8 +524,22 @@ static int launch(const GemmProblem& p, cudaStream_t stream) {
         FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
+    ProfRec rec{};
+    if (g_prof_on) {
+        cudaEventCreate(&rec.e0);
+        cudaEventCreate(&rec.e1);
+        const double dense = 2.0 * p.M * static_cast<double>(p.N) * p.K * p.G;
+        rec.algo_flops = p.algo_flops > 0 ? p.algo_flops : dense;
+        rec.mma_flops = dense * (PLANES == 2 ? 3.0 : 1.0);
+        cudaEventRecord(rec.e0, stream);
+    }
     kern<<<grid, kThreads, smem, stream>>>(tmA, tmAlo, tmB, tmBlo, a);
     FCUDA_CHECK_LAUNCH();
+    count_launch();
+    if (g_prof_on) {
+        cudaEventRecord(rec.e1, stream);
+        g_prof.push_back(rec);
+    }
     return 0;
 }
 
@@ -558,7 +609,8 @@ simt_gemm_kernel(const float* __restrict__ A_hi, const float* __restrict__ A_lo,
             if (args.epilogue == EPI_ROWMAJOR) {
                 args.D[(static_cast<size_t>(g) * args.M + m) * args.ldd + n] = v;
             } else if (args.epilogue == EPI_NCHW) {
-                const int img = m / args.P, pix = m - img * args.P;
+                const long long mg = args.m_offset + m;
+                const int img = static_cast<int>(mg / args.P), pix = static_cast<int>(mg - static_cast<long long>(img) * args.P);
                 if (args.bias) v += args.bias[n];
                 if (args.relu) v = fmaxf(v, 0.f);
                 args.D[(static_cast<size_t>(img) * args.N + n) * args.P + pix] = v;
@@ -573,7 +625,7 @@ int simt_gemm(const GemmProblem& p, cudaStream_t stream) {
     GemmKernelArgs a;
     a.D = p.D; a.bias = p.bias;
     a.M = p.M; a.N = p.N; a.K = p.K; a.G = p.G;
-    a.epilogue = p.epilogue; a.ldd = p.ldd; a.P = p.P > 0 ? p.P : 1; a.relu = p.relu; a.split_k = 1;
+    a.epilogue = p.epilogue; a.ldd = p.ldd; a.P = p.P > 0 ? p.P : 1; a.relu = p.relu; a.split_k = 1; a.m_offset = p.m_offset;
     a.num_m = ceil_div(p.M, 64); a.num_n = ceil_div(p.N, 64); a.k_blocks_total = 0;
     const long long as = p.a_batch_stride ? p.a_batch_stride : static_cast<long long>(p.M) * p.K;
     const long long bs = p.b_batch_stride ? p.b_batch_stride : static_cast<long long>(p.N) * p.K;

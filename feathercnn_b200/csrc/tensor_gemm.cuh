@@ -38,16 +38,23 @@ struct GemmProblem {
     int epilogue;      // GemmEpilogue
     int ldd;           // EPI_ROWMAJOR / EPI_COLMAJOR_ATOMIC leading dimension (floats)
     int P;             // EPI_NCHW: pixels per image
+    long long m_offset;  // EPI_NCHW: global pixel index of row 0 (chunked im2col); image = (m_offset + m) / P
     const float* bias; // EPI_NCHW: per-n bias or null
     int relu;          // EPI_NCHW: fuse max(0, .)
     int split_k;       // >=1; only with EPI_COLMAJOR_ATOMIC
     long long a_batch_stride;  // floats between consecutive g in A; 0 => dense (M*K)
     long long b_batch_stride;  // floats between consecutive g in B; 0 => dense (N*K)
+    double algo_flops;         // algorithmic FLOPs this launch stands for (profiling only; 0 => 2*M*N*K*G)
 };
 
 // Launches the persistent tcgen05 kernel on `stream`.  Returns 0 or a negative fcuda error.
 // Requirements: K % 4 == 0, 16-byte aligned operand pointers.  M/N/K tails are zero-filled by TMA.
 int tensor_gemm(const GemmProblem& p, cudaStream_t stream);
+
+// Per-launch profiling of the TensorGEMM (bench.py's roofline leg): when enabled every tensor_gemm launch is
+// bracketed by CUDA events on its own stream.  collect() synchronises and returns totals since enable.
+void gemm_profile_enable(bool on);
+void gemm_profile_collect(double* total_ms, double* algo_flops, double* mma_flops, long long* launches);
 
 // True when the problem satisfies the TMA alignment rules above.
 bool tensor_gemm_supported(const GemmProblem& p);

@@ -1,0 +1,322 @@
+// Winograd F(6,3) and F(2,3) transform kernels (sm_100a).
+//
+// Replaces, on the GPU:
+//   transformKernel_F6x6_3x3           /root/reference/src/booster/avx/winograd_kernels_F63.cpp:222-271   (filter, at Init)
+//   pad_input + winogradInputFrameTransformSeq   generic_kernels.cpp:31-48, winograd_kernels_F63.cpp:272-513
+//   winogradOutputTransform<RELU,BIAS>           winograd_kernels_F63.cpp:1029-1269
+//   F(2,3) variant                     /root/reference/src/booster/arm/winograd_kernels.cpp:115-279 (NEON only upstream)
+// The 64 (16) per-tile-element GEMMs in between run on tcgen05 (tensor_gemm.cu).
+//
+// Layouts (private to this backend — parity is defined on NCHW blobs only):
+//   U[e][oc][ic]   transformed filters, K-major rows for the TensorGEMM B operand
+//   V[e][t][ic]    transformed input tiles, t = chunk-local tile index, K-major rows for the A operand
+//   M[e][t][oc]    products
+// Each of U and V exists as a TF32-exact "hi" plane and (3xTF32 mode) an fp32-remainder "lo" plane.
+//
+// Data movement: a block stages a (32 channels) x (8 rows) x (4 tiles wide) slab through shared memory so that
+// global reads are coalesced along x and global writes are coalesced along the channel (K) dimension;
+// zero padding is applied by the bounds check of the slab load (no padded copy of the input is made).
+#include "winograd.cuh"
+#include "common.cuh"
+
+namespace fcuda {
+
+// ------------------------------------------------------------------------------------------------
+// 1-D transforms
+// ------------------------------------------------------------------------------------------------
+// B^T for F(6,3): same constants and operation order as winograd_kernels_F63.cpp:297-321.
+__device__ __forceinline__ void f63_bt(const float (&r)[8], float (&o)[8]) {
+    o[0] = (r[0] - r[6]) + (r[4] - r[2]) * 5.25f;
+    o[7] = (r[7] - r[1]) + (r[3] - r[5]) * 5.25f;
+    const float t1 = (r[2] + r[6]) - r[4] * 4.25f;
+    const float t2 = (r[1] + r[5]) - r[3] * 4.25f;
+    const float s1 = r[4] * 1.25f;
+    const float s2 = r[3] * 2.5f;
+    float p1 = r[6] + (r[2] * 0.25f - s1);
+    float p2 = (r[1] * 0.5f - s2) + r[5] * 2.f;
+    o[3] = p1 + p2;
+    o[4] = p1 - p2;
+    p1 = r[6] + (r[2] - s1) * 4.f;
+    p2 = (r[1] * 2.f - s2) + r[5] * 0.5f;
+    o[5] = p1 + p2;
+    o[6] = p1 - p2;
+    o[1] = t1 + t2;
+    o[2] = t1 - t2;
+}
+
+// A^T for F(6,3): winograd_kernels_F63.cpp:1040-1045.
+__device__ __forceinline__ void f63_at(const float (&m)[8], float (&s)[6]) {
+    const float a12 = m[1] + m[2], s12 = m[1] - m[2];
+    const float a34 = m[3] + m[4], s34 = m[3] - m[4];
+    const float a56 = m[5] + m[6], s56 = m[5] - m[6];
+    s[0] = m[0] + a12 + a34 + 32.f * a56;
+    s[1] = s12 + 2.f * s34 + 16.f * s56;
+    s[2] = a12 + 4.f * a34 + 8.f * a56;
+    s[3] = s12 + 8.f * s34 + 4.f * s56;
+    s[4] = a12 + 16.f * a34 + 2.f * a56;
+    s[5] = s12 + 32.f * s34 + s56 + m[7];
+}
+
+// F(2,3): B^T = [1 0 -1 0; 0 1 1 0; 0 -1 1 0; 0 1 0 -1], A^T = [1 1 1 0; 0 1 -1 -1]
+__device__ __forceinline__ void f23_bt(const float (&r)[4], float (&o)[4]) {
+    o[0] = r[0] - r[2];
+    o[1] = r[1] + r[2];
+    o[2] = r[2] - r[1];
+    o[3] = r[1] - r[3];
+}
+__device__ __forceinline__ void f23_at(const float (&m)[4], float (&s)[2]) {
+    s[0] = m[0] + m[1] + m[2];
+    s[1] = m[1] - m[2] - m[3];
+}
+
+template <int T> struct Wino;  // T = input tile edge
+template <> struct Wino<8> {
+    static constexpr int kIn = 8, kOut = 6;
+    __device__ static __forceinline__ void bt(const float (&r)[8], float (&o)[8]) { f63_bt(r, o); }
+    __device__ static __forceinline__ void at(const float (&m)[8], float (&s)[6]) { f63_at(m, s); }
+};
+template <> struct Wino<4> {
+    static constexpr int kIn = 4, kOut = 2;
+    __device__ static __forceinline__ void bt(const float (&r)[4], float (&o)[4]) { f23_bt(r, o); }
+    __device__ static __forceinline__ void at(const float (&m)[4], float (&s)[2]) { f23_at(m, s); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Filter transform  U = G g G^T   (Init time)
+// ------------------------------------------------------------------------------------------------
+// G for F(6,3): the reference's table, winograd_kernels_F63.cpp:191-201 (rows 5/6 pre-divided by 32 to match
+// the x32 in the output transform).
+__constant__ float kG63[8][3] = {
+    {1.0f, 0.0f, 0.0f},
+    {-2.0f / 9, -2.0f / 9, -2.0f / 9},
+    {-2.0f / 9, 2.0f / 9, -2.0f / 9},
+    {1.0f / 90, 1.0f / 45, 2.0f / 45},
+    {1.0f / 90, -1.0f / 45, 2.0f / 45},
+    {1.0f / 45, 1.0f / 90, 1.0f / 180},
+    {1.0f / 45, -1.0f / 90, 1.0f / 180},
+    {0.0f, 0.0f, 1.0f}};
+__constant__ float kG23[4][3] = {{1.f, 0.f, 0.f}, {0.5f, 0.5f, 0.5f}, {0.5f, -0.5f, 0.5f}, {0.f, 0.f, 1.f}};
+
+template <int T>
+__device__ __forceinline__ float wino_G(int i, int k) {
+    if constexpr (T == 8) return kG63[i][k];
+    else return kG23[i][k];
+}
+
+template <int T>
+__global__ void __launch_bounds__(128)
+wino_filter_kernel(const float* __restrict__ w, float* __restrict__ U_hi, float* __restrict__ U_lo, int OC, int IC) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // oc * IC + ic
+    if (idx >= OC * IC) return;
+    const int oc = idx / IC, ic = idx - oc * IC;
+    float g[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) g[i] = w[static_cast<size_t>(idx) * 9 + i];
+    float mid[T][3];
+#pragma unroll
+    for (int i = 0; i < T; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s += wino_G<T>(i, k) * g[k * 3 + j];
+            mid[i][j] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < T; ++i)
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s += mid[i][k] * wino_G<T>(j, k);
+            const size_t o = (static_cast<size_t>(i * T + j) * OC + oc) * IC + ic;
+            if (U_lo) {
+                float hi, lo;
+                split_tf32(s, hi, lo);
+                U_hi[o] = hi;
+                U_lo[o] = lo;
+            } else {
+                U_hi[o] = s;
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Input transform  V = B^T d B
+// ------------------------------------------------------------------------------------------------
+constexpr int kSegTiles = 4;  // tiles per block along x (one warp each)
+constexpr int kChBlock = 32;  // channels per block (one lane each)
+
+template <int T>
+__global__ void __launch_bounds__(128)
+wino_input_kernel(const float* __restrict__ in, float* __restrict__ V_hi, float* __restrict__ V_lo, WinoGeom g,
+                  int R0, int Tc) {
+    using W = Wino<T>;
+    constexpr int OT = W::kOut;
+    constexpr int COLS = OT * kSegTiles + (T - OT);
+    constexpr int CH_STRIDE = T * COLS + 1;  // odd => conflict-free when lanes index channels
+    __shared__ float slab[kChBlock * CH_STRIDE];
+
+    const int segs = (g.tilesX + kSegTiles - 1) / kSegTiles;
+    const int seg = blockIdx.x % segs;
+    const int Rl = blockIdx.x / segs;  // chunk-local tile-row
+    const int R = R0 + Rl;
+    const int n = R / g.tilesY, ty = R - n * g.tilesY;
+    const int tx0 = seg * kSegTiles;
+    const int c0 = blockIdx.y * kChBlock;
+    const int gy0 = ty * OT - g.pad_top, gx0 = tx0 * OT - g.pad_left;
+
+    const float* img = in + static_cast<size_t>(n) * g.C_in * g.H * g.W;
+    for (int idx = threadIdx.x; idx < kChBlock * T * COLS; idx += 128) {
+        const int c = idx / (T * COLS);
+        const int rem = idx - c * (T * COLS);
+        const int r = rem / COLS, x = rem - r * COLS;
+        const int ic = c0 + c, gy = gy0 + r, gx = gx0 + x;
+        float v = 0.f;
+        if (ic < g.C_in && gy >= 0 && gy < g.H && gx >= 0 && gx < g.W)
+            v = __ldg(img + (static_cast<size_t>(ic) * g.H + gy) * g.W + gx);
+        slab[c * CH_STRIDE + r * COLS + x] = v;
+    }
+    __syncthreads();
+
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = tx0 + w, ic = c0 + lane;
+    if (tx >= g.tilesX || ic >= g.C_in) return;
+    const float* d = slab + lane * CH_STRIDE + w * OT;
+
+    float t[T][T];
+#pragma unroll
+    for (int x = 0; x < T; ++x) {
+        float col[T], o[T];
+#pragma unroll
+        for (int y = 0; y < T; ++y) col[y] = d[y * COLS + x];
+        W::bt(col, o);
+#pragma unroll
+        for (int y = 0; y < T; ++y) t[y][x] = o[y];
+    }
+    const size_t tp = static_cast<size_t>(Rl) * g.tilesX + tx;  // chunk-local tile index
+    const size_t plane = static_cast<size_t>(Tc) * g.C_in;     // floats per tile element
+    float* vh = V_hi + tp * g.C_in + ic;
+    float* vl = V_lo ? V_lo + tp * g.C_in + ic : nullptr;
+#pragma unroll
+    for (int a = 0; a < T; ++a) {
+        float o[T];
+        W::bt(t[a], o);
+#pragma unroll
+        for (int b = 0; b < T; ++b) {
+            const size_t off = static_cast<size_t>(a * T + b) * plane;
+            if (vl) {
+                float hi, lo;
+                split_tf32(o[b], hi, lo);
+                vh[off] = hi;
+                vl[off] = lo;
+            } else {
+                vh[off] = o[b];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output transform  Y = A^T M A  (+bias, ReLU), clipped NCHW store
+// ------------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(128)
+wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const float* __restrict__ bias, WinoGeom g,
+                   int R0, int Tc, int relu) {
+    using W = Wino<T>;
+    constexpr int OT = W::kOut;
+    constexpr int COLS = OT * kSegTiles;
+    constexpr int CH_STRIDE = OT * COLS + 1;
+    __shared__ float slab[kChBlock * CH_STRIDE];
+
+    const int segs = (g.tilesX + kSegTiles - 1) / kSegTiles;
+    const int seg = blockIdx.x % segs;
+    const int Rl = blockIdx.x / segs;
+    const int R = R0 + Rl;
+    const int n = R / g.tilesY, ty = R - n * g.tilesY;
+    const int tx0 = seg * kSegTiles;
+    const int c0 = blockIdx.y * kChBlock;
+
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = tx0 + w, oc = c0 + lane;
+    if (tx < g.tilesX && oc < g.C_out) {
+        const size_t tp = static_cast<size_t>(Rl) * g.tilesX + tx;
+        const size_t plane = static_cast<size_t>(Tc) * g.C_out;
+        const float* m = M + tp * g.C_out + oc;
+        float tmp[OT][T];
+#pragma unroll
+        for (int b = 0; b < T; ++b) {
+            float col[T], s[OT];
+#pragma unroll
+            for (int a = 0; a < T; ++a) col[a] = __ldg(m + static_cast<size_t>(a * T + b) * plane);
+            W::at(col, s);
+#pragma unroll
+            for (int i = 0; i < OT; ++i) tmp[i][b] = s[i];
+        }
+        const float bv = bias ? __ldg(bias + oc) : 0.f;
+        float* dst = slab + lane * CH_STRIDE + w * OT;
+#pragma unroll
+        for (int i = 0; i < OT; ++i) {
+            float s[OT];
+            W::at(tmp[i], s);
+#pragma unroll
+            for (int j = 0; j < OT; ++j) {
+                float v = s[j] + bv;
+                if (relu) v = fmaxf(v, 0.f);
+                dst[i * COLS + j] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    const int oy0 = ty * OT, ox0 = tx0 * OT;
+    float* img = out + static_cast<size_t>(n) * g.C_out * g.OH * g.OW;
+    for (int idx = threadIdx.x; idx < kChBlock * OT * COLS; idx += 128) {
+        const int c = idx / (OT * COLS);
+        const int rem = idx - c * (OT * COLS);
+        const int r = rem / COLS, x = rem - r * COLS;
+        const int o = c0 + c, oy = oy0 + r, ox = ox0 + x;
+        if (o < g.C_out && oy < g.OH && ox < g.OW)
+            img[(static_cast<size_t>(o) * g.OH + oy) * g.OW + ox] = slab[c * CH_STRIDE + r * COLS + x];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host launchers
+// ------------------------------------------------------------------------------------------------
+int wino_filter_transform(int tile, const float* w, float* U_hi, float* U_lo, int OC, int IC, cudaStream_t s) {
+    const int total = OC * IC;
+    const int blocks = ceil_div(total, 128);
+    if (tile == 8) wino_filter_kernel<8><<<blocks, 128, 0, s>>>(w, U_hi, U_lo, OC, IC);
+    else wino_filter_kernel<4><<<blocks, 128, 0, s>>>(w, U_hi, U_lo, OC, IC);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+int wino_input_transform(int tile, const float* in, float* V_hi, float* V_lo, const WinoGeom& g, int R0, int R1,
+                         cudaStream_t s) {
+    const int segs = ceil_div(g.tilesX, kSegTiles);
+    const int Tc = (R1 - R0) * g.tilesX;
+    dim3 grid(static_cast<unsigned>(segs) * (R1 - R0), ceil_div(g.C_in, kChBlock));
+    if (tile == 8) wino_input_kernel<8><<<grid, 128, 0, s>>>(in, V_hi, V_lo, g, R0, Tc);
+    else wino_input_kernel<4><<<grid, 128, 0, s>>>(in, V_hi, V_lo, g, R0, Tc);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+int wino_output_transform(int tile, const float* M, float* out, const float* bias, const WinoGeom& g, int R0, int R1,
+                          int relu, cudaStream_t s) {
+    const int segs = ceil_div(g.tilesX, kSegTiles);
+    const int Tc = (R1 - R0) * g.tilesX;
+    dim3 grid(static_cast<unsigned>(segs) * (R1 - R0), ceil_div(g.C_out, kChBlock));
+    if (tile == 8) wino_output_kernel<8><<<grid, 128, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+    else wino_output_kernel<4><<<grid, 128, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+}  // namespace fcuda

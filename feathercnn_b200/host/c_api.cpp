@@ -1,0 +1,73 @@
+// extern "C" face of feather::Net for language bindings (ctypes in feathercnn_b200/net.py).
+// Declared in include/feather_c.h.
+#include <feather_c.h>
+
+#include <feather/net.h>
+#include <string.h>
+
+#include <string>
+
+using feather::Net;
+
+extern "C" {
+
+void* fnet_create(void) { return new Net(); }
+void fnet_destroy(void* h) { delete static_cast<Net*>(h); }
+void fnet_set_fusion(void* h, int enable) { static_cast<Net*>(h)->SetFusion(enable != 0); }
+void fnet_set_cuda_graph(void* h, int enable) { static_cast<Net*>(h)->SetCudaGraph(enable != 0); }
+void fnet_set_stream(void* h, void* stream) { static_cast<Net*>(h)->SetStream(stream); }
+int fnet_load_param(void* h, const char* path) { return static_cast<Net*>(h)->LoadParam(path); }
+int fnet_load_param_text(void* h, const char* text) { return static_cast<Net*>(h)->LoadParamFromText(text); }
+int fnet_load_weights(void* h, const char* path) { return static_cast<Net*>(h)->LoadWeights(path); }
+int fnet_init_from_path(void* h, const char* path) { return static_cast<Net*>(h)->InitFromPath(path); }
+int fnet_init_from_buffer(void* h, const void* buf, size_t size) { return static_cast<Net*>(h)->InitFromBuffer(buf, size); }
+int fnet_prepare_weight_arena(void* h) { return static_cast<Net*>(h)->PrepareWeightArena(); }
+int fnet_weight_arena(void* h, float** device_ptr, size_t* floats) {
+    Net* n = static_cast<Net*>(h);
+    *device_ptr = n->WeightArena();
+    *floats = n->WeightArenaFloats();
+    return 0;
+}
+int fnet_attach_weights(void* h) { return static_cast<Net*>(h)->AttachWeights(); }
+int fnet_feed_input_batch(void* h, const char* name, const float* host, int n, int c, int hh, int w) {
+    return static_cast<Net*>(h)->FeedInputBatch(name, host, n, c, hh, w);
+}
+int fnet_feed_input_device(void* h, const char* name, const float* dev, int n, int c, int hh, int w) {
+    return static_cast<Net*>(h)->FeedInputDevice(name, dev, n, c, hh, w);
+}
+int fnet_forward(void* h) { return static_cast<Net*>(h)->Forward(); }
+int fnet_forward_batch(void* h, const float* host_nchw, int batch) { return static_cast<Net*>(h)->ForwardBatch(host_nchw, batch); }
+int fnet_synchronize(void* h) { return static_cast<Net*>(h)->Synchronize(); }
+int fnet_blob_shape(void* h, const char* name, int* n, int* c, int* hh, int* w) {
+    Net* net = static_cast<Net*>(h);
+    std::map<std::string, feather::Blob<float>*>::iterator it = net->blob_map.find(name);
+    if (it == net->blob_map.end()) return -1;
+    *n = it->second->num(); *c = it->second->channels(); *hh = it->second->height(); *w = it->second->width();
+    return 0;
+}
+int fnet_extract_blob(void* h, const char* name, float* host_out) { return static_cast<Net*>(h)->ExtractBlob(host_out, name); }
+int fnet_extract_device(void* h, const char* name, const float** dev, int* n, int* c, int* hh, int* w) {
+    return static_cast<Net*>(h)->ExtractDevice(name, dev, n, c, hh, w);
+}
+unsigned long long fnet_launches_per_forward(void* h) { return static_cast<Net*>(h)->LaunchesPerForward(); }
+int fnet_input_shape(void* h, int* c, int* hh, int* w) {
+    static_cast<Net*>(h)->InputShape(c, hh, w);
+    return 0;
+}
+// Writes the blob names separated by '\n' into buf (NUL terminated); returns the length needed.
+size_t fnet_blob_names(void* h, char* buf, size_t cap) {
+    std::string joined;
+    for (const std::string& s : static_cast<Net*>(h)->BlobNames()) {
+        if (!joined.empty()) joined += '\n';
+        joined += s;
+    }
+    if (buf && cap > 0) {
+        const size_t n = joined.size() < cap - 1 ? joined.size() : cap - 1;
+        memcpy(buf, joined.data(), n);
+        buf[n] = '\0';
+    }
+    return joined.size() + 1;
+}
+const char* fnet_input_name(void* h) { return static_cast<Net*>(h)->InputName().c_str(); }
+
+}  // extern "C"

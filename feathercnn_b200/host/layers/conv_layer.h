@@ -1,0 +1,152 @@
+// ConvLayer — serves ncnn "Convolution" and "ConvolutionDepthWise" (mirrors
+// /root/reference/src/layers/conv_layer.h:26-194; same ncnn param ids, same call protocol into ConvBooster).
+#pragma once
+
+#include <feather/booster.h>
+#include <feather/layer.h>
+#include <stdlib.h>
+
+namespace feather {
+inline namespace b200 {  // ABI tag: keeps these symbols apart from the reference build when both are loaded
+
+class ConvLayer : public Layer {
+public:
+    explicit ConvLayer(RuntimeParameter<float>* rt_param)
+        : Layer(rt_param), bias_data(NULL), processed_kernel(NULL), processed_weights(NULL), init_algo(-1) {
+        _fusible = true;
+    }
+    ~ConvLayer() { delete processed_weights; }
+
+    int LoadParam(const ncnn::ParamDict& pd) {
+        const int dilation_w = pd.get(2, 1);
+        const int dilation_h = pd.get(12, dilation_w);
+        if (dilation_w > 1 || dilation_h > 1) {
+            LOGE("Dilated convolution is not supported in FeatherCNN.");
+            return FEATHER_ERR_UNSUPPORTED;  // conv_layer.h:41-47
+        }
+        if (pd.get(8, 0)) {
+            LOGE("int8 convolution is not supported in FeatherCNN.");
+            return FEATHER_ERR_UNSUPPORTED;  // conv_layer.h:49-54
+        }
+        conv_param.kernel_w = pd.get(1, 0);
+        conv_param.kernel_h = pd.get(11, conv_param.kernel_w);
+        conv_param.stride_w = pd.get(3, 1);
+        conv_param.stride_h = pd.get(13, conv_param.stride_w);
+        conv_param.pad_left = pd.get(4, 0);
+        conv_param.pad_bottom = pd.get(14, conv_param.pad_left);
+        conv_param.pad_right = pd.get(4, 0);
+        conv_param.pad_top = pd.get(14, conv_param.pad_left);
+        conv_param.group = pd.get(7, 1);
+        conv_param.output_channels = pd.get(0, 0);
+        conv_param.bias_term = pd.get(5, 0);
+        conv_param.activation = booster::None;
+        const int weight_data_size = pd.get(6, 0);
+        if (conv_param.group == 0 || conv_param.output_channels % conv_param.group) {
+            LOGE("Layer %s output_channels is not divisible by its group", this->name.c_str());
+            return FEATHER_ERR_UNSUPPORTED;  // the reference exit(0)s here (conv_layer.h:70-74)
+        }
+        num_output = conv_param.output_channels;
+        conv_param.output_channels /= conv_param.group;
+        if (conv_param.output_channels <= 0 || conv_param.kernel_h <= 0 || conv_param.kernel_w <= 0) return FEATHER_ERR_WEIGHTS;
+        conv_param.input_channels = weight_data_size / conv_param.output_channels / conv_param.kernel_h / conv_param.kernel_w;
+
+        weights.push_back(NewWeightBlob(this->name + "_weights", conv_param.output_channels, conv_param.input_channels,
+                                        conv_param.kernel_h, conv_param.kernel_w));
+        if (conv_param.bias_term) {
+            // The reference sizes the bias by output_channels/group (conv_layer.h:86), which is wrong for
+            // depthwise-with-bias; the file holds num_output values, so read those.
+            weights.push_back(NewWeightBlob(this->name + "_bias", num_output, 1, 1, 1));
+        }
+        return 0;
+    }
+
+    int LoadWeights(const ncnn::ModelBin& mb) {
+        const int weight_data_size =
+            conv_param.input_channels * conv_param.output_channels * conv_param.kernel_h * conv_param.kernel_w;
+        ncnn::Mat weight_data = mb.load(weight_data_size, 0);
+        if (weight_data.empty() || this->weights.empty()) return FEATHER_ERR_WEIGHTS;
+        int rc = this->weights[0]->CopyDataFromMat(weight_data);
+        if (rc) return rc;
+        if (conv_param.bias_term) {
+            ncnn::Mat bias_mat = mb.load(num_output, 1);
+            if (bias_mat.empty() || this->weights.size() < 2) return FEATHER_ERR_WEIGHTS;
+            rc = weights[1]->CopyDataFromMat(bias_mat);
+        }
+        return rc;
+    }
+
+    int Reshape() {
+        const Blob<float>* bottom_blob = this->bottoms[0];
+        conv_param.input_w = bottom_blob->width();
+        conv_param.input_h = bottom_blob->height();
+        if (conv_param.input_channels != static_cast<int>(bottom_blob->channels())) {
+            LOGE("Loaded convolution layer %s has %d input channels while bottom blob has %zu channels",
+                 this->name.c_str(), conv_param.input_channels, bottom_blob->channels());
+            return FEATHER_ERR_TOPOLOGY;
+        }
+        if (conv_param.group == conv_param.input_channels) conv_param.output_channels = conv_param.input_channels;
+        conv_param.AssignOutputDim();
+        const int batch = bottom_blob->num();
+        tops[0]->ReshapeWithRealloc(batch, conv_param.output_channels, conv_param.output_h, conv_param.output_w);
+        int rc = conv_booster.SelectAlgo(&this->conv_param);
+        if (rc) return rc;
+        if (const char* force = getenv("FEATHER_FORCE_CONV_ALGO")) {  // ForceSelectAlgo hook, avx/booster.cpp:313-317
+            booster::ConvBooster forced;
+            forced.ForceSelectAlgo(static_cast<booster::ConvAlgo>(atoi(force)));
+            size_t a = 0, b = 0;
+            if (conv_booster.GetAlgo() != booster::DEPTHWISE && forced.GetBufferSize(&conv_param, &a, &b, batch) == 0)
+                conv_booster = forced;
+        }
+        size_t buffer_size = 0, dull = 0;
+        rc = conv_booster.GetBufferSize(&conv_param, &buffer_size, &dull, batch);
+        if (rc) return rc;
+        MEMPOOL_CHECK_RETURN(this->common_mempool->Request(sizeof(float) * buffer_size));
+        if (init_algo >= 0 && init_algo != conv_booster.GetAlgo()) return Init();  // shape change switched algorithms
+        return 0;
+    }
+
+    int Init() {
+        size_t buffer_size = 0, processed_kernel_size = 0;
+        int rc = conv_booster.GetBufferSize(&conv_param, &buffer_size, &processed_kernel_size, 1);
+        if (rc) return rc;
+        if (!processed_weights) processed_weights = new Blob<float>(this->name + "_proc_weights");
+        processed_weights->ReshapeWithRealloc(1, 1, 1, static_cast<int>(processed_kernel_size));
+        if (!processed_weights->data() || !weights[0]->data()) return FEATHER_ERR_WEIGHTS;
+        rc = conv_booster.Init(&conv_param, processed_weights->data(), weights[0]->data(), stream());
+        if (rc) return rc;
+        this->processed_kernel = processed_weights->data();
+        if (conv_param.bias_term) bias_data = this->weights[1]->data();
+        init_algo = conv_booster.GetAlgo();
+        return 0;
+    }
+
+    int Forward() {
+        float* buffer = NULL;
+        MEMPOOL_CHECK_RETURN(this->common_mempool->GetPtr(&buffer));
+        return conv_booster.Forward(&conv_param, tops[0]->data(), bottoms[0]->data(), processed_kernel, buffer, bias_data,
+                                    bottoms[0]->num(), stream());
+    }
+
+    int Fuse(Layer* next_layer) {  // conv_layer.h:174-185
+        if (next_layer->type.compare("ReLU") == 0) {
+            conv_param.activation = booster::ReLU;
+            return 1;
+        }
+        return 0;
+    }
+
+    const booster::ConvParam& param() const { return conv_param; }
+    int algo() const { return conv_booster.GetAlgo(); }
+
+protected:
+    booster::ConvBooster conv_booster;
+    booster::ConvParam conv_param;
+    float* bias_data;
+    float* processed_kernel;
+    Blob<float>* processed_weights;
+    int init_algo;
+    int num_output = 0;
+};
+
+}  // inline namespace b200
+}  // namespace feather

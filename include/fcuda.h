@@ -1,0 +1,150 @@
+/* fcuda.h — C ABI of the B200 (sm_100a) compute backend that replaces FeatherCNN's `booster`.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to /root/reference).
+ * Conventions, all inherited from the reference boundary:
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers unless a parameter says "host";
+ *   - tensors are fp32, NCHW, channel stride exactly H*W (src/blob.cpp:86-93); a leading batch dimension
+ *     `batch` (images, image stride C*H*W) is the one extension — the reference is batch-1 (src/blob.cpp:73);
+ *   - buffer sizes are in FLOATS, not bytes (src/layers/conv_layer.h:112,159);
+ *   - the library allocates nothing on the hot path: the caller owns outputs, packed kernels and scratch
+ *     (src/booster/include/booster/booster.h:155);
+ *   - return 0 on success, negative int on failure: -1 unsupported algorithm / partial groups
+ *     (src/booster/avx/booster.cpp:306-307,349-353), -100 bad sizes, -200 unsupported parameter, -700 CUDA error;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous.
+ */
+#ifndef FCUDA_H
+#define FCUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* booster::ConvAlgo, src/booster/include/booster/booster.h:42-51 (same numbering). */
+enum FcudaConvAlgo {
+    FCUDA_NAIVE = 0,            /* CUDA-core fp32 implicit GEMM (device-side second opinion) */
+    FCUDA_IM2COL = 1,           /* pack kernel + tcgen05 TensorGEMM, bias/ReLU fused in the epilogue */
+    FCUDA_SGECONV = 2,          /* stub in the reference's AVX dispatcher; unsupported here too (-1) */
+    FCUDA_DEPTHWISE = 3,        /* warp-shuffle stencil */
+    FCUDA_WINOGRADF63 = 4,      /* F(6,3): input transform -> 64-way tcgen05 TensorGEMM -> output transform(+bias+ReLU) */
+    FCUDA_WINOGRADF63FUSED = 5, /* not selected by the reference (avx/booster.cpp:291-292); unsupported (-1) */
+    FCUDA_WINOGRADF23 = 6       /* F(2,3): 16-way TensorGEMM; stub in both reference dispatchers, real here */
+};
+
+/* booster::ActivationType, booster.h:53-57 */
+enum FcudaActivation { FCUDA_ACT_NONE = 0, FCUDA_ACT_RELU = 1 };
+
+/* Field-compatible with booster::ConvParam (booster.h:59-77): 15 ints, bool, enum. */
+typedef struct FcudaConvParam {
+    int output_channels;
+    int input_channels;
+    int input_h;
+    int input_w;
+    int kernel_h;
+    int kernel_w;
+    int output_h;
+    int output_w;
+    int stride_h;
+    int stride_w;
+    int pad_left;
+    int pad_bottom;
+    int pad_right;
+    int pad_top;
+    int group;
+    unsigned char bias_term; /* bool */
+    int activation;          /* FcudaActivation */
+} FcudaConvParam;
+
+/* Arithmetic mode of the tensor-core contraction (global, default FCUDA_PRECISION_TF32X3).
+ *   TF32X3: operands split into TF32 hi + fp32 lo planes, 3 MMAs per k-step — fp32-equivalent results.
+ *   TF32  : single TF32 MMA — ~2.5e-4 relative error per layer, 3x fewer MMAs. */
+enum FcudaPrecision { FCUDA_PRECISION_TF32X3 = 0, FCUDA_PRECISION_TF32 = 1 };
+int fcuda_set_precision(int precision);
+int fcuda_get_precision(void);
+
+/* Working-set target (bytes) for the Winograd / im2col intermediates so that they stay L2-resident
+ * between the pack, TensorGEMM and unpack kernels (default 48 MiB of the 126 MB L2; 0 = one chunk). */
+int fcuda_set_l2_chunk_bytes(size_t bytes);
+size_t fcuda_get_l2_chunk_bytes(void);
+
+/* ConvParam::AssignOutputDim, booster.h:113-125. */
+int fcuda_conv_assign_output_dim(FcudaConvParam* param);
+
+/* ConvBooster::SelectAlgo, avx/booster.cpp:283-310 (same rule, same -1 for partial groups). */
+int fcuda_conv_select_algo(const FcudaConvParam* param, int* algo);
+
+/* GET_BUFFER_SIZE_FUNC, booster.h:151: scratch and processed-kernel sizes in floats for `batch` images. */
+int fcuda_conv_get_buffer_size(const FcudaConvParam* param, int algo, int batch, size_t* scratch_floats,
+                               size_t* packed_kernel_floats);
+
+/* INIT_FUNC, booster.h:152: transforms/packs the raw (OC, IC/group, KH, KW) kernel once.
+ * `raw_kernel` may be a host or a device pointer.  Synchronous with respect to `raw_kernel`. */
+int fcuda_conv_init(const FcudaConvParam* param, int algo, float* packed_kernel, const float* raw_kernel,
+                    void* stream);
+
+/* FORWARD_FUNC, booster.h:153: output (batch, OC, OH, OW) <- input (batch, IC, H, W).
+ * `bias` is OC floats or NULL when !bias_term; param->activation fuses ReLU (conv_layer.h:174-185). */
+int fcuda_conv_forward(const FcudaConvParam* param, int algo, float* output, const float* input,
+                       const float* packed_kernel, float* scratch, const float* bias, int batch, void* stream);
+
+/* The 64-way batched "TensorGEMM" itself (avx/winograd_kernels_F63.cpp:518-757), exposed for tests and
+ * profiling:  for g < G:  D[g][m][n] = sum_k A[g][m][k] * B[g][n][k]   (row-major, K-major operands).
+ * a_lo/b_lo are the fp32 remainders of the TF32 split (may be NULL => plain TF32). */
+int fcuda_tensor_gemm(float* d, const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
+                      int m, int n, int k, int g, void* stream);
+/* Elementwise TF32 split used to prepare TensorGEMM operands: hi + lo == x exactly. */
+int fcuda_split_tf32(float* hi, float* lo, const float* x, size_t n, void* stream);
+
+/* InnerProductLayer (src/layers/inner_product_layer.h:33-170; sgemv.cpp:317-395): z = W x + b per image. */
+int fcuda_inner_product_get_buffer_size(int input_size, int output_size, int batch, size_t* scratch_floats,
+                                        size_t* packed_kernel_floats);
+int fcuda_inner_product_init(int input_size, int output_size, float* packed_kernel, const float* raw_kernel,
+                             void* stream);
+int fcuda_inner_product_forward(int input_size, int output_size, float* output, const float* input,
+                                const float* packed_kernel, const float* bias, float* scratch, int relu, int batch,
+                                void* stream);
+
+/* PoolingLayer::Forward (src/layers/pooling_layer.h:38-91) incl. its ceil-mode output size (:129-130,
+ * fcuda_pooling_out_dim) and its window start that subtracts both pads (:56,:67). type 0 = max, else average. */
+int fcuda_pooling_out_dim(int in, int pad_a, int pad_b, int kernel, int stride);
+int fcuda_pooling_forward(float* output, const float* input, int channels, int in_h, int in_w, int type,
+                          int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_left, int pad_right,
+                          int pad_top, int pad_bottom, int global_pooling, int batch, void* stream);
+
+/* booster::batchnorm<has_bias,has_scale,has_relu> (avx/generic_kernels.cpp:237-279):
+ * y = beta[c]*x + alpha[c]; then *scale[c] (if scale), +scale_bias[c] (if scale_bias), ReLU (if relu). */
+int fcuda_batchnorm_forward(float* output, const float* input, int channels, size_t stride, const float* alpha,
+                            const float* beta, const float* scale, const float* scale_bias, int relu, int batch,
+                            void* stream);
+/* booster::scale<has_bias> (avx/generic_kernels.cpp:203-233): y = x*scale[c] (+bias[c]). */
+int fcuda_scale_forward(float* output, const float* input, int channels, size_t stride, const float* scale,
+                        const float* bias, int batch, void* stream);
+/* booster::add_relu<fuse_relu> (avx/generic_kernels.cpp:138-169). */
+int fcuda_eltwise_add_forward(float* output, const float* a, const float* b, size_t n, int relu, void* stream);
+/* ReluLayer::Forward (src/layers/relu_layer.h:29-41). */
+int fcuda_relu_forward(float* output, const float* input, size_t n, void* stream);
+/* SoftmaxLayer::Forward (src/layers/softmax_layer.h:32-55): over each image's whole blob. */
+int fcuda_softmax_forward(float* output, const float* input, size_t n_per_image, int batch, void* stream);
+/* DropoutLayer::Forward (src/layers/dropout_layer.h:36-57): y = x*scale (copy when scale == 1). */
+int fcuda_dropout_forward(float* output, const float* input, size_t n, float scale, void* stream);
+/* ConcatLayer / SplitLayer copies (src/layers/concat_layer.h:37-47, split_layer.h:43-53): copies `channels`
+ * channels of every image into dst at channel offset `dst_channel_offset` of a dst with `dst_channels`. */
+int fcuda_copy_channels(float* dst, int dst_channels, int dst_channel_offset, const float* src, int channels,
+                        size_t stride, int batch, void* stream);
+
+/* Profiling aid for bench.py's roofline leg: while enabled, every TensorGEMM launch is bracketed by CUDA events
+ * on its own stream.  fcuda_profile_collect synchronises and reports, since the last enable: summed device time
+ * (ms), the algorithmic FLOPs those launches stand for (direct-conv count, booster.h:145-148; 2*in*out*batch for
+ * InnerProduct), the tensor-pipe FLOPs actually issued (x3 in TF32X3 mode) and the launch count. */
+void fcuda_profile_tensor_gemm(int enable);
+int fcuda_profile_collect(double* total_ms, double* algo_flops, double* mma_flops, long long* launches);
+
+/* Number of kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
+unsigned long long fcuda_launch_count(void);
+void fcuda_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCUDA_H */

@@ -1,0 +1,42 @@
+/* feather_c.h — C ABI of the host-side feather::Net (libfeather_b200.so) for language bindings.
+ * Every function forwards to the C++ method of the same meaning in include/feather/net.h, which in turn mirrors
+ * /root/reference/src/net.h:30-70 and README.md:56-75.  Handles are opaque; ints are 0 / negative error codes. */
+#ifndef FEATHER_C_H
+#define FEATHER_C_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+void* fnet_create(void);                                         /* Net::Net(), net.cpp:31-39 */
+void fnet_destroy(void* net);
+void fnet_set_fusion(void* net, int enable);                     /* live TryFuse pass, layer.h:61-68 */
+void fnet_set_cuda_graph(void* net, int enable);
+void fnet_set_stream(void* net, void* cuda_stream);
+int fnet_load_param(void* net, const char* param_path);          /* Net::LoadParam, net.cpp:54-170 */
+int fnet_load_param_text(void* net, const char* param_text);     /* same grammar from memory */
+int fnet_load_weights(void* net, const char* bin_path);          /* Net::LoadWeights, net.cpp:172-230 */
+int fnet_init_from_path(void* net, const char* model_path);      /* README.md:60 */
+int fnet_init_from_buffer(void* net, const void* buf, size_t size); /* README.md:62 */
+int fnet_prepare_weight_arena(void* net);                        /* non-root ranks: lay out the arena, no file I/O */
+int fnet_weight_arena(void* net, float** device_ptr, size_t* floats);
+int fnet_attach_weights(void* net);                              /* after the arena was filled (NCCL broadcast) */
+int fnet_feed_input_batch(void* net, const char* input_name, const float* host_nchw, int n, int c, int h, int w);
+int fnet_feed_input_device(void* net, const char* input_name, const float* device_nchw, int n, int c, int h, int w);
+int fnet_forward(void* net);                                     /* Net::Forward, net.cpp:298-334 */
+int fnet_forward_batch(void* net, const float* host_nchw, int batch); /* README.md:65 with a batch */
+int fnet_synchronize(void* net);
+int fnet_blob_shape(void* net, const char* blob, int* n, int* c, int* h, int* w);
+int fnet_extract_blob(void* net, const char* blob, float* host_out);  /* README.md:69 */
+int fnet_extract_device(void* net, const char* blob, const float** device_ptr, int* n, int* c, int* h, int* w);
+unsigned long long fnet_launches_per_forward(void* net);
+int fnet_input_shape(void* net, int* c, int* h, int* w);
+size_t fnet_blob_names(void* net, char* buf, size_t cap);
+const char* fnet_input_name(void* net);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -90,7 +90,10 @@ static const float kG[8][3] = {
     {1.0f / 45, -1.0f / 90, 1.0f / 180},
     {0.0f, 0.0f, 1.0f}};
 
-/* U = G g G^T, winograd_kernels_F63.cpp:222-254 (naive_gemm_temp 8x3x3, transpose, 8x8x3). */
+/* U = G g G^T.  winograd_kernels_F63.cpp:222-254 computes mid = G g (naive_gemm_temp 8x3x3), transposes it
+ * and multiplies by G again, i.e. it stores bigBlock = G (G g)^T = U^T; its SSE input transform produces V^T to
+ * match.  Those storage orientations are private to the AVX backend (SURVEY.md §8 preamble); this restatement keeps
+ * the same arithmetic (same products, same fp32 summation order over k) in the textbook orientation. */
 static void kernel_transform(const float* g, float* U /*8x8*/) {
     float mid[8][3];
     for (int i = 0; i < 8; ++i)
@@ -102,12 +105,8 @@ static void kernel_transform(const float* g, float* U /*8x8*/) {
     for (int i = 0; i < 8; ++i)
         for (int j = 0; j < 8; ++j) {
             float s = 0.f;
-            for (int k = 0; k < 3; ++k) s += kG[i][k] * mid[j][k]; /* ktm x mid^T, then read transposed */
-            /* bigBlock = ktm(8x3) * outBlock(3x8) where outBlock = mid^T  => bigBlock[i][j] = sum_k G[i][k]*mid[j][k].
-             * The reference stores bigBlock row-major as the 8x8 tile: tile[i][j] = (G g^T ... ) — note this equals
-             * (G (G g)^T)[i][j] = (G g^T G^T)[i][j] = U^T-of-textbook; the matching input transform convention below
-             * keeps the pair consistent (the reference multiplies tile element-wise with V in the same index order). */
-            U[i * 8 + j] = s;
+            for (int k = 0; k < 3; ++k) s += kG[i][k] * mid[j][k]; /* bigBlock[i][j] of the reference */
+            U[j * 8 + i] = s;                                       /* == (G g G^T)[j][i] */
         }
 }
 
@@ -188,11 +187,7 @@ void oracle_conv_winograd_f63(const OracleConvParam* p, const float* input, cons
         for (int t = 0; t < nB; ++t) {
             float M[64];
             for (int e = 0; e < 64; ++e) M[e] = 0.f;
-            /* TensorGEMM, :518-757: M_e[oc,tile] = sum_ic U_e[oc,ic] * V_e[ic,tile].  U is stored as the
-             * reference stores it (row i from the first G product, see kernel_transform): the tile element
-             * pairing is U[i][j] <-> V[j][i]?  No: the reference loads "bigBlock" rows as the 16 4-float chunks
-             * d=0..15 exactly like V's row-major 8x8, so the pairing is element-for-element in row-major order
-             * and U (as computed) must therefore be read transposed relative to the textbook G g G^T. */
+            /* TensorGEMM, :518-757: M_e[oc,tile] = sum_ic U_e[oc,ic] * V_e[ic,tile], fp32, ic ascending. */
             for (int ic = 0; ic < IC; ++ic) {
                 const float* u = U + ((size_t)oc * IC + ic) * 64;
                 const float* v = V + ((size_t)ic * nB + t) * 64;

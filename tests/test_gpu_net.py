@@ -1,0 +1,131 @@
+"""Whole-net GPU parity: every named blob of feather::Net::Forward against the unmodified reference build
+(oracle/_ref, feather::Net of /root/reference) — or the oracle's interpreter when _ref is absent — at the
+north-star tolerance max|d|/max|ref| <= 1e-3 per blob (SURVEY.md §8d "Parity gate"); the measured figure for the
+default 3xTF32 path is ~1e-5 and is asserted at 2e-4."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _save(model_dir, name, **kw):
+    from feathercnn_b200.tools import modelgen
+    m = modelgen.ZOO[name](**kw)
+    return m, m.save(model_dir / name)
+
+
+def _cpu_net(oracle, param, binf):
+    if oracle.reference_available():
+        return oracle.ReferenceNet(param, binf)
+    return oracle.OracleNet(param, binf)
+
+
+def _gpu_net(param, binf, **kw):
+    from feathercnn_b200.net import Net
+    net = Net(**kw)
+    net.LoadParam(param)
+    net.LoadWeights(binf)
+    return net
+
+
+def _compare_all_blobs(oracle, m, param, binf, batch, tol, gpu_kw=None, blobs=None):
+    from feathercnn_b200.tools import modelgen
+    shape = m.shape["data"]
+    x = np.stack([modelgen.synthetic_input(shape, i) for i in range(batch)])
+    net = _gpu_net(param, binf, **(gpu_kw or {}))
+    net.Forward(x)
+    names = blobs or sorted(m.blobs)
+    got = {b: net.Extract(b) for b in names}
+    cpu = _cpu_net(oracle, param, binf)
+    worst = 0.0
+    for i in range(batch):
+        cpu.forward(x[i])
+        for b in names:
+            e = rel_err(got[b][i], cpu.extract(b))
+            worst = max(worst, e)
+            assert e < tol, (b, i, e)
+    return worst, net
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_mini_net_every_blob(cuda, oracle, model_dir, batch):
+    m, (param, binf) = _save(model_dir, "mini")
+    _compare_all_blobs(oracle, m, param, binf, batch, 2e-4)
+
+
+def test_single_conv_config1(cuda, oracle, model_dir):
+    """BASELINE.json configs[0]: 3x3 conv 64->64 on 56x56, Forward() numerics baseline."""
+    m, (param, binf) = _save(model_dir, "single_conv")
+    _compare_all_blobs(oracle, m, param, binf, 2, 2e-4)
+
+
+def test_fusion_and_graph_preserve_outputs(cuda, oracle, model_dir):
+    m, (param, binf) = _save(model_dir, "mini")
+    from feathercnn_b200.tools import modelgen
+    x = np.stack([modelgen.synthetic_input(m.shape["data"], i) for i in range(4)])
+    plain = _gpu_net(param, binf)
+    plain.Forward(x)
+    want = plain.Extract("prob")
+    fused = _gpu_net(param, binf, fusion=True)
+    fused.Forward(x)
+    assert fused.launches_per_forward < plain.launches_per_forward
+    np.testing.assert_allclose(fused.Extract("prob"), want, rtol=1e-5, atol=1e-7)
+    graph = _gpu_net(param, binf, fusion=True, cuda_graph=True)
+    for _ in range(3):  # eager warm-up, capture, replay
+        graph.Forward(x)
+        np.testing.assert_allclose(graph.Extract("prob"), want, rtol=1e-5, atol=1e-7)
+    graph.Forward(x[:2])  # shape change -> re-capture
+    np.testing.assert_allclose(graph.Extract("prob"), want[:2], rtol=1e-5, atol=1e-7)
+
+
+def test_readme_api_and_feathermodel_container(cuda, oracle, model_dir):
+    """README.md:56-75: InitFromPath / Forward(float*) / ExtractBlob / GetBlobDataSize."""
+    from feathercnn_b200.net import Net
+    from feathercnn_b200.tools import feathermodel, modelgen
+    m, (param, binf) = _save(model_dir, "mini")
+    fm = feathermodel.pack(param, binf, model_dir / "mini.feathermodel")
+    x = modelgen.synthetic_input(m.shape["data"], 0)
+    a = Net(); a.InitFromPath(fm); a.Forward(x)
+    b = Net(); b.InitFromPath(model_dir / "mini"); b.Forward(x)   # falls back to .param/.bin
+    c = Net(); c.InitFromBuffer(open(fm, "rb").read()); c.Forward(x)
+    pa, pb, pc = a.Extract("prob"), b.Extract("prob"), c.Extract("prob")
+    np.testing.assert_array_equal(pa, pb)
+    np.testing.assert_array_equal(pa, pc)
+    cpu = _cpu_net(oracle, param, binf)
+    cpu.forward(x)
+    assert rel_err(pa[0], cpu.extract("prob")) < 2e-4
+
+
+MODELS = [("vgg16", 2), ("resnet50", 2), ("mobilenet_v1", 2)]
+
+
+@pytest.mark.parametrize("name,batch", MODELS)
+def test_benchmark_models_every_blob(cuda, oracle, model_dir, name, batch):
+    """BASELINE.json configs[1-3] architectures at 224x224; all blobs, images 0..batch-1."""
+    m, (param, binf) = _save(model_dir, name)
+    worst, net = _compare_all_blobs(oracle, m, param, binf, batch, 1e-3)
+    print(f"{name}: worst blob rel err {worst:.2e}, launches/forward {net.launches_per_forward}")
+    assert worst < 2e-4
+
+
+@pytest.mark.parametrize("name", ["resnet50", "mobilenet_v1"])
+def test_benchmark_models_fused_final_output(cuda, oracle, model_dir, name):
+    m, (param, binf) = _save(model_dir, name)
+    _compare_all_blobs(oracle, m, param, binf, 1, 2e-4, gpu_kw=dict(fusion=True, cuda_graph=True), blobs=["prob"])
+
+
+def test_batch_independence_bit_identical(cuda, oracle, model_dir):
+    """§8(e): results do not depend on how a batch is split — image i of a batch of 6 equals the same image run
+    alone or in a shard of 3 (what two ranks of a sharded job would compute), bit for bit."""
+    from feathercnn_b200.tools import modelgen
+    m, (param, binf) = _save(model_dir, "mini")
+    x = np.stack([modelgen.synthetic_input(m.shape["data"], i) for i in range(6)])
+    net = _gpu_net(param, binf)
+    net.Forward(x)
+    full = net.Extract("prob")
+    net.Forward(x[3:])
+    np.testing.assert_array_equal(net.Extract("prob"), full[3:])
+    net.Forward(x[4:5])
+    np.testing.assert_array_equal(net.Extract("prob"), full[4:5])
