@@ -165,6 +165,7 @@ def main() -> None:
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--l2-chunk-mb", type=float, default=None)
+    ap.add_argument("--lean", action="store_true", help="profiling aid: device-resident leg only (no e2e / roofline / cpu legs)")
     args = ap.parse_args()
     if args.batch <= 0:
         args.batch = DEFAULT_BATCH[args.model]
@@ -250,6 +251,14 @@ def main() -> None:
         barrier()
         ms_dev = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop() if sampler else None
+
+        if args.lean:
+            if rank == 0:
+                print(json.dumps({"lean": True, "value": world * B * args.steps / (ms_dev * 1e-3),
+                                  "ms_per_step": ms_dev / args.steps, "launches_per_step": int(launches)}), flush=True)
+            if world > 1:
+                dist.destroy_process_group()
+            return
 
         # ---- end-to-end leg: pinned host input -> H2D -> Forward -> D2H of the result, every step -----------
         n, c, h, w = net.BlobShape(out_name)
