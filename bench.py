@@ -141,9 +141,11 @@ def run_reference(args, rank: int, world: int) -> None:
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * r["sec_per_forward_mean"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model}_{in_shape[1]}x{in_shape[2]}", "impl_detail":
-                   "unmodified FeatherCNN AVX build (oracle/_ref), 1 thread per process", "timed_steps_per_process":
-                   min(args.steps, 3)},
+        "config": {"workload": f"{args.model}_b{args.batch}_{in_shape[1]}x{in_shape[2]}", "batch_per_gpu": args.batch,
+                   "impl_detail": "unmodified FeatherCNN AVX build (oracle/_ref); the reference has no batch dimension "
+                                  "(src/blob.cpp:73) and is race-free only at 1 thread (src/net.cpp:38), so the batch is "
+                                  "run as independent single-image Forwards, one single-thread process per physical core",
+                   "timed_forwards_per_process": min(args.steps, 3)},
         "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": r["procs"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

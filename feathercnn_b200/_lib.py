@@ -59,6 +59,7 @@ def fcuda() -> ctypes.CDLL:
             "fcuda_get_l2_chunk_bytes": (sz, []),
             "fcuda_conv_assign_output_dim": (i, [P]),
             "fcuda_conv_select_algo": (i, [P, ctypes.POINTER(i)]),
+            "fcuda_conv_select_algo_tuned": (i, [P, ctypes.POINTER(i)]),
             "fcuda_conv_get_buffer_size": (i, [P, i, i, szp, szp]),
             "fcuda_conv_init": (i, [P, i, vp, vp, vp]),
             "fcuda_conv_forward": (i, [P, i, vp, vp, vp, vp, vp, i, vp]),

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "conv_direct.cuh"
+#include "conv_igemm.cuh"
 #include "depthwise.cuh"
 #include "layers.cuh"
 #include "pack.cuh"
@@ -27,7 +28,11 @@ int env_precision() {
 size_t env_chunk() {
     const char* e = getenv("FCUDA_L2_CHUNK_MB");
     if (e) return static_cast<size_t>(atof(e) * 1024.0 * 1024.0);
-    return static_cast<size_t>(48) << 20;
+    // Default: effectively one chunk per layer.  Measured on B200 (profiles/r01_sweep_chunk.log): VGG-16 b64 runs
+    // 25.9 / 14.7 / 12.5 / 11.4 ms per step at 12 / 48 / 192 MiB / unbounded — the intermediates do not stay
+    // L2-resident across the three kernels, so smaller chunks only add launches and tail effects.  The bound keeps
+    // the scratch pool finite for very large batches.
+    return static_cast<size_t>(8) << 30;
 }
 
 int g_precision = env_precision();
@@ -127,6 +132,18 @@ int make_plan(const FcudaConvParam* p, int algo, int batch, ConvPlan* plan) {
             pl.packed_floats = static_cast<size_t>(pl.np) * OC * pl.pg.Kp;
             return 0;
         }
+        case FCUDA_SGECONV: {
+            // implicit GEMM straight from NCHW: stride 1, 16-byte TMA strides (W % 4, IC % 4); a 1x1 layer is
+            // addressed as one H*W-long row so only H*W % 4 matters there
+            if (p->group != 1 || p->stride_h != 1 || p->stride_w != 1 || IC % 4 != 0) return -1;
+            const bool pointwise = p->kernel_h == 1 && p->kernel_w == 1 && p->pad_left == 0 && p->pad_right == 0 &&
+                                   p->pad_top == 0 && p->pad_bottom == 0;
+            if (pointwise ? (p->input_h * p->input_w) % 4 != 0 : p->input_w % 4 != 0) return -1;
+            pl.pg = pack_geom(p);
+            pl.scratch_floats = 0;
+            pl.packed_floats = static_cast<size_t>(pl.np) * OC * IC * p->kernel_h * p->kernel_w;
+            return 0;
+        }
         case FCUDA_DEPTHWISE: {
             if (p->group != IC || OC != IC) return -1;
             DwGeom& g = pl.dg;
@@ -138,8 +155,8 @@ int make_plan(const FcudaConvParam* p, int algo, int batch, ConvPlan* plan) {
             return 0;
         }
         default:
-            // SGECONV / WINOGRADF63FUSED: stubs or unselected in the reference's AVX dispatcher
-            // (avx/booster.cpp:105-118, 291-292); "This algo is not supported" => -1 (booster.cpp:349-353).
+            // WINOGRADF63FUSED: unselected in the reference's AVX dispatcher and crashing as wired
+            // (avx/booster.cpp:258, 291-292); "This algo is not supported" => -1 (booster.cpp:349-353).
             return -1;
     }
 }
@@ -201,6 +218,24 @@ int fcuda_conv_select_algo(const FcudaConvParam* p, int* algo) {
     return 0;
 }
 
+int fcuda_conv_select_algo_tuned(const FcudaConvParam* p, int* algo) {
+    int rc = fcuda_conv_select_algo(p, algo);
+    if (rc != 0 || *algo == FCUDA_DEPTHWISE) return rc;
+    ConvPlan probe;
+    if (make_plan(p, FCUDA_SGECONV, 1, &probe) != 0) return 0;  // keep the reference choice
+    const int IC = p->input_channels, OC = p->output_channels;
+    if (*algo == FCUDA_WINOGRADF63) {
+        // non-fused Winograd moves 64/36 x (2*in + out) through HBM; below ~128 channels on large images that traffic
+        // outweighs its 4.5x MMA saving and the single-kernel implicit GEMM wins
+        if (IC <= 128 && OC <= 128 && p->output_w >= 28) *algo = FCUDA_SGECONV;
+    } else if (*algo == FCUDA_IM2COL) {
+        // stride-1 layers the reference sends to im2col (1x1, 5x5, small images): no packed intermediate at all
+        const int ow = (p->kernel_h == 1 && p->kernel_w == 1) ? p->output_h * p->output_w : p->output_w;
+        if (ow >= 16) *algo = FCUDA_SGECONV;
+    }
+    return 0;
+}
+
 int fcuda_conv_get_buffer_size(const FcudaConvParam* p, int algo, int batch, size_t* scratch_floats,
                                size_t* packed_kernel_floats) {
     ConvPlan pl;
@@ -233,6 +268,12 @@ int fcuda_conv_init(const FcudaConvParam* p, int algo, float* packed, const floa
         case FCUDA_IM2COL: {
             const size_t plane = static_cast<size_t>(OC) * pl.pg.Kp;
             rc = pack_weights(d_raw, packed, pl.np == 2 ? packed + plane : nullptr, OC, pl.pg.K, pl.pg.Kp, s);
+            break;
+        }
+        case FCUDA_SGECONV: {
+            const int taps = p->kernel_h * p->kernel_w;
+            const size_t plane = static_cast<size_t>(OC) * IC * taps;
+            rc = conv_igemm_pack_weights(d_raw, packed, pl.np == 2 ? packed + plane : nullptr, OC, IC, taps, s);
             break;
         }
         case FCUDA_NAIVE:
@@ -307,6 +348,22 @@ int fcuda_conv_forward(const FcudaConvParam* p, int algo, float* output, const f
                 if ((rc = tensor_gemm(g, s))) return rc;
             }
             return 0;
+        }
+        case FCUDA_SGECONV: {
+            const int taps = p->kernel_h * p->kernel_w;
+            IgemmProblem g{};
+            g.input = input; g.w_hi = packed;
+            g.w_lo = pl.np == 2 ? packed + static_cast<size_t>(OC) * IC * taps : nullptr;
+            g.bias = b; g.output = output;
+            g.N = batch; g.IC = IC; g.OC = OC;
+            g.KH = p->kernel_h; g.KW = p->kernel_w; g.pad_top = p->pad_top; g.pad_left = p->pad_left;
+            if (taps == 1 && p->pad_top == 0 && p->pad_left == 0) {  // pointwise: one long row per image
+                g.H = 1; g.W = p->input_h * p->input_w; g.OH = 1; g.OW = p->output_h * p->output_w;
+            } else {
+                g.H = p->input_h; g.W = p->input_w; g.OH = p->output_h; g.OW = p->output_w;
+            }
+            g.planes = pl.np; g.relu = relu;
+            return conv_igemm_forward(g, s);
         }
         case FCUDA_NAIVE:
             return conv_direct(input, packed, b, output, pl.pg, OC, relu, batch, s);

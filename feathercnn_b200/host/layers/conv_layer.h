@@ -2,9 +2,12 @@
 // /root/reference/src/layers/conv_layer.h:26-194; same ncnn param ids, same call protocol into ConvBooster).
 #pragma once
 
+#include <cuda_runtime_api.h>
 #include <feather/booster.h>
 #include <feather/layer.h>
 #include <stdlib.h>
+
+#include <vector>
 
 namespace feather {
 inline namespace b200 {  // ABI tag: keeps these symbols apart from the reference build when both are loaded
@@ -15,7 +18,10 @@ public:
         : Layer(rt_param), bias_data(NULL), processed_kernel(NULL), processed_weights(NULL), init_algo(-1) {
         _fusible = true;
     }
-    ~ConvLayer() { delete processed_weights; }
+    ~ConvLayer() {
+        delete processed_weights;
+        delete folded_bias;
+    }
 
     int LoadParam(const ncnn::ParamDict& pd) {
         const int dilation_w = pd.get(2, 1);
@@ -88,7 +94,12 @@ public:
         conv_param.AssignOutputDim();
         const int batch = bottom_blob->num();
         tops[0]->ReshapeWithRealloc(batch, conv_param.output_channels, conv_param.output_h, conv_param.output_w);
-        int rc = conv_booster.SelectAlgo(&this->conv_param);
+        // FEATHER_ALGO_POLICY=reference keeps avx/booster.cpp:283-310 verbatim; default is the B200 cost model
+        static const bool reference_policy = [] {
+            const char* e = getenv("FEATHER_ALGO_POLICY");
+            return e && e[0] == 'r';
+        }();
+        int rc = reference_policy ? conv_booster.SelectAlgo(&this->conv_param) : conv_booster.SelectAlgoTuned(&this->conv_param);
         if (rc) return rc;
         if (const char* force = getenv("FEATHER_FORCE_CONV_ALGO")) {  // ForceSelectAlgo hook, avx/booster.cpp:313-317
             booster::ConvBooster forced;
@@ -112,10 +123,40 @@ public:
         if (!processed_weights) processed_weights = new Blob<float>(this->name + "_proc_weights");
         processed_weights->ReshapeWithRealloc(1, 1, 1, static_cast<int>(processed_kernel_size));
         if (!processed_weights->data() || !weights[0]->data()) return FEATHER_ERR_WEIGHTS;
-        rc = conv_booster.Init(&conv_param, processed_weights->data(), weights[0]->data(), stream());
+        const float* raw = weights[0]->data();
+        Blob<float> scaled_w(this->name + "_folded_weights");
+        if (!fold_mul.empty()) {
+            // BN/Scale folded into the filters: W'[oc] = W[oc] * mul[oc], b' = b * mul + add (exact algebra of
+            // y = s*(beta*(conv + b) + alpha) + t; what the reference's dead Fuse hooks were meant to reach).
+            const int oc = static_cast<int>(fold_mul.size());
+            const size_t per_oc = weights[0]->data_size() / oc;
+            Blob<float> mul_dev(this->name + "_fold_mul");
+            mul_dev.ReshapeWithRealloc(1, 1, 1, oc);
+            scaled_w.ReshapeWithRealloc(1, 1, 1, static_cast<int>(weights[0]->data_size()));
+            if (!mul_dev.data() || !scaled_w.data()) return FEATHER_ERR_CUDA;
+            if ((rc = mul_dev.CopyFromHost(fold_mul.data(), stream()))) return rc;
+            rc = fcuda_scale_forward(scaled_w.data(), raw, oc, per_oc, mul_dev.data(), NULL, 1, stream());
+            if (rc) return rc;
+            std::vector<float> b(oc, 0.f);
+            if (had_bias) {
+                if ((rc = weights[1]->CopyToHost(b.data(), stream()))) return rc;
+            }
+            for (int i = 0; i < oc; ++i) b[i] = b[i] * fold_mul[i] + fold_add[i];
+            if (!folded_bias) folded_bias = new Blob<float>(this->name + "_folded_bias");
+            folded_bias->ReshapeWithRealloc(1, 1, 1, oc);
+            if (!folded_bias->data()) return FEATHER_ERR_CUDA;
+            if ((rc = folded_bias->CopyFromHost(b.data(), stream()))) return rc;
+            raw = scaled_w.data();
+        }
+        rc = conv_booster.Init(&conv_param, processed_weights->data(), raw, stream());
         if (rc) return rc;
+        if (!fold_mul.empty()) {
+            // scaled_w / mul_dev are released when this scope ends: make sure the kernels reading them finished
+            if (cudaStreamSynchronize(static_cast<cudaStream_t>(stream())) != cudaSuccess) return FEATHER_ERR_CUDA;
+        }
         this->processed_kernel = processed_weights->data();
-        if (conv_param.bias_term) bias_data = this->weights[1]->data();
+        if (!fold_mul.empty()) bias_data = folded_bias->data();
+        else if (conv_param.bias_term) bias_data = this->weights[1]->data();
         init_algo = conv_booster.GetAlgo();
         return 0;
     }
@@ -127,12 +168,37 @@ public:
                                     bottoms[0]->num(), stream());
     }
 
-    int Fuse(Layer* next_layer) {  // conv_layer.h:174-185
+    int Fuse(Layer* next_layer) {  // conv_layer.h:174-185, extended to BatchNorm and Scale
+        if (conv_param.activation == booster::ReLU) return 0;  // the activation is always last
         if (next_layer->type.compare("ReLU") == 0) {
             conv_param.activation = booster::ReLU;
             return 1;
         }
-        return 0;
+        const bool is_bn = next_layer->type.compare("BatchNorm") == 0;
+        const bool is_scale = next_layer->type.compare("Scale") == 0;
+        if (!is_bn && !is_scale) return 0;
+        if (next_layer->weights.empty() || !next_layer->weights[0]->data()) return 0;
+        const int oc = static_cast<int>(next_layer->weights[0]->data_size());
+        if (oc != num_output) return 0;
+        std::vector<float> m(oc, 1.f), a(oc, 0.f);
+        if (is_bn) {  // weights = {alpha, beta}: y = beta*x + alpha (batchnorm_layer.h:70-75)
+            if (next_layer->weights.size() < 2 || !next_layer->weights[1]->data()) return 0;
+            if (next_layer->weights[0]->CopyToHost(a.data(), stream()) || next_layer->weights[1]->CopyToHost(m.data(), stream())) return 0;
+        } else {      // weights = {scale[, bias]}: y = x*scale + bias (scale_layer.h:75-86)
+            if (next_layer->weights[0]->CopyToHost(m.data(), stream())) return 0;
+            if (next_layer->weights.size() > 1 && next_layer->weights[1]->CopyToHost(a.data(), stream())) return 0;
+        }
+        if (fold_mul.empty()) {
+            fold_mul.assign(oc, 1.f);
+            fold_add.assign(oc, 0.f);
+            had_bias = conv_param.bias_term != 0;
+            conv_param.bias_term = 1;
+        }
+        for (int i = 0; i < oc; ++i) {
+            fold_add[i] = fold_add[i] * m[i] + a[i];
+            fold_mul[i] = fold_mul[i] * m[i];
+        }
+        return 1;
     }
 
     const booster::ConvParam& param() const { return conv_param; }
@@ -146,6 +212,11 @@ protected:
     Blob<float>* processed_weights;
     int init_algo;
     int num_output = 0;
+    // BN / Scale folding (Net::SetFusion): per-output-channel multiplier and offset applied at Init
+    std::vector<float> fold_mul, fold_add;
+    bool had_bias = false;
+    Blob<float>* folded_bias = NULL;
+
 };
 
 }  // inline namespace b200

@@ -25,7 +25,8 @@ extern "C" {
 enum FcudaConvAlgo {
     FCUDA_NAIVE = 0,            /* CUDA-core fp32 implicit GEMM (device-side second opinion) */
     FCUDA_IM2COL = 1,           /* pack kernel + tcgen05 TensorGEMM, bias/ReLU fused in the epilogue */
-    FCUDA_SGECONV = 2,          /* stub in the reference's AVX dispatcher; unsupported here too (-1) */
+    FCUDA_SGECONV = 2,          /* implicit GEMM straight from NCHW (TMA im2col addressing, no packed intermediate);
+                                   stride 1 only; a stub in the reference's AVX dispatcher (avx/booster.cpp:105-118) */
     FCUDA_DEPTHWISE = 3,        /* warp-shuffle stencil */
     FCUDA_WINOGRADF63 = 4,      /* F(6,3): input transform -> 64-way tcgen05 TensorGEMM -> output transform(+bias+ReLU) */
     FCUDA_WINOGRADF63FUSED = 5, /* not selected by the reference (avx/booster.cpp:291-292); unsupported (-1) */
@@ -63,8 +64,9 @@ enum FcudaPrecision { FCUDA_PRECISION_TF32X3 = 0, FCUDA_PRECISION_TF32 = 1 };
 int fcuda_set_precision(int precision);
 int fcuda_get_precision(void);
 
-/* Working-set target (bytes) for the Winograd / im2col intermediates so that they stay L2-resident
- * between the pack, TensorGEMM and unpack kernels (default 48 MiB of the 126 MB L2; 0 = one chunk). */
+/* Upper bound (bytes) on the Winograd / im2col intermediates of one chunk: a layer whose packed operands exceed it is
+ * processed in several pack -> TensorGEMM -> unpack rounds over the batch (default 8 GiB, i.e. one round for the
+ * benchmark configs — small L2-sized chunks measured slower on B200; 0 = never chunk). */
 int fcuda_set_l2_chunk_bytes(size_t bytes);
 size_t fcuda_get_l2_chunk_bytes(void);
 
@@ -73,6 +75,10 @@ int fcuda_conv_assign_output_dim(FcudaConvParam* param);
 
 /* ConvBooster::SelectAlgo, avx/booster.cpp:283-310 (same rule, same -1 for partial groups). */
 int fcuda_conv_select_algo(const FcudaConvParam* param, int* algo);
+
+/* B200 cost-model variant of SelectAlgo: starts from the reference rule and moves bandwidth-bound Winograd layers
+ * (<= 128 channels on images >= 28 wide) and stride-1 im2col layers to FCUDA_SGECONV.  Same return convention. */
+int fcuda_conv_select_algo_tuned(const FcudaConvParam* param, int* algo);
 
 /* GET_BUFFER_SIZE_FUNC, booster.h:151: scratch and processed-kernel sizes in floats for `batch` images. */
 int fcuda_conv_get_buffer_size(const FcudaConvParam* param, int algo, int batch, size_t* scratch_floats,

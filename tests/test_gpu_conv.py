@@ -88,12 +88,12 @@ def test_conv_matches_reference_build(cuda, oracle, reference, case):
     assert rel_err(got[0], want) < 2e-4, case[0]
 
 
-@pytest.mark.parametrize("algo_name", ["NAIVE", "IM2COL", "WINOGRADF63", "WINOGRADF23"])
+@pytest.mark.parametrize("algo_name", ["NAIVE", "IM2COL", "SGECONV", "WINOGRADF63", "WINOGRADF23"])
 def test_forced_algorithms_agree(cuda, oracle, restatement, algo_name):
     """ForceSelectAlgo (avx/booster.cpp:313-317): every algorithm computes the same convolution."""
     from feathercnn_b200 import booster
     booster.set_precision(booster.PRECISION_TF32X3)
-    case = ("forced", 48, 32, 21, 26, 3, 1, 1, 1, True, True)
+    case = ("forced", 48, 32, 21, 28, 3, 1, 1, 1, True, True)
     p, x, wt, b = _data(oracle, case, 2, seed=3)
     got, used = _gpu_conv(cuda, case, x, wt, b, algo=getattr(booster, algo_name))
     assert used == getattr(booster, algo_name)
@@ -106,12 +106,51 @@ def test_unsupported_algorithms_return_minus_one(cuda, oracle):
     from feathercnn_b200 import booster
     from feathercnn_b200._lib import fcuda
     p = booster.ConvParam.make(64, 64, 16, 16, 3, pad=1)
-    for algo in (booster.SGECONV, booster.WINOGRADF63FUSED):  # stubs / unselected upstream, avx/booster.cpp:105-118,291-292
-        s, k = ctypes.c_size_t(), ctypes.c_size_t()
-        assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), algo, 1, ctypes.byref(s), ctypes.byref(k)) == -1
+    s, k = ctypes.c_size_t(), ctypes.c_size_t()
+    # unselected and crashing upstream, avx/booster.cpp:258,291-292
+    assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), booster.WINOGRADF63FUSED, 1, ctypes.byref(s), ctypes.byref(k)) == -1
+    # the implicit GEMM is stride-1 only and needs 16-byte rows
+    for bad in (booster.ConvParam.make(64, 64, 16, 16, 3, stride=2, pad=1), booster.ConvParam.make(64, 64, 16, 18, 3, pad=1),
+                booster.ConvParam.make(64, 6, 16, 16, 3, pad=1)):
+        assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(bad), booster.SGECONV, 1, ctypes.byref(s), ctypes.byref(k)) == -1
     pg = booster.ConvParam.make(64, 64, 16, 16, 3, pad=1, group=4)  # partial groups: avx/booster.cpp:304-308
     a = ctypes.c_int()
     assert fcuda().fcuda_conv_select_algo(ctypes.byref(pg), ctypes.byref(a)) == -1
+
+
+SGECONV_CASES = [
+    # oc, ic, h, w, k, pad, bias, relu
+    (64, 64, 56, 56, 3, 1, True, True),      # VGG conv1_2 class (two boxes per row)
+    (128, 64, 28, 28, 3, 1, False, False),   # one 28-wide box per row, BN = 128
+    (64, 256, 28, 28, 1, 0, False, True),    # pointwise: addressed as one 784-long row
+    (36, 20, 12, 16, 3, 1, True, False),     # IC, OC not multiples of 32: TMA zero-fills the channel tail
+    (16, 8, 5, 224, 3, 1, True, True),       # 7 boxes per row, image wider than a tile
+    (24, 12, 15, 20, 5, 2, True, False),     # 5x5
+    (32, 32, 9, 12, 3, 0, True, False),      # no padding
+    (200, 64, 14, 16, 1, 0, True, False),    # OC > 128: two N tiles
+]
+
+
+@pytest.mark.parametrize("geom", SGECONV_CASES)
+@pytest.mark.parametrize("batch", [1, 3])
+def test_sgeconv_implicit_gemm(cuda, oracle, restatement, geom, batch):
+    """FCUDA_SGECONV: implicit GEMM from NCHW (TMA box addressing = im2col + zero padding), vs fp64 direct conv."""
+    from feathercnn_b200 import booster
+    booster.set_precision(booster.PRECISION_TF32X3)
+    oc, ic, h, w, k, pad, bias, relu = geom
+    case = ("sgeconv", oc, ic, h, w, k, 1, pad, 1, bias, relu)
+    p, x, wt, b = _data(oracle, case, batch, seed=13)
+    got, used = _gpu_conv(cuda, case, x, wt, b, algo=booster.SGECONV)
+    assert used == booster.SGECONV
+    for n in range(batch):
+        assert rel_err(got[n], restatement.conv(p, x[n], wt, b, f64=True)) < 2e-4, (geom, n)
+    booster.set_precision(booster.PRECISION_TF32)
+    try:
+        got1, _ = _gpu_conv(cuda, case, x, wt, b, algo=booster.SGECONV)
+    finally:
+        booster.set_precision(booster.PRECISION_TF32X3)
+    for n in range(batch):
+        assert rel_err(got1[n], restatement.conv(p, x[n], wt, b, f64=True)) < 2e-3, (geom, n)
 
 
 def test_plain_tf32_meets_north_star_bar_on_im2col(cuda, oracle, restatement):
@@ -133,14 +172,16 @@ def test_l2_chunking_is_invisible(cuda, oracle, restatement):
     case = ("chunk", 32, 32, 30, 30, 3, 1, 1, 1, True, False)
     p, x, wt, b = _data(oracle, case, 5, seed=9)
     outs = []
-    for chunk in (48 << 20, 1 << 18, 0):  # default, tiny (many chunks), single chunk
+    from feathercnn_b200._lib import fcuda
+    default = fcuda().fcuda_get_l2_chunk_bytes()
+    for chunk in (default, 1 << 18, 0):  # default (one chunk), tiny (many chunks), unbounded
         booster.set_l2_chunk_bytes(chunk)
         try:
             for algo in (booster.WINOGRADF63, booster.IM2COL):
                 got, _ = _gpu_conv(cuda, case, x, wt, b, algo=algo)
                 outs.append(got)
         finally:
-            booster.set_l2_chunk_bytes(48 << 20)
+            booster.set_l2_chunk_bytes(default)
     for i in (2, 4):
         np.testing.assert_array_equal(outs[i], outs[0])      # Winograd, any chunking: bit-identical
         np.testing.assert_array_equal(outs[i + 1], outs[1])  # im2col, any chunking: bit-identical

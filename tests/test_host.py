@@ -96,9 +96,34 @@ def test_workspace_planning_is_host_only_and_consistent():
         booster.set_precision(booster.PRECISION_TF32X3)
     # errors: partial groups / unsupported algorithms are -1 like avx/booster.cpp:304-308,349-353
     s, k = ctypes.c_size_t(), ctypes.c_size_t()
-    assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), booster.SGECONV, 1, ctypes.byref(s), ctypes.byref(k)) == -1
+    assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), booster.WINOGRADF63FUSED, 1, ctypes.byref(s), ctypes.byref(k)) == -1
+    assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), booster.SGECONV, 1, ctypes.byref(s), ctypes.byref(k)) == 0
+    assert s.value == 0 and k.value == 2 * 9 * 64 * 64   # implicit GEMM: no scratch, [tap][OC][IC] hi+lo
     assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), booster.WINOGRADF63, 0, ctypes.byref(s), ctypes.byref(k)) == -100
     assert fcuda().fcuda_pooling_out_dim(112, 0, 0, 3, 2) == 56
+
+
+def test_tuned_select_algo_moves_bandwidth_bound_layers():
+    """B200 cost model: VGG conv1_2/conv2_x and stride-1 pointwise layers go to the implicit GEMM; deep layers stay
+    on Winograd; everything the implicit GEMM cannot address keeps the reference choice."""
+    from feathercnn_b200 import booster
+    from feathercnn_b200._lib import fcuda
+
+    def tuned(*a, **kw):
+        p = booster.ConvParam.make(*a, **kw)
+        al = ctypes.c_int()
+        assert fcuda().fcuda_conv_select_algo_tuned(ctypes.byref(p), ctypes.byref(al)) == 0
+        return al.value
+
+    assert tuned(64, 64, 224, 224, 3, pad=1) == booster.SGECONV
+    assert tuned(128, 128, 112, 112, 3, pad=1) == booster.SGECONV
+    assert tuned(256, 256, 56, 56, 3, pad=1) == booster.WINOGRADF63
+    assert tuned(512, 512, 14, 14, 3, pad=1) == booster.WINOGRADF63
+    assert tuned(64, 3, 224, 224, 3, pad=1) == booster.IM2COL          # IC % 4 != 0
+    assert tuned(256, 64, 56, 56, 1) == booster.SGECONV                # ResNet pointwise
+    assert tuned(512, 256, 56, 56, 1, stride=2) == booster.IM2COL      # strided: reference choice
+    assert tuned(2048, 512, 7, 7, 1) == booster.IM2COL                 # 49 pixels: rows not 16-byte multiples
+    assert tuned(32, 32, 56, 56, 3, stride=1, pad=1, group=32) == booster.DEPTHWISE
 
 
 def _net():
