@@ -133,15 +133,11 @@ int make_plan(const FcudaConvParam* p, int algo, int batch, ConvPlan* plan) {
             return 0;
         }
         case FCUDA_SGECONV: {
-            // implicit GEMM straight from NCHW: stride 1, 16-byte TMA strides (W % 4, IC % 4); a 1x1 layer is
-            // addressed as one H*W-long row so only H*W % 4 matters there
-            if (p->group != 1 || p->stride_h != 1 || p->stride_w != 1 || IC % 4 != 0) return -1;
-            const bool pointwise = p->kernel_h == 1 && p->kernel_w == 1 && p->pad_left == 0 && p->pad_right == 0 &&
-                                   p->pad_top == 0 && p->pad_bottom == 0;
-            if (pointwise ? (p->input_h * p->input_w) % 4 != 0 : p->input_w % 4 != 0) return -1;
+            // implicit GEMM straight from NCHW: any kernel / stride / padding, group 1
+            if (p->group != 1) return -1;
             pl.pg = pack_geom(p);
             pl.scratch_floats = 0;
-            pl.packed_floats = static_cast<size_t>(pl.np) * OC * IC * p->kernel_h * p->kernel_w;
+            pl.packed_floats = conv_igemm_packed_floats(OC, IC, p->kernel_h * p->kernel_w, pl.np);
             return 0;
         }
         case FCUDA_DEPTHWISE: {
@@ -221,17 +217,15 @@ int fcuda_conv_select_algo(const FcudaConvParam* p, int* algo) {
 int fcuda_conv_select_algo_tuned(const FcudaConvParam* p, int* algo) {
     int rc = fcuda_conv_select_algo(p, algo);
     if (rc != 0 || *algo == FCUDA_DEPTHWISE) return rc;
-    ConvPlan probe;
-    if (make_plan(p, FCUDA_SGECONV, 1, &probe) != 0) return 0;  // keep the reference choice
     const int IC = p->input_channels, OC = p->output_channels;
     if (*algo == FCUDA_WINOGRADF63) {
         // non-fused Winograd moves 64/36 x (2*in + out) through HBM; below ~128 channels on large images that traffic
         // outweighs its 4.5x MMA saving and the single-kernel implicit GEMM wins
         if (IC <= 128 && OC <= 128 && p->output_w >= 28) *algo = FCUDA_SGECONV;
     } else if (*algo == FCUDA_IM2COL) {
-        // stride-1 layers the reference sends to im2col (1x1, 5x5, small images): no packed intermediate at all
-        const int ow = (p->kernel_h == 1 && p->kernel_w == 1) ? p->output_h * p->output_w : p->output_w;
-        if (ow >= 16) *algo = FCUDA_SGECONV;
+        // everything the reference sends to im2col + SGEMM (1x1, strided, 7x7, IC = 3, small images): gather the
+        // patches inside the GEMM instead of materialising them
+        *algo = FCUDA_SGECONV;
     }
     return 0;
 }
@@ -272,7 +266,7 @@ int fcuda_conv_init(const FcudaConvParam* p, int algo, float* packed, const floa
         }
         case FCUDA_SGECONV: {
             const int taps = p->kernel_h * p->kernel_w;
-            const size_t plane = static_cast<size_t>(OC) * IC * taps;
+            const size_t plane = conv_igemm_packed_floats(OC, IC, taps, 1);
             rc = conv_igemm_pack_weights(d_raw, packed, pl.np == 2 ? packed + plane : nullptr, OC, IC, taps, s);
             break;
         }
@@ -353,11 +347,13 @@ int fcuda_conv_forward(const FcudaConvParam* p, int algo, float* output, const f
             const int taps = p->kernel_h * p->kernel_w;
             IgemmProblem g{};
             g.input = input; g.w_hi = packed;
-            g.w_lo = pl.np == 2 ? packed + static_cast<size_t>(OC) * IC * taps : nullptr;
+            g.w_lo = pl.np == 2 ? packed + conv_igemm_packed_floats(OC, IC, taps, 1) : nullptr;
             g.bias = b; g.output = output;
             g.N = batch; g.IC = IC; g.OC = OC;
             g.KH = p->kernel_h; g.KW = p->kernel_w; g.pad_top = p->pad_top; g.pad_left = p->pad_left;
-            if (taps == 1 && p->pad_top == 0 && p->pad_left == 0) {  // pointwise: one long row per image
+            g.stride_h = p->stride_h; g.stride_w = p->stride_w;
+            if (taps == 1 && p->pad_top == 0 && p->pad_left == 0 && p->stride_h == 1 && p->stride_w == 1) {
+                // pointwise stride 1: address each image as one H*W-long row (fuller 32-pixel boxes)
                 g.H = 1; g.W = p->input_h * p->input_w; g.OH = 1; g.OW = p->output_h * p->output_w;
             } else {
                 g.H = p->input_h; g.W = p->input_w; g.OH = p->output_h; g.OW = p->output_w;

@@ -25,8 +25,8 @@ extern "C" {
 enum FcudaConvAlgo {
     FCUDA_NAIVE = 0,            /* CUDA-core fp32 implicit GEMM (device-side second opinion) */
     FCUDA_IM2COL = 1,           /* pack kernel + tcgen05 TensorGEMM, bias/ReLU fused in the epilogue */
-    FCUDA_SGECONV = 2,          /* implicit GEMM straight from NCHW (TMA im2col addressing, no packed intermediate);
-                                   stride 1 only; a stub in the reference's AVX dispatcher (avx/booster.cpp:105-118) */
+    FCUDA_SGECONV = 2,          /* implicit GEMM straight from NCHW: patches gathered inside the tcgen05 kernel, no packed
+                                   intermediate; a stub in the reference's AVX dispatcher (avx/booster.cpp:105-118) */
     FCUDA_DEPTHWISE = 3,        /* warp-shuffle stencil */
     FCUDA_WINOGRADF63 = 4,      /* F(6,3): input transform -> 64-way tcgen05 TensorGEMM -> output transform(+bias+ReLU) */
     FCUDA_WINOGRADF63FUSED = 5, /* not selected by the reference (avx/booster.cpp:291-292); unsupported (-1) */
@@ -77,7 +77,7 @@ int fcuda_conv_assign_output_dim(FcudaConvParam* param);
 int fcuda_conv_select_algo(const FcudaConvParam* param, int* algo);
 
 /* B200 cost-model variant of SelectAlgo: starts from the reference rule and moves bandwidth-bound Winograd layers
- * (<= 128 channels on images >= 28 wide) and stride-1 im2col layers to FCUDA_SGECONV.  Same return convention. */
+ * (<= 128 channels on images >= 28 wide) and the im2col layers to FCUDA_SGECONV.  Same return convention. */
 int fcuda_conv_select_algo_tuned(const FcudaConvParam* param, int* algo);
 
 /* GET_BUFFER_SIZE_FUNC, booster.h:151: scratch and processed-kernel sizes in floats for `batch` images. */

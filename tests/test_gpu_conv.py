@@ -109,36 +109,40 @@ def test_unsupported_algorithms_return_minus_one(cuda, oracle):
     s, k = ctypes.c_size_t(), ctypes.c_size_t()
     # unselected and crashing upstream, avx/booster.cpp:258,291-292
     assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), booster.WINOGRADF63FUSED, 1, ctypes.byref(s), ctypes.byref(k)) == -1
-    # the implicit GEMM is stride-1 only and needs 16-byte rows
-    for bad in (booster.ConvParam.make(64, 64, 16, 16, 3, stride=2, pad=1), booster.ConvParam.make(64, 64, 16, 18, 3, pad=1),
-                booster.ConvParam.make(64, 6, 16, 16, 3, pad=1)):
-        assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(bad), booster.SGECONV, 1, ctypes.byref(s), ctypes.byref(k)) == -1
+    # grouped (non-depthwise) convolution is unsupported by every algorithm, like upstream
+    bad = booster.ConvParam.make(64, 64, 16, 16, 3, pad=1, group=4)
+    for algo in (booster.SGECONV, booster.IM2COL, booster.WINOGRADF63, booster.DEPTHWISE):
+        assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(bad), algo, 1, ctypes.byref(s), ctypes.byref(k)) == -1
     pg = booster.ConvParam.make(64, 64, 16, 16, 3, pad=1, group=4)  # partial groups: avx/booster.cpp:304-308
     a = ctypes.c_int()
     assert fcuda().fcuda_conv_select_algo(ctypes.byref(pg), ctypes.byref(a)) == -1
 
 
 SGECONV_CASES = [
-    # oc, ic, h, w, k, pad, bias, relu
-    (64, 64, 56, 56, 3, 1, True, True),      # VGG conv1_2 class (two boxes per row)
-    (128, 64, 28, 28, 3, 1, False, False),   # one 28-wide box per row, BN = 128
-    (64, 256, 28, 28, 1, 0, False, True),    # pointwise: addressed as one 784-long row
-    (36, 20, 12, 16, 3, 1, True, False),     # IC, OC not multiples of 32: TMA zero-fills the channel tail
-    (16, 8, 5, 224, 3, 1, True, True),       # 7 boxes per row, image wider than a tile
-    (24, 12, 15, 20, 5, 2, True, False),     # 5x5
-    (32, 32, 9, 12, 3, 0, True, False),      # no padding
-    (200, 64, 14, 16, 1, 0, True, False),    # OC > 128: two N tiles
+    # oc, ic, h, w, k, stride, pad, bias, relu
+    (64, 64, 56, 56, 3, 1, 1, True, True),      # VGG conv1_2 class (two boxes per row)
+    (128, 64, 28, 28, 3, 1, 1, False, False),   # one 28-wide box per row, BN = 128
+    (64, 256, 28, 28, 1, 1, 0, False, True),    # pointwise: addressed as one 784-long row
+    (36, 20, 12, 17, 3, 1, 1, True, False),     # IC, OC not multiples of 32, odd width
+    (16, 8, 5, 224, 3, 1, 1, True, True),       # 7 boxes per row, image wider than a tile
+    (24, 12, 15, 20, 5, 1, 2, True, False),     # 5x5
+    (32, 32, 9, 12, 3, 1, 0, True, False),      # no padding
+    (200, 64, 14, 16, 1, 1, 0, True, False),    # OC > 128: two N tiles
+    (64, 3, 64, 64, 7, 2, 3, True, False),      # ResNet conv1 class: 7x7 stride 2, IC = 3 (padded to 4)
+    (32, 32, 17, 19, 3, 2, 1, True, True),      # 3x3 stride 2, odd sizes
+    (128, 64, 28, 28, 1, 2, 0, False, False),   # strided pointwise (ResNet downsample)
+    (16, 2048, 7, 7, 1, 1, 0, True, False),     # deep K (64 channel blocks), 49-pixel images
 ]
 
 
 @pytest.mark.parametrize("geom", SGECONV_CASES)
 @pytest.mark.parametrize("batch", [1, 3])
 def test_sgeconv_implicit_gemm(cuda, oracle, restatement, geom, batch):
-    """FCUDA_SGECONV: implicit GEMM from NCHW (TMA box addressing = im2col + zero padding), vs fp64 direct conv."""
+    """FCUDA_SGECONV: implicit GEMM from NCHW (patches gathered inside the tcgen05 kernel), vs fp64 direct conv."""
     from feathercnn_b200 import booster
     booster.set_precision(booster.PRECISION_TF32X3)
-    oc, ic, h, w, k, pad, bias, relu = geom
-    case = ("sgeconv", oc, ic, h, w, k, 1, pad, 1, bias, relu)
+    oc, ic, h, w, k, stride, pad, bias, relu = geom
+    case = ("sgeconv", oc, ic, h, w, k, stride, pad, 1, bias, relu)
     p, x, wt, b = _data(oracle, case, batch, seed=13)
     got, used = _gpu_conv(cuda, case, x, wt, b, algo=booster.SGECONV)
     assert used == booster.SGECONV

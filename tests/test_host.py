@@ -104,8 +104,8 @@ def test_workspace_planning_is_host_only_and_consistent():
 
 
 def test_tuned_select_algo_moves_bandwidth_bound_layers():
-    """B200 cost model: VGG conv1_2/conv2_x and stride-1 pointwise layers go to the implicit GEMM; deep layers stay
-    on Winograd; everything the implicit GEMM cannot address keeps the reference choice."""
+    """B200 cost model: VGG conv1_2/conv2_x and every layer the reference sends to im2col go to the implicit GEMM;
+    deep 3x3 layers stay on Winograd F(6,3); depthwise stays depthwise."""
     from feathercnn_b200 import booster
     from feathercnn_b200._lib import fcuda
 
@@ -119,10 +119,11 @@ def test_tuned_select_algo_moves_bandwidth_bound_layers():
     assert tuned(128, 128, 112, 112, 3, pad=1) == booster.SGECONV
     assert tuned(256, 256, 56, 56, 3, pad=1) == booster.WINOGRADF63
     assert tuned(512, 512, 14, 14, 3, pad=1) == booster.WINOGRADF63
-    assert tuned(64, 3, 224, 224, 3, pad=1) == booster.IM2COL          # IC % 4 != 0
+    assert tuned(64, 3, 224, 224, 3, pad=1) == booster.SGECONV         # reference: IM2COL (IC % 4 != 0)
     assert tuned(256, 64, 56, 56, 1) == booster.SGECONV                # ResNet pointwise
-    assert tuned(512, 256, 56, 56, 1, stride=2) == booster.IM2COL      # strided: reference choice
-    assert tuned(2048, 512, 7, 7, 1) == booster.IM2COL                 # 49 pixels: rows not 16-byte multiples
+    assert tuned(512, 256, 56, 56, 1, stride=2) == booster.SGECONV     # strided downsample
+    assert tuned(64, 3, 224, 224, 7, stride=2, pad=3) == booster.SGECONV
+    assert tuned(512, 512, 7, 7, 3, pad=1) == booster.SGECONV          # reference: IM2COL (input_h <= 8)
     assert tuned(32, 32, 56, 56, 3, stride=1, pad=1, group=32) == booster.DEPTHWISE
 
 
