@@ -2,24 +2,27 @@
 //
 // Replaces the idea of the reference's SGECONV algorithm (/root/reference/src/booster/arm/sgeconv.cpp:1311-1856,
 // "packs B directly from the padded input, no materialised im2col"; a stub in the AVX dispatcher,
-// avx/booster.cpp:105-118) with a Blackwell formulation that has NO intermediate in HBM at all:
+// avx/booster.cpp:105-118) and of im2col + packed SGEMM (avx/booster.cpp:83-102) with a Blackwell formulation that
+// has NO intermediate in HBM and not even an A tile in shared memory:
 //
-//   D[pixel][oc] = sum_{tap=(u,v)} sum_{ic}  X[n][ic][oy*s+u-pad][ox*s+v-pad] * W[oc][ic][u][v]
+//   D[pixel][oc] = sum_k  A[pixel][k] * Wp[oc][k],    k = (u*KW + v)*IC + ic,
+//   A[pixel][k]  = X[n][ic][oy*s+u-pad][ox*s+v-pad]   (0 outside the image: the im2col rule, generic_kernels.cpp:66-67)
 //
-//   M tile     = 128 output pixels = four 32-pixel row segments ("boxes", consecutive in (n, oy, ox/32) order).
-//   A operand  = gathered by 16 producer warps directly from the input (coalesced along x, zero padding and stride by
-//                index arithmetic — the im2col rule of generic_kernels.cpp:66-67), split on the fly into TF32 hi and
-//                fp32 lo and stored as 16-byte vectors into shared memory in the canonical MN-major UMMA layout for
-//                32-bit operands (128-byte rows of 32 pixels per channel, 32-byte-chunk swizzle, layout type
-//                SWIZZLE_128B_BASE32B).  TMA cannot do this gather: its innermost box coordinate must be 16-byte
-//                aligned, and a 3x3 tap shifts x by one float (measured: illegal-instruction trap).
-//   B operand  = filters re-packed once at Init to Wp[tap][oc][ic] (K-major rows), TF32 hi / fp32 lo planes, by TMA.
-//   MMA        = one thread issues tcgen05.mma kind::tf32 (A MN-major, B K-major), 3 MMAs per k-step in 3xTF32 mode,
-//                fp32 accumulators in a 2-deep TMEM ring.
+//   M tile     = 128 output pixels = four 32-pixel row segments ("boxes", consecutive in (n, oy, ox/32) order);
+//                pixel <-> TMEM lane.
+//   A operand  = lives in TENSOR MEMORY.  Twelve producer warps (3 groups x 4; group g serves every third k-block) each
+//                own 32 pixels (= their TMEM lane quadrant): a thread gathers the 32 k-values of its pixel (loads
+//                coalesced across lanes along x; offsets and tap coordinates come from a small shared-memory table,
+//                validity from per-pixel row/column bit masks), splits them into TF32 hi + fp32 lo and writes them with
+//                tcgen05.st.  (TMA cannot gather: its innermost box coordinate must be 16-byte aligned — a +-1 pixel
+//                tap shift traps; an A tile in shared memory costs 3x the instructions and all of the smem bandwidth.)
+//   B operand  = filters re-packed once at Init to Wp[oc][k] (K-major), TF32 hi / fp32 lo planes, loaded by TMA.
+//   MMA        = one thread issues tcgen05.mma kind::tf32 with A from TMEM ("TS" form), 3 MMAs per k-step in 3xTF32
+//                mode, fp32 accumulators in a 2-deep TMEM ring next to the 4-deep A ring.
 //   epilogue   = tcgen05.ld -> +bias -> ReLU -> NCHW store; lanes hold consecutive pixels -> 128-byte coalesced rows.
 //
-// Used where non-fused Winograd is bandwidth-bound (large images, <= 128 channels) and for the layers the reference
-// sends to im2col + SGEMM (1x1, strided, 5x5/7x7).
+// Used where non-fused Winograd is bandwidth-bound (large images, <= 128 channels) and for every layer the reference
+// sends to im2col + SGEMM (1x1, strided, 7x7, IC = 3).
 #include "conv_igemm.cuh"
 
 #include "common.cuh"
@@ -29,10 +32,10 @@ namespace fcuda {
 
 namespace {
 
-constexpr int kProducerWarps = 16;  // two groups of 8: group g gathers the k-blocks whose running index has parity g
-constexpr int kThreadsIg = (8 + kProducerWarps) * 32;  // warp 0 TMA(B), warp 1 MMA, warps 4-7 epilogue, 8.. producers
-constexpr int kABox = 32 * 32 * 4;      // one 32-pixel box: 32 channel rows of 128 bytes = 4 KB
-constexpr int kATileBytes = 4 * kABox;  // 128 pixels x 32 channels = 16 KB
+constexpr int kGroups = 3;                                // producer groups, 4 warps (128 pixels) each
+constexpr int kThreadsIg = (8 + 4 * kGroups) * 32;        // warp 0 TMA(B), 1 MMA, 4-7 epilogue, 8.. producers
+constexpr int kStagesIg = 4;                              // ring depth shared by the smem B tiles and the TMEM A tiles
+constexpr int kMaxTableK = 8192;                          // k-table entries that fit beside the B ring
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -56,27 +59,15 @@ struct IgemmArgs {
     const float* bias;
     int N, IC, H, W, OC, OH, OW;
     int KH, KW, pad_top, pad_left, stride_h, stride_w;
+    int K;                   // KH*KW*IC
+    int kblocks;             // ceil(K / 32)
+    int use_table;           // 0 => pointwise (k == ic), offsets computed arithmetically
     int bpr;                 // 32-pixel boxes per output row
     long long total_boxes;   // N * OH * bpr
-    int cblocks;             // ceil(IC / 32)
     int num_n;               // ceil(OC / BN)
     long long pixel_tiles;   // ceil(total_boxes / 4)
     int relu;
 };
-
-// MN-major 32-bit operand.  tcgen05 accepts only one shared-memory layout for MN-major tf32: 128-byte rows of 32 MN
-// elements swizzled in 32-byte chunks ("SWIZZLE_128B_BASE32B", layout type 1, Swizzle<2,5,2>: byte-offset bits [5,7)
-// ^= bits [7,9)), atoms of 32 MN x 4 K rows (512 B).  LBO = byte stride between atoms along MN (one 4 KB box),
-// SBO = byte stride between 4-row K groups (512 B).  Verified on B200 against TMA's SWIZZLE_128B_ATOM_32B tiles.
-__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
-    d |= static_cast<uint64_t>(1) << 61;  // SWIZZLE_128B_BASE32B
-    return d;
-}
 
 struct BoxCoord { int n, oy, ox0; bool valid; };
 
@@ -92,18 +83,48 @@ __device__ __forceinline__ BoxCoord decode_box(long long b, const IgemmArgs& a) 
     return c;
 }
 
-template <int BN, int PLANES, int STAGES>
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int BN, int PLANES>
 __global__ void __launch_bounds__(kThreadsIg, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
                   const IgemmArgs args) {
+    constexpr int STAGES = kStagesIg;
     constexpr int kBTile = BN * 32 * 4;
-    constexpr int kStage = PLANES * (kATileBytes + kBTile);
-    // stage layout: [A_hi][B_hi][A_lo][B_lo]
+    constexpr int kStage = PLANES * kBTile;                 // smem per stage: [B_hi][B_lo]
+    constexpr uint32_t kAccCols = 2 * BN;                   // accumulator ring
+    constexpr uint32_t kAStageCols = 32 * PLANES;           // [A_hi (32 cols)][A_lo (32 cols)]
+    constexpr uint32_t kNeedCols = kAccCols + STAGES * kAStageCols;
+    constexpr uint32_t kTmemCols = kNeedCols <= 32 ? 32 : kNeedCols <= 64 ? 64 : kNeedCols <= 128 ? 128 : kNeedCols <= 256 ? 256 : 512;
+    static_assert(kNeedCols <= 512, "TMEM budget");
+
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    int2* ktab = reinterpret_cast<int2*>(smem + STAGES * kStage);  // {element offset, (u << 16) | v} per k
 
     __shared__ uint64_t b_full_bar[STAGES];   // filters landed (TMA transaction bytes)
-    __shared__ uint64_t a_ready_bar[STAGES];  // 8 producer warps finished the gathered A tile
+    __shared__ uint64_t a_ready_bar[STAGES];  // the 4 producer warps of the owning group stored their TMEM quadrant
     __shared__ uint64_t empty_bar[STAGES];    // MMAs that read the stage have retired
     __shared__ uint64_t tmem_full_bar[2];
     __shared__ uint64_t tmem_empty_bar[2];
@@ -112,13 +133,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const long long total_tiles = args.pixel_tiles * args.num_n;
-    const int taps = args.KH * args.KW;
-    const int kblocks = args.cblocks * taps;
+    const int kblocks = args.kblocks;
+    const int plane = args.H * args.W;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&b_full_bar[s], 1);
-            ptx::mbar_init(&a_ready_bar[s], 8);
+            ptx::mbar_init(&a_ready_bar[s], 4);
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -131,7 +152,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         ptx::prefetch_tensormap(&tmW);
         if (PLANES == 2) ptx::prefetch_tensormap(&tmWlo);
     }
-    constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    if (args.use_table) {
+        for (int k = threadIdx.x; k < kblocks * 32; k += kThreadsIg) {
+            int2 e = make_int2(0, 0x7fff7fff);  // padding rows: coordinates no mask bit can satisfy
+            if (k < args.K) {
+                const int tap = k / args.IC, ic = k - tap * args.IC;
+                const int u = tap / args.KW, v = tap - u * args.KW;
+                e = make_int2(ic * plane + u * args.W + v, (u << 16) | v);
+            }
+            ktab[k] = e;
+        }
+    }
     if (warp == 1) {
         ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
         ptx::tmem_relinquish();
@@ -140,6 +171,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t tmem_a0 = tmem_base + kAccCols;
 
     if (warp == 0) {
         // ===================== TMA producer for the filter tiles =====================
@@ -148,23 +180,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_blk = static_cast<int>(tile % args.num_n);
-                for (int cb = 0; cb < args.cblocks; ++cb) {
-                    for (int tap = 0; tap < taps; ++tap) {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* st = smem + stage * kStage;
-                        ptx::mbar_arrive_expect_tx(&b_full_bar[stage], PLANES * kBTile);
-                        ptx::tma_load_3d(st + kATileBytes, &tmW, &b_full_bar[stage], cb * 32, n_blk * BN, tap);
-                        if (PLANES == 2)
-                            ptx::tma_load_3d(st + 2 * kATileBytes + kBTile, &tmWlo, &b_full_bar[stage], cb * 32, n_blk * BN, tap);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                    }
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * kStage;
+                    ptx::mbar_arrive_expect_tx(&b_full_bar[stage], PLANES * kBTile);
+                    ptx::tma_load_3d(st, &tmW, &b_full_bar[stage], kb * 32, n_blk * BN, 0);
+                    if (PLANES == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, &b_full_bar[stage], kb * 32, n_blk * BN, 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(BN) | (1u << 15);  // A is MN-major
+            constexpr uint32_t idesc = make_idesc_tf32(BN);
             int stage = 0;
             uint32_t phase = 0;
             long long it = 0;
@@ -179,20 +208,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     ptx::mbar_wait(&b_full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t st = ptx::smem_u32(smem + stage * kStage);
-                    const uint64_t dB = make_smem_desc_sw128(st + kATileBytes);
-                    const uint64_t dBlo = make_smem_desc_sw128(st + 2 * kATileBytes + kBTile);
+                    const uint64_t dB = make_smem_desc_sw128(st);
+                    const uint64_t dBlo = make_smem_desc_sw128(st + kBTile);
+                    const uint32_t ta = tmem_a0 + stage * kAStageCols;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // 8 channels per MMA = two 4-row K groups = 1 KB
-                        const uint64_t dA = make_smem_desc_mn_sw128(st + k * 1024, kABox, 512);
-                        const uint64_t dAlo = make_smem_desc_mn_sw128(st + kATileBytes + kBTile + k * 1024, kABox, 512);
+                    for (int k = 0; k < 4; ++k) {  // 8 k-values (TMEM columns) per MMA
                         const uint64_t koff = static_cast<uint64_t>(k * 2);  // B: +32 bytes inside the swizzle atom
                         const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
                         if (PLANES == 2) {
-                            ptx::umma_tf32(tmem_d, dAlo, dB + koff, idesc, first);
-                            ptx::umma_tf32(tmem_d, dA, dBlo + koff, idesc, 1u);
-                            ptx::umma_tf32(tmem_d, dA, dB + koff, idesc, 1u);
+                            umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + koff, idesc, first);   // A_lo * B_hi
+                            umma_tf32_ts(tmem_d, ta + k * 8, dBlo + koff, idesc, 1u);         // A_hi * B_lo
+                            umma_tf32_ts(tmem_d, ta + k * 8, dB + koff, idesc, 1u);           // A_hi * B_hi
                         } else {
-                            ptx::umma_tf32(tmem_d, dA, dB + koff, idesc, first);
+                            umma_tf32_ts(tmem_d, ta + k * 8, dB + koff, idesc, first);
                         }
                     }
                     ptx::umma_commit(&empty_bar[stage]);
@@ -202,65 +230,77 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             }
         }
     } else if (warp >= 8) {
-        // ===================== A producers: im2col gather + 3xTF32 split into UMMA MN-major tiles =====================
+        // ===================== A producers: gather + 3xTF32 split -> tensor memory =====================
         const int pw = warp - 8;
-        const int group = pw >> 3;  // 0 / 1: which k-block parity this warp serves
-        const int wsub = pw & 7;    // channels wsub*4 .. wsub*4+3 of the 32-channel block
-        const int q = lane >> 3;    // box (32-pixel segment) of this lane's 4 pixels
-        const int xb = (lane & 7) * 4;  // first of the lane's 4 consecutive pixels inside the box
-        const size_t plane = static_cast<size_t>(args.H) * args.W;
+        const int group = pw >> 2;
+        const int q = warp & 3;  // TMEM lane quadrant this warp may write == box index inside the tile
+        const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
         long long g = 0;  // running k-block index over all tiles of this CTA
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const long long ptile = tile / args.num_n;
             const BoxCoord bx = decode_box(ptile * 4 + q, args);
+            const int ox = bx.ox0 + lane;
+            const bool pix_ok = bx.valid && ox < args.OW;
             const int iy0 = bx.oy * args.stride_h - args.pad_top;
-            const int ix0 = (bx.ox0 + xb) * args.stride_w - args.pad_left;
-            const float* img = args.in + static_cast<size_t>(bx.valid ? bx.n : 0) * args.IC * plane;
-            for (int cb = 0; cb < args.cblocks; ++cb) {
-                for (int tap = 0; tap < taps; ++tap, ++g) {
-                    if ((g & 1) != group) continue;
-                    const int stage = static_cast<int>(g % STAGES);
-                    const uint32_t phase = static_cast<uint32_t>((g / STAGES) & 1);
-                    const int u = tap / args.KW, v = tap - u * args.KW;
-                    const int iy = iy0 + u;
-                    const bool row_ok = bx.valid && iy >= 0 && iy < args.H;
-                    float x[4][4];
+            const int ix0 = ox * args.stride_w - args.pad_left;
+            uint32_t rowmask = 0, colmask = 0;  // bit u / v set <=> that tap row / column lies inside the image
+            if (pix_ok) {
+                for (int u = 0; u < args.KH; ++u) rowmask |= (iy0 + u >= 0 && iy0 + u < args.H) ? (1u << u) : 0u;
+                for (int v = 0; v < args.KW; ++v) colmask |= (ix0 + v >= 0 && ix0 + v < args.W) ? (1u << v) : 0u;
+            }
+            const float* base = args.in + (static_cast<long long>(bx.valid ? bx.n : 0) * args.IC) * plane +
+                                static_cast<long long>(iy0) * args.W + ix0;
+            for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                if (static_cast<int>(g % kGroups) != group) continue;
+                const int stage = static_cast<int>(g % STAGES);
+                const uint32_t phase = static_cast<uint32_t>((g / STAGES) & 1);
+                const uint32_t ta = tmem_a0 + lane_base + stage * kAStageCols;
+                bool waited = false;
 #pragma unroll
-                    for (int ci = 0; ci < 4; ++ci) {
-                        const int c = cb * 32 + wsub * 4 + ci;
-                        const float* rp = img + static_cast<size_t>(c) * plane + static_cast<size_t>(iy) * args.W;
-                        const bool c_ok = row_ok && c < args.IC;
+                for (int half = 0; half < 2; ++half) {
+                    float x[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int ix = ix0 + j * args.stride_w + v;
-                            x[ci][j] = (c_ok && ix >= 0 && ix < args.W) ? __ldg(rp + ix) : 0.f;
-                        }
-                    }
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // loads are in flight while the slot drains
-                    uint8_t* st = smem + stage * kStage;
-#pragma unroll
-                    for (int ci = 0; ci < 4; ++ci) {
-                        const int cl = wsub * 4 + ci;  // channel row inside the 32-channel block
-                        // row cl of box q: 128 bytes; 32-byte chunk index swizzled with (row & 3)
-                        const uint32_t off = static_cast<uint32_t>(q) * kABox + static_cast<uint32_t>(cl) * 128 +
-                                             ((static_cast<uint32_t>(xb >> 3) ^ (cl & 3)) << 5) + ((xb & 7) << 2);
-                        if (PLANES == 2) {
-                            float4 h, l;
-                            split_tf32(x[ci][0], h.x, l.x);
-                            split_tf32(x[ci][1], h.y, l.y);
-                            split_tf32(x[ci][2], h.z, l.z);
-                            split_tf32(x[ci][3], h.w, l.w);
-                            *reinterpret_cast<float4*>(st + off) = h;
-                            *reinterpret_cast<float4*>(st + kATileBytes + kBTile + off) = l;
+                    for (int r = 0; r < 16; ++r) {
+                        const int k = kb * 32 + half * 16 + r;
+                        int off;
+                        bool ok;
+                        if (args.use_table) {
+                            const int2 e = ktab[k];
+                            off = e.x;
+                            ok = ((rowmask >> (e.y >> 16)) & (colmask >> (e.y & 0xffff)) & 1u) != 0;
                         } else {
-                            *reinterpret_cast<float4*>(st + off) = make_float4(x[ci][0], x[ci][1], x[ci][2], x[ci][3]);
+                            off = k * plane;
+                            ok = pix_ok && k < args.K;
                         }
+                        x[r] = ok ? __ldg(base + off) : 0.f;
                     }
-                    // make the generic-proxy writes visible to the tensor core's async-proxy reads
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&a_ready_bar[stage]);
+                    if (!waited) {  // the loads are in flight while the ring slot drains
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ptx::tc_fence_after();
+                        waited = true;
+                    }
+                    uint32_t hi[16];
+                    if (PLANES == 2) {
+                        uint32_t lo[16];
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            float h, l;
+                            split_tf32(x[r], h, l);
+                            hi[r] = __float_as_uint(h);
+                            lo[r] = __float_as_uint(l);
+                        }
+                        tmem_st_32x16(ta + half * 16, hi);
+                        tmem_st_32x16(ta + 32 + half * 16, lo);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) hi[r] = __float_as_uint(x[r]);
+                        tmem_st_32x16(ta + half * 16, hi);
+                    }
                 }
+                tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&a_ready_bar[stage]);
             }
         }
     } else if (warp >= 4) {
@@ -314,18 +354,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
 }
 
-// W[oc][ic][tap] -> Wp[tap][oc][icp] hi/lo planes (icp = IC rounded up to 4 for TMA's 16-byte row rule)
+// W[oc][ic][tap] -> Wp[oc][Kf] hi/lo planes, k = tap*IC + ic, Kf = K rounded up to 4 (TMA's 16-byte row rule)
 __global__ void __launch_bounds__(256)
 igemm_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int OC, int IC,
-                          int ICp, int taps) {
+                          int taps, int Kf) {
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const size_t total = static_cast<size_t>(OC) * ICp * taps;
+    const size_t total = static_cast<size_t>(OC) * Kf;
     if (idx >= total) return;
-    const int ic = static_cast<int>(idx % ICp);
-    const size_t t = idx / ICp;
-    const int oc = static_cast<int>(t % OC);
-    const int tap = static_cast<int>(t / OC);
-    const float v = ic < IC ? w[(static_cast<size_t>(oc) * IC + ic) * taps + tap] : 0.f;
+    const int k = static_cast<int>(idx % Kf);
+    const int oc = static_cast<int>(idx / Kf);
+    float v = 0.f;
+    if (k < IC * taps) {
+        const int tap = k / IC, ic = k - tap * IC;
+        v = w[(static_cast<size_t>(oc) * IC + ic) * taps + tap];
+    }
     if (lo) {
         float h, l;
         split_tf32(v, h, l);
@@ -336,16 +378,17 @@ igemm_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, f
     }
 }
 
-template <int BN, int PLANES, int STAGES>
+template <int BN, int PLANES>
 int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return FCUDA_ERR_CUDA;
     CUtensorMap tmW, tmWlo;
     const int taps = p.KH * p.KW;
-    const int ICp = (p.IC + 3) & ~3;
+    const int K = taps * p.IC;
+    const int Kf = (K + 3) & ~3;
     for (int pl = 0; pl < PLANES; ++pl) {
-        cuuint64_t dims[3] = {(cuuint64_t)ICp, (cuuint64_t)p.OC, (cuuint64_t)taps};
-        cuuint64_t strides[2] = {(cuuint64_t)ICp * 4, (cuuint64_t)ICp * p.OC * 4};
+        cuuint64_t dims[3] = {(cuuint64_t)Kf, (cuuint64_t)p.OC, 1};
+        cuuint64_t strides[2] = {(cuuint64_t)Kf * 4, (cuuint64_t)Kf * p.OC * 4};
         cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         const float* base = pl == 0 ? p.w_hi : p.w_lo;
@@ -363,22 +406,25 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     a.N = p.N; a.IC = p.IC; a.H = p.H; a.W = p.W; a.OC = p.OC; a.OH = p.OH; a.OW = p.OW;
     a.KH = p.KH; a.KW = p.KW; a.pad_top = p.pad_top; a.pad_left = p.pad_left;
     a.stride_h = p.stride_h; a.stride_w = p.stride_w;
+    a.K = K;
+    a.kblocks = ceil_div(K, 32);
+    a.use_table = taps > 1 ? 1 : 0;
     a.bpr = ceil_div(p.OW, 32);
     a.total_boxes = static_cast<long long>(p.N) * p.OH * a.bpr;
-    a.cblocks = ceil_div(p.IC, 32);
     a.num_n = ceil_div(p.OC, BN);
     a.pixel_tiles = (a.total_boxes + 3) / 4;
     a.relu = p.relu;
     const long long total = a.pixel_tiles * a.num_n;
     const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
-    constexpr int kStage = PLANES * (kATileBytes + BN * 32 * 4);
-    static_assert(STAGES * kStage + 1024 <= 227 * 1024, "smem budget");
-    const int smem = STAGES * kStage + 1024;
-    auto kern = conv_igemm_kernel<BN, PLANES, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    constexpr int kStage = PLANES * BN * 32 * 4;
+    const int table_bytes = a.use_table ? a.kblocks * 32 * 8 : 0;
+    const int smem = kStagesIg * kStage + table_bytes + 1024;
+    if (smem > 227 * 1024) return -1;
+    auto kern = conv_igemm_kernel<BN, PLANES>;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
         FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_smem = smem;
     }
     kern<<<grid, kThreadsIg, smem, stream>>>(tmW, tmWlo, a);
     FCUDA_CHECK_LAUNCH();
@@ -388,24 +434,31 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
 
 }  // namespace
 
+bool conv_igemm_supported(int IC, int KH, int KW) {
+    if (KH > 16 || KW > 16) return false;               // tap masks are 16-bit
+    if (KH * KW > 1 && KH * KW * IC > kMaxTableK) return false;  // k-table must fit in shared memory
+    return true;
+}
+
 size_t conv_igemm_packed_floats(int OC, int IC, int taps, int planes) {
-    return static_cast<size_t>(planes) * taps * OC * ((IC + 3) & ~3);
+    return static_cast<size_t>(planes) * OC * ((taps * IC + 3) & ~3);
 }
 
 int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, int IC, int taps, cudaStream_t s) {
-    const int ICp = (IC + 3) & ~3;
-    const size_t total = static_cast<size_t>(OC) * ICp * taps;
-    igemm_pack_weights_kernel<<<static_cast<unsigned>(ceil_div_sz(total, 256)), 256, 0, s>>>(w, w_hi, w_lo, OC, IC, ICp, taps);
+    const int Kf = (taps * IC + 3) & ~3;
+    const size_t total = static_cast<size_t>(OC) * Kf;
+    igemm_pack_weights_kernel<<<static_cast<unsigned>(ceil_div_sz(total, 256)), 256, 0, s>>>(w, w_hi, w_lo, OC, IC, taps, Kf);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;
 }
 
 int conv_igemm_forward(const IgemmProblem& p, cudaStream_t stream) {
+    if (!conv_igemm_supported(p.IC, p.KH, p.KW)) return -1;
     const bool x3 = p.planes == 2;
-    if (p.OC <= 32) return x3 ? launch_igemm<32, 2, 4>(p, stream) : launch_igemm<32, 1, 8>(p, stream);
-    if (p.OC <= 64) return x3 ? launch_igemm<64, 2, 4>(p, stream) : launch_igemm<64, 1, 8>(p, stream);
-    return x3 ? launch_igemm<128, 2, 3>(p, stream) : launch_igemm<128, 1, 6>(p, stream);
+    if (p.OC <= 32) return x3 ? launch_igemm<32, 2>(p, stream) : launch_igemm<32, 1>(p, stream);
+    if (p.OC <= 64) return x3 ? launch_igemm<64, 2>(p, stream) : launch_igemm<64, 1>(p, stream);
+    return x3 ? launch_igemm<128, 2>(p, stream) : launch_igemm<128, 1>(p, stream);
 }
 
 }  // namespace fcuda

@@ -6,7 +6,7 @@ namespace fcuda {
 
 struct IgemmProblem {
     const float* input;   // (N, IC, H, W) fp32 NCHW
-    const float* w_hi;    // packed filters [tap][OC][IC], TF32-exact plane
+    const float* w_hi;    // packed filters [OC][Kf], k = tap*IC + ic, TF32-exact plane
     const float* w_lo;    // fp32 remainder plane (planes == 2) or null
     const float* bias;    // OC floats or null
     float* output;        // (N, OC, OH, OW)
@@ -16,9 +16,11 @@ struct IgemmProblem {
     int relu;
 };
 
-// Floats of the packed filter buffer ([tap][OC][ICp] per plane, ICp = IC rounded up to 4).
+// Kernel extents up to 16x16 and (for KH*KW > 1) KH*KW*IC <= 8192 (shared-memory k-table).
+bool conv_igemm_supported(int IC, int KH, int KW);
+// Floats of the packed filter buffer ([OC][Kf] per plane, Kf = KH*KW*IC rounded up to 4).
 size_t conv_igemm_packed_floats(int OC, int IC, int taps, int planes);
-// raw (OC, IC, KH, KW) -> [tap][OC][ICp] hi (+ lo) planes.
+// raw (OC, IC, KH, KW) -> [OC][Kf] hi (+ lo) planes.
 int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, int IC, int taps, cudaStream_t s);
 int conv_igemm_forward(const IgemmProblem& p, cudaStream_t stream);
 

@@ -134,7 +134,7 @@ int make_plan(const FcudaConvParam* p, int algo, int batch, ConvPlan* plan) {
         }
         case FCUDA_SGECONV: {
             // implicit GEMM straight from NCHW: any kernel / stride / padding, group 1
-            if (p->group != 1) return -1;
+            if (p->group != 1 || !conv_igemm_supported(IC, p->kernel_h, p->kernel_w)) return -1;
             pl.pg = pack_geom(p);
             pl.scratch_floats = 0;
             pl.packed_floats = conv_igemm_packed_floats(OC, IC, p->kernel_h * p->kernel_w, pl.np);
@@ -225,7 +225,7 @@ int fcuda_conv_select_algo_tuned(const FcudaConvParam* p, int* algo) {
     } else if (*algo == FCUDA_IM2COL) {
         // everything the reference sends to im2col + SGEMM (1x1, strided, 7x7, IC = 3, small images): gather the
         // patches inside the GEMM instead of materialising them
-        *algo = FCUDA_SGECONV;
+        if (conv_igemm_supported(IC, p->kernel_h, p->kernel_w)) *algo = FCUDA_SGECONV;
     }
     return 0;
 }
