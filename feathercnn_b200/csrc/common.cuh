@@ -39,11 +39,8 @@ int sm_count();
 // mantissa bits) and the exact fp32 remainder "lo".  hi + lo == v exactly; the tensor
 // core then truncates lo to TF32, leaving a relative error of ~2^-22 per operand.
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-    uint32_t u = __float_as_uint(v);
-    // round to nearest (ties away) on bit 13, then clear the low 13 bits
-    uint32_t r = (u + 0x1000u) & 0xFFFFE000u;
-    // Inf/NaN: keep as is (exponent all ones) — adding could overflow the exponent field.
-    if ((u & 0x7F800000u) == 0x7F800000u) r = u & 0xFFFFE000u;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));  // round to nearest (ties away), low 13 mantissa bits zero
     hi = __uint_as_float(r);
     lo = v - hi;
 }

@@ -61,7 +61,7 @@ struct IgemmArgs {
     int KH, KW, pad_top, pad_left, stride_h, stride_w;
     int K;                   // KH*KW*IC
     int kblocks;             // ceil(K / 32)
-    int use_table;           // 0 => pointwise (k == ic), offsets computed arithmetically
+    int use_table;           // 0 => IC % 32 == 0: every k-block is 32 channels of ONE tap, offsets are arithmetic
     int bpr;                 // 32-pixel boxes per output row
     long long total_boxes;   // N * OH * bpr
     int num_n;               // ceil(OC / BN)
@@ -121,7 +121,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    int2* ktab = reinterpret_cast<int2*>(smem + STAGES * kStage);  // {element offset, (u << 16) | v} per k
+    int2* ktab = reinterpret_cast<int2*>(smem + STAGES * kStage);  // {element offset, tap index} per k
 
     __shared__ uint64_t b_full_bar[STAGES];   // filters landed (TMA transaction bytes)
     __shared__ uint64_t a_ready_bar[STAGES];  // the 4 producer warps of the owning group stored their TMEM quadrant
@@ -154,11 +154,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
     if (args.use_table) {
         for (int k = threadIdx.x; k < kblocks * 32; k += kThreadsIg) {
-            int2 e = make_int2(0, 0x7fff7fff);  // padding rows: coordinates no mask bit can satisfy
+            int2 e = make_int2(0, 63);  // padding rows: tap 63 is never valid
             if (k < args.K) {
                 const int tap = k / args.IC, ic = k - tap * args.IC;
                 const int u = tap / args.KW, v = tap - u * args.KW;
-                e = make_int2(ic * plane + u * args.W + v, (u << 16) | v);
+                e = make_int2(ic * plane + u * args.W + v, tap);
             }
             ktab[k] = e;
         }
@@ -181,7 +181,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_blk = static_cast<int>(tile % args.num_n);
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * kStage;
                     ptx::mbar_arrive_expect_tx(&b_full_bar[stage], PLANES * kBTile);
                     ptx::tma_load_3d(st, &tmW, &b_full_bar[stage], kb * 32, n_blk * BN, 0);
@@ -243,36 +243,51 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const bool pix_ok = bx.valid && ox < args.OW;
             const int iy0 = bx.oy * args.stride_h - args.pad_top;
             const int ix0 = ox * args.stride_w - args.pad_left;
-            uint32_t rowmask = 0, colmask = 0;  // bit u / v set <=> that tap row / column lies inside the image
+            unsigned long long tapmask = 0;  // bit (u*KW+v) set <=> that tap of this pixel lies inside the image
             if (pix_ok) {
-                for (int u = 0; u < args.KH; ++u) rowmask |= (iy0 + u >= 0 && iy0 + u < args.H) ? (1u << u) : 0u;
-                for (int v = 0; v < args.KW; ++v) colmask |= (ix0 + v >= 0 && ix0 + v < args.W) ? (1u << v) : 0u;
+                for (int u = 0; u < args.KH; ++u) {
+                    if (iy0 + u < 0 || iy0 + u >= args.H) continue;
+                    for (int v = 0; v < args.KW; ++v)
+                        if (ix0 + v >= 0 && ix0 + v < args.W) tapmask |= 1ull << (u * args.KW + v);
+                }
             }
             const float* base = args.in + (static_cast<long long>(bx.valid ? bx.n : 0) * args.IC) * plane +
                                 static_cast<long long>(iy0) * args.W + ix0;
+            asm volatile("" : "+l"(base));  // opaque, see the fast path below
             for (int kb = 0; kb < kblocks; ++kb, ++g) {
                 if (static_cast<int>(g % kGroups) != group) continue;
                 const int stage = static_cast<int>(g % STAGES);
                 const uint32_t phase = static_cast<uint32_t>((g / STAGES) & 1);
                 const uint32_t ta = tmem_a0 + lane_base + stage * kAStageCols;
                 bool waited = false;
+                // fast path (IC % 32 == 0): the whole k-block is one tap -> one predicate, pointer + r*plane
+                const float* kp = base;
+                bool kb_ok = false;
+                if (!args.use_table) {
+                    const int k0 = kb * 32;
+                    const int tap = k0 / args.IC, ic0 = k0 - tap * args.IC;
+                    const int u = tap / args.KW, v = tap - u * args.KW;
+                    kp = base + (static_cast<long long>(ic0) * plane + u * args.W + v);
+                    kb_ok = ((tapmask >> tap) & 1ull) != 0;
+                    // keep the pointer opaque: otherwise nvcc re-derives every address from args.in with ~8 integer
+                    // instructions per load; bumped by `plane` it is one IMAD.WIDE per load
+                    asm volatile("" : "+l"(kp));
+                }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     float x[16];
+                    if (!args.use_table) {
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const int k = kb * 32 + half * 16 + r;
-                        int off;
-                        bool ok;
-                        if (args.use_table) {
-                            const int2 e = ktab[k];
-                            off = e.x;
-                            ok = ((rowmask >> (e.y >> 16)) & (colmask >> (e.y & 0xffff)) & 1u) != 0;
-                        } else {
-                            off = k * plane;
-                            ok = pix_ok && k < args.K;
+                        for (int r = 0; r < 16; ++r) {
+                            x[r] = kb_ok ? __ldg(kp) : 0.f;
+                            kp += plane;
                         }
-                        x[r] = ok ? __ldg(base + off) : 0.f;
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            const int2 e = ktab[kb * 32 + half * 16 + r];
+                            x[r] = ((tapmask >> e.y) & 1ull) ? __ldg(base + e.x) : 0.f;
+                        }
                     }
                     if (!waited) {  // the loads are in flight while the ring slot drains
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -312,7 +327,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const int n_blk = static_cast<int>(tile - ptile * args.num_n);
             const int as = static_cast<int>(it & 1);
             const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
-            ptx::mbar_wait(&tmem_full_bar[as], aphase);
+            ptx::mbar_wait_relaxed(&tmem_full_bar[as], aphase);
             ptx::tc_fence_after();
             const BoxCoord bx = decode_box(ptile * 4 + q, args);  // this warp's 32 TMEM lanes are box q
             const int ox = bx.ox0 + lane;
@@ -408,7 +423,7 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     a.stride_h = p.stride_h; a.stride_w = p.stride_w;
     a.K = K;
     a.kblocks = ceil_div(K, 32);
-    a.use_table = taps > 1 ? 1 : 0;
+    a.use_table = (p.IC % 32 == 0) ? 0 : 1;
     a.bpr = ceil_div(p.OW, 32);
     a.total_boxes = static_cast<long long>(p.N) * p.OH * a.bpr;
     a.num_n = ceil_div(p.OC, BN);
@@ -435,8 +450,8 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
 }  // namespace
 
 bool conv_igemm_supported(int IC, int KH, int KW) {
-    if (KH > 16 || KW > 16) return false;               // tap masks are 16-bit
-    if (KH * KW > 1 && KH * KW * IC > kMaxTableK) return false;  // k-table must fit in shared memory
+    if (KH * KW > 63) return false;                               // per-pixel tap validity mask is 64-bit
+    if (IC % 32 != 0 && KH * KW * IC > kMaxTableK) return false;  // k-table must fit in shared memory
     return true;
 }
 

@@ -16,7 +16,7 @@ struct IgemmProblem {
     int relu;
 };
 
-// Kernel extents up to 16x16 and (for KH*KW > 1) KH*KW*IC <= 8192 (shared-memory k-table).
+// KH*KW <= 63 and, unless IC % 32 == 0, KH*KW*IC <= 8192 (shared-memory k-table).
 bool conv_igemm_supported(int IC, int KH, int KW);
 // Floats of the packed filter buffer ([OC][Kf] per plane, Kf = KH*KW*IC rounded up to 4).
 size_t conv_igemm_packed_floats(int OC, int IC, int taps, int planes);
