@@ -175,59 +175,65 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer for the filter tiles =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_blk = static_cast<int>(tile % args.num_n);
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    ptx::mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+        const bool leader = ptx::elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_blk = static_cast<int>(tile % args.num_n);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                ptx::mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+                if (leader) {
                     uint8_t* st = smem + stage * kStage;
                     ptx::mbar_arrive_expect_tx(&b_full_bar[stage], PLANES * kBTile);
                     ptx::tma_load_3d(st, &tmW, &b_full_bar[stage], kb * 32, n_blk * BN, 0);
                     if (PLANES == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, &b_full_bar[stage], kb * 32, n_blk * BN, 0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            long long it = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int as = static_cast<int>(it & 1);
-                const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
-                ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.  Descriptors are
+        // formed once: per k-block only the stage offset (in 16-byte units / TMEM columns) is added.
+        constexpr uint32_t idesc = make_idesc_tf32(BN);
+        const bool leader = ptx::elect_one();
+        const uint64_t dB0 = make_smem_desc_sw128(ptx::smem_u32(smem));
+        int stage = 0;
+        uint32_t phase = 0;
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = static_cast<int>(it & 1);
+            const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
+            ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                ptx::mbar_wait(&a_ready_bar[stage], phase);
+                ptx::mbar_wait(&b_full_bar[stage], phase);
                 ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    ptx::mbar_wait(&a_ready_bar[stage], phase);
-                    ptx::mbar_wait(&b_full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint32_t st = ptx::smem_u32(smem + stage * kStage);
-                    const uint64_t dB = make_smem_desc_sw128(st);
-                    const uint64_t dBlo = make_smem_desc_sw128(st + kBTile);
+                if (leader) {
+                    const uint64_t dB = dB0 + static_cast<uint64_t>(stage * (kStage >> 4));
+                    const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
                     const uint32_t ta = tmem_a0 + stage * kAStageCols;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // 8 k-values (TMEM columns) per MMA
-                        const uint64_t koff = static_cast<uint64_t>(k * 2);  // B: +32 bytes inside the swizzle atom
+                    for (int k = 0; k < 4; ++k) {  // 8 k-values (TMEM columns / 32 smem bytes) per MMA
                         const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
                         if (PLANES == 2) {
-                            umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + koff, idesc, first);   // A_lo * B_hi
-                            umma_tf32_ts(tmem_d, ta + k * 8, dBlo + koff, idesc, 1u);         // A_hi * B_lo
-                            umma_tf32_ts(tmem_d, ta + k * 8, dB + koff, idesc, 1u);           // A_hi * B_hi
+                            umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);   // A_lo * B_hi
+                            umma_tf32_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_hi * B_lo
+                            umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);           // A_hi * B_hi
                         } else {
-                            umma_tf32_ts(tmem_d, ta + k * 8, dB + koff, idesc, first);
+                            umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, first);
                         }
                     }
                     ptx::umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tmem_full_bar[as]);
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (leader) ptx::umma_commit(&tmem_full_bar[as]);
+            __syncwarp();
         }
     } else if (warp >= 8) {
         // ===================== A producers: gather + 3xTF32 split -> tensor memory =====================
@@ -235,7 +241,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int group = pw >> 2;
         const int q = warp & 3;  // TMEM lane quadrant this warp may write == box index inside the tile
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-        long long g = 0;  // running k-block index over all tiles of this CTA
+        // running k-block index over all tiles of this CTA, kept as three small wrapping counters
+        int g_mod = 0;        // g % kGroups
+        int stage = 0;        // g % STAGES
+        uint32_t phase = 0;   // (g / STAGES) & 1
+        const int cblocks = args.IC >> 5;  // fast path only
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const long long ptile = tile / args.num_n;
             const BoxCoord bx = decode_box(ptile * 4 + q, args);
@@ -254,21 +264,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const float* base = args.in + (static_cast<long long>(bx.valid ? bx.n : 0) * args.IC) * plane +
                                 static_cast<long long>(iy0) * args.W + ix0;
             asm volatile("" : "+l"(base));  // opaque, see the fast path below
-            for (int kb = 0; kb < kblocks; ++kb, ++g) {
-                if (static_cast<int>(g % kGroups) != group) continue;
-                const int stage = static_cast<int>(g % STAGES);
-                const uint32_t phase = static_cast<uint32_t>((g / STAGES) & 1);
-                const uint32_t ta = tmem_a0 + lane_base + stage * kAStageCols;
+            int tap = 0, tu = 0, tv = 0, cb = 0;  // fast path: k-block kb = tap * cblocks + cb, tap = tu*KW + tv
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const bool mine = g_mod == group;
+                const int my_stage = stage;
+                const uint32_t my_phase = phase;
+                const int my_tap = tap, my_u = tu, my_v = tv, my_cb = cb;
+                // advance the counters for the next k-block
+                if (++g_mod == kGroups) g_mod = 0;
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (++cb == cblocks) { cb = 0; ++tap; if (++tv == args.KW) { tv = 0; ++tu; } }
+                if (!mine) continue;
+                const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
                 bool waited = false;
                 // fast path (IC % 32 == 0): the whole k-block is one tap -> one predicate, pointer + r*plane
                 const float* kp = base;
                 bool kb_ok = false;
                 if (!args.use_table) {
-                    const int k0 = kb * 32;
-                    const int tap = k0 / args.IC, ic0 = k0 - tap * args.IC;
-                    const int u = tap / args.KW, v = tap - u * args.KW;
-                    kp = base + (static_cast<long long>(ic0) * plane + u * args.W + v);
-                    kb_ok = ((tapmask >> tap) & 1ull) != 0;
+                    kp = base + (static_cast<long long>(my_cb * 32) * plane + my_u * args.W + my_v);
+                    kb_ok = ((tapmask >> my_tap) & 1ull) != 0;
                     // keep the pointer opaque: otherwise nvcc re-derives every address from args.in with ~8 integer
                     // instructions per load; bumped by `plane` it is one IMAD.WIDE per load
                     asm volatile("" : "+l"(kp));
@@ -290,7 +304,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         }
                     }
                     if (!waited) {  // the loads are in flight while the ring slot drains
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ptx::mbar_wait(&empty_bar[my_stage], my_phase ^ 1);
                         ptx::tc_fence_after();
                         waited = true;
                     }
@@ -299,10 +313,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         uint32_t lo[16];
 #pragma unroll
                         for (int r = 0; r < 16; ++r) {
-                            float h, l;
-                            split_tf32(x[r], h, l);
-                            hi[r] = __float_as_uint(h);
-                            lo[r] = __float_as_uint(l);
+                            // hi = x with the 13 sub-TF32 mantissa bits cleared (what the tensor core would read
+                            // anyway), lo = x - hi exactly: 2 instructions per element instead of 5 for round-to-nearest;
+                            // the residual after the hardware truncates lo is <= 2^-21 |x| either way
+                            hi[r] = __float_as_uint(x[r]) & 0xFFFFE000u;
+                            lo[r] = __float_as_uint(x[r] - __uint_as_float(hi[r]));
                         }
                         tmem_st_32x16(ta + half * 16, hi);
                         tmem_st_32x16(ta + 32 + half * 16, lo);
@@ -315,7 +330,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 tmem_st_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&a_ready_bar[stage]);
+                if (lane == 0) ptx::mbar_arrive(&a_ready_bar[my_stage]);
             }
         }
     } else if (warp >= 4) {

@@ -93,20 +93,22 @@ tensor_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int ks = tile / (tiles_per_g * args.G);
-                const int rem = tile - ks * (tiles_per_g * args.G);
-                const int g = rem / tiles_per_g;
-                const int mn = rem - g * tiles_per_g;
-                const int m_blk = mn / args.num_n;
-                const int n_blk = mn - m_blk * args.num_n;
-                const int kb0 = ks * kb_per_split;
-                const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        // whole warp walks the loop (warp-uniform control flow), one elected lane issues
+        const bool leader = ptx::elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int ks = tile / (tiles_per_g * args.G);
+            const int rem = tile - ks * (tiles_per_g * args.G);
+            const int g = rem / tiles_per_g;
+            const int mn = rem - g * tiles_per_g;
+            const int m_blk = mn / args.num_n;
+            const int n_blk = mn - m_blk * args.num_n;
+            const int kb0 = ks * kb_per_split;
+            const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (leader) {
                     uint8_t* st = smem + stage * L::kStage;
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStage);
                     ptx::tma_load_3d(st, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM, g);
@@ -115,52 +117,55 @@ tensor_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         ptx::tma_load_3d(st + L::kATile + L::kBTile, &tmAlo, &full_bar[stage], kb * kBK, m_blk * kBM, g);
                         ptx::tma_load_3d(st + 2 * L::kATile + L::kBTile, &tmBlo, &full_bar[stage], kb * kBK, n_blk * BN, g);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int ks = tile / (tiles_per_g * args.G);
-                const int kb0 = ks * kb_per_split;
-                const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        constexpr uint32_t idesc = make_idesc_tf32(BN);
+        const bool leader = ptx::elect_one();
+        const uint64_t d0 = make_smem_desc_sw128(ptx::smem_u32(smem));  // descriptors differ only in the start address
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int ks = tile / (tiles_per_g * args.G);
+            const int kb0 = ks * kb_per_split;
+            const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint32_t st = ptx::smem_u32(smem + stage * L::kStage);
-                    const uint64_t dA = make_smem_desc_sw128(st);
-                    const uint64_t dB = make_smem_desc_sw128(st + L::kATile);
-                    const uint64_t dAlo = make_smem_desc_sw128(st + L::kATile + L::kBTile);
-                    const uint64_t dBlo = make_smem_desc_sw128(st + 2 * L::kATile + L::kBTile);
+                if (leader) {
+                    // start-address field is in 16-byte units; 32 bytes (8 tf32) per k-step inside the swizzle atom
+                    const uint64_t dA = d0 + static_cast<uint64_t>(stage * (L::kStage >> 4));
+                    const uint64_t dB = dA + static_cast<uint64_t>(L::kATile >> 4);
+                    const uint64_t dAlo = dB + static_cast<uint64_t>(L::kBTile >> 4);
+                    const uint64_t dBlo = dAlo + static_cast<uint64_t>(L::kATile >> 4);
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k) {
-                        // advance 8 tf32 = 32 bytes inside the 128-byte swizzle atom: +2 in 16-byte units
-                        const uint64_t koff = static_cast<uint64_t>(k * 2);
                         const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
                         if (PLANES == 2) {
-                            ptx::umma_tf32(tmem_d, dAlo + koff, dB + koff, idesc, first);
-                            ptx::umma_tf32(tmem_d, dA + koff, dBlo + koff, idesc, 1u);
-                            ptx::umma_tf32(tmem_d, dA + koff, dB + koff, idesc, 1u);
+                            ptx::umma_tf32(tmem_d, dAlo + 2 * k, dB + 2 * k, idesc, first);
+                            ptx::umma_tf32(tmem_d, dA + 2 * k, dBlo + 2 * k, idesc, 1u);
+                            ptx::umma_tf32(tmem_d, dA + 2 * k, dB + 2 * k, idesc, 1u);
                         } else {
-                            ptx::umma_tf32(tmem_d, dA + koff, dB + koff, idesc, first);
+                            ptx::umma_tf32(tmem_d, dA + 2 * k, dB + 2 * k, idesc, first);
                         }
                     }
                     ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (leader) ptx::umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
+            __syncwarp();
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
