@@ -214,11 +214,10 @@ def tensor_gemm(a: torch.Tensor, b: torch.Tensor, x3: bool = True) -> torch.Tens
     n = b.shape[1]
     a = a.contiguous(); b = b.contiguous()
     d = torch.empty((g, m, n), device=a.device)
-    if x3:
-        ah, al, bh, bl = (torch.empty_like(t) for t in (a, a, b, b))
-        _check("fcuda_split_tf32", lib.fcuda_split_tf32(_ptr(ah), _ptr(al), _ptr(a), a.numel(), _stream()))
+    if x3:  # A is split inside the kernel (tensor memory); B carries its hi / lo planes
+        bh, bl = torch.empty_like(b), torch.empty_like(b)
         _check("fcuda_split_tf32", lib.fcuda_split_tf32(_ptr(bh), _ptr(bl), _ptr(b), b.numel(), _stream()))
-        _check("fcuda_tensor_gemm", lib.fcuda_tensor_gemm(_ptr(d), _ptr(ah), _ptr(al), _ptr(bh), _ptr(bl), m, n, k, g, _stream()))
+        _check("fcuda_tensor_gemm", lib.fcuda_tensor_gemm(_ptr(d), _ptr(a), _ptr(bh), _ptr(bl), m, n, k, g, _stream()))
     else:
-        _check("fcuda_tensor_gemm", lib.fcuda_tensor_gemm(_ptr(d), _ptr(a), None, _ptr(b), None, m, n, k, g, _stream()))
+        _check("fcuda_tensor_gemm", lib.fcuda_tensor_gemm(_ptr(d), _ptr(a), _ptr(b), None, m, n, k, g, _stream()))
     return d

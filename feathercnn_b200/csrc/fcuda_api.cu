@@ -93,7 +93,8 @@ int make_plan(const FcudaConvParam* p, int algo, int batch, ConvPlan* plan) {
             g.tilesX = ceil_div(g.OW, ot);  // == (Wp + 3) / 6 for F(6,3), winograd_kernels_F63.cpp:2320
             g.tilesY = ceil_div(g.OH, ot);
             pl.total_tile_rows = batch * g.tilesY;
-            const size_t bytes_per_row = static_cast<size_t>(g.tilesX) * pl.TT * (static_cast<size_t>(pl.np) * IC + OC) * 4;
+            // V is stored once as plain fp32 (the TensorGEMM splits it in-kernel), M once
+            const size_t bytes_per_row = static_cast<size_t>(g.tilesX) * pl.TT * (static_cast<size_t>(IC) + OC) * 4;
             const size_t u_bytes = static_cast<size_t>(pl.np) * pl.TT * IC * OC * 4;
             size_t budget = g_l2_chunk;
             if (budget && budget < 2 * u_bytes) budget = 2 * u_bytes;  // do not re-stream U more than the data it multiplies
@@ -104,7 +105,7 @@ int make_plan(const FcudaConvParam* p, int algo, int batch, ConvPlan* plan) {
             pl.rows_per_chunk = ceil_div(pl.total_tile_rows, nchunks);
             pl.Tc_max = static_cast<size_t>(pl.rows_per_chunk) * g.tilesX;
             if (pl.Tc_max > 0x7fffffffULL / 64) return -100;
-            pl.scratch_floats = pl.TT * pl.Tc_max * (static_cast<size_t>(pl.np) * IC + OC);
+            pl.scratch_floats = pl.TT * pl.Tc_max * (static_cast<size_t>(IC) + OC);
             pl.packed_floats = static_cast<size_t>(pl.np) * pl.TT * IC * OC;
             return 0;
         }
@@ -119,7 +120,7 @@ int make_plan(const FcudaConvParam* p, int algo, int batch, ConvPlan* plan) {
                 return 0;
             }
             pl.im2col_tc = true;
-            const size_t bytes_per_pixel = static_cast<size_t>(pl.np) * pl.pg.Kp * 4;
+            const size_t bytes_per_pixel = static_cast<size_t>(pl.pg.Kp) * 4;
             long long pix = g_l2_chunk ? static_cast<long long>(g_l2_chunk / bytes_per_pixel) : pl.total_pixels;
             pix = pix / 128 * 128;
             if (pix < 128) pix = 128;
@@ -128,7 +129,7 @@ int make_plan(const FcudaConvParam* p, int algo, int batch, ConvPlan* plan) {
             const long long nchunks = (pl.total_pixels + pix - 1) / pix;
             pix = ((pl.total_pixels + nchunks - 1) / nchunks + 127) / 128 * 128;
             pl.pixels_per_chunk = static_cast<int>(pix);
-            pl.scratch_floats = static_cast<size_t>(pl.np) * pix * pl.pg.Kp;
+            pl.scratch_floats = static_cast<size_t>(pix) * pl.pg.Kp;
             pl.packed_floats = static_cast<size_t>(pl.np) * OC * pl.pg.Kp;
             return 0;
         }
@@ -301,15 +302,14 @@ int fcuda_conv_forward(const FcudaConvParam* p, int algo, float* output, const f
         case FCUDA_WINOGRADF23: {
             const size_t v_plane = static_cast<size_t>(pl.TT) * pl.Tc_max * IC;
             const size_t u_plane = static_cast<size_t>(pl.TT) * IC * OC;
-            float* V_hi = scratch;
-            float* V_lo = pl.np == 2 ? scratch + v_plane : nullptr;
-            float* Mbuf = scratch + static_cast<size_t>(pl.np) * v_plane;
+            float* V = scratch;  // plain fp32; the TensorGEMM makes the TF32 hi/lo split on chip
+            float* Mbuf = scratch + v_plane;
             for (int R0 = 0; R0 < pl.total_tile_rows; R0 += pl.rows_per_chunk) {
                 const int R1 = R0 + pl.rows_per_chunk < pl.total_tile_rows ? R0 + pl.rows_per_chunk : pl.total_tile_rows;
                 const int Tc = (R1 - R0) * pl.wg.tilesX;
-                if ((rc = wino_input_transform(pl.tile, input, V_hi, V_lo, pl.wg, R0, R1, s))) return rc;
+                if ((rc = wino_input_transform(pl.tile, input, V, pl.wg, R0, R1, s))) return rc;
                 GemmProblem g{};
-                g.A_hi = V_hi; g.A_lo = V_lo;
+                g.A = V;
                 g.B_hi = packed; g.B_lo = pl.np == 2 ? packed + u_plane : nullptr;
                 g.D = Mbuf;
                 g.M = Tc; g.N = OC; g.K = IC; g.G = pl.TT;
@@ -323,16 +323,14 @@ int fcuda_conv_forward(const FcudaConvParam* p, int algo, float* output, const f
             return 0;
         }
         case FCUDA_IM2COL: {
-            const size_t p_plane = static_cast<size_t>(pl.pixels_per_chunk) * pl.pg.Kp;
             const size_t w_plane = static_cast<size_t>(OC) * pl.pg.Kp;
-            float* P_hi = scratch;
-            float* P_lo = pl.np == 2 ? scratch + p_plane : nullptr;
+            float* P = scratch;
             for (long long m0 = 0; m0 < pl.total_pixels; m0 += pl.pixels_per_chunk) {
                 const int rows = static_cast<int>(m0 + pl.pixels_per_chunk < pl.total_pixels ? pl.pixels_per_chunk
                                                                                                : pl.total_pixels - m0);
-                if ((rc = im2col_pack(input, P_hi, P_lo, pl.pg, m0, rows, s))) return rc;
+                if ((rc = im2col_pack(input, P, nullptr, pl.pg, m0, rows, s))) return rc;
                 GemmProblem g{};
-                g.A_hi = P_hi; g.A_lo = P_lo;
+                g.A = P;
                 g.B_hi = packed; g.B_lo = pl.np == 2 ? packed + w_plane : nullptr;
                 g.D = output;
                 g.M = rows; g.N = OC; g.K = pl.pg.Kp; g.G = 1;
@@ -370,12 +368,12 @@ int fcuda_conv_forward(const FcudaConvParam* p, int algo, float* output, const f
     }
 }
 
-int fcuda_tensor_gemm(float* d, const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int m,
-                      int n, int k, int g, void* stream) {
+int fcuda_tensor_gemm(float* d, const float* a, const float* b_hi, const float* b_lo, int m, int n, int k, int g,
+                      void* stream) {
     GemmProblem p{};
-    p.A_hi = a_hi; p.A_lo = a_lo; p.B_hi = b_hi; p.B_lo = b_lo; p.D = d;
+    p.A = a; p.B_hi = b_hi; p.B_lo = b_lo; p.D = d;
     p.M = m; p.N = n; p.K = k; p.G = g;
-    p.planes = (a_lo && b_lo) ? 2 : 1;
+    p.planes = b_lo ? 2 : 1;
     p.epilogue = EPI_ROWMAJOR; p.ldd = n; p.split_k = 1;
     return tensor_gemm(p, as_stream(stream));
 }
@@ -393,7 +391,8 @@ int fcuda_inner_product_get_buffer_size(int input_size, int output_size, int bat
                                         size_t* packed_kernel_floats) {
     if (input_size <= 0 || output_size <= 0 || batch < 1) return -100;
     const int np = fc_tensor_path(input_size) ? planes() : 1;
-    if (packed_kernel_floats) *packed_kernel_floats = static_cast<size_t>(np) * output_size * input_size;
+    // W (the streamed operand) is kept once as plain fp32; only the small activation matrix gets hi/lo planes
+    if (packed_kernel_floats) *packed_kernel_floats = static_cast<size_t>(output_size) * input_size;
     if (scratch_floats) *scratch_floats = np == 2 ? 2 * static_cast<size_t>(batch) * input_size : 0;
     return 0;
 }
@@ -406,12 +405,7 @@ int fcuda_inner_product_init(int input_size, int output_size, float* packed, con
     float* tmp;
     int rc = stage_to_device(raw, n, &d_raw, &tmp, s);
     if (rc) return rc;
-    const int np = fc_tensor_path(input_size) ? planes() : 1;
-    if (np == 2) {
-        rc = split_tf32_planes(d_raw, packed, packed + n, n, s);
-    } else if (cudaMemcpyAsync(packed, d_raw, n * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
-        rc = FCUDA_ERR_CUDA;
-    }
+    if (cudaMemcpyAsync(packed, d_raw, n * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = FCUDA_ERR_CUDA;
     if (tmp) {
         cudaStreamSynchronize(s);
         cudaFree(tmp);
@@ -427,12 +421,11 @@ int fcuda_inner_product_forward(int input_size, int output_size, float* output, 
     const bool tc = fc_tensor_path(input_size);
     const int np = tc ? planes() : 1;
     if (np == 2 && !scratch) return -100;
-    const size_t wn = static_cast<size_t>(output_size) * input_size;
     const size_t xn = static_cast<size_t>(batch) * input_size;
     int rc = fill_rows(output, bias, output_size, batch, s);  // out[b][o] = bias[o]; the GEMM accumulates on top
     if (rc) return rc;
     GemmProblem g{};
-    g.A_hi = packed; g.A_lo = np == 2 ? packed + wn : nullptr;  // A = W (out x in): output features on the 128-row M side
+    g.A = packed;  // A = W (out x in), plain fp32: output features on the 128-row M side
     g.B_hi = input; g.B_lo = nullptr;                           // B = X (batch x in)
     if (np == 2) {
         if ((rc = split_tf32_planes(input, scratch, scratch + xn, xn, s))) return rc;

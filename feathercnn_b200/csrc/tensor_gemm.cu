@@ -39,6 +39,75 @@ struct SmemLayout {
     static constexpr int kStage = PLANES * (kATile + kBTile);
 };
 
+// Drains one 128 x BN accumulator (TMEM lanes q*32 .. q*32+31 for this warp) through the fused store selected by
+// args.epilogue.  Shared by the smem-operand kernel and the TMEM-A (3xTF32) kernel.
+template <int BN>
+__device__ __forceinline__ void epilogue_store(const GemmKernelArgs& args, uint32_t tmem_base, int as, int q, int lane,
+                                               int g, int m_blk, int n_blk) {
+    const int m = m_blk * kBM + q * 32 + lane;
+    const bool m_ok = m < args.M;
+    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+
+    // per-row output bases
+    size_t row_base = 0;
+    int img = 0, pix = 0;
+    if (args.epilogue == EPI_ROWMAJOR) {
+        row_base = (static_cast<size_t>(g) * args.M + (m_ok ? m : 0)) * args.ldd;
+    } else if (args.epilogue == EPI_NCHW) {
+        const long long mg = args.m_offset + (m_ok ? m : 0);
+        img = static_cast<int>(mg / args.P);
+        pix = static_cast<int>(mg - static_cast<long long>(img) * args.P);
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n0 = n_blk * BN + c0;
+        if (n0 >= args.N) break;  // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr0 + c0, r);
+        ptx::tmem_ld_wait();
+        if (m_ok) {
+            if (args.epilogue == EPI_ROWMAJOR) {
+                float* dst = args.D + row_base + n0;
+                if (n0 + 32 <= args.N && (args.ldd & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        *reinterpret_cast<float4*>(dst + j) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j < args.N) dst[j] = __uint_as_float(r[j]);
+                }
+            } else if (args.epilogue == EPI_NCHW) {
+                // lanes hold consecutive pixels -> each column store is a coalesced 128-byte line
+                float* dst = args.D + (static_cast<size_t>(img) * args.N + n0) * args.P + pix;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (n0 + j < args.N) {
+                        float v = __uint_as_float(r[j]);
+                        if (args.bias) v += __ldg(args.bias + n0 + j);
+                        if (args.relu) v = fmaxf(v, 0.f);
+                        dst[static_cast<size_t>(j) * args.P] = v;
+                    }
+                }
+            } else {  // EPI_COLMAJOR_ATOMIC
+                float* dst = args.D + static_cast<size_t>(n0) * args.ldd + m;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (n0 + j < args.N) {
+                        if (args.split_k > 1)
+                            atomicAdd(dst + static_cast<size_t>(j) * args.ldd, __uint_as_float(r[j]));
+                        else
+                            dst[static_cast<size_t>(j) * args.ldd] += __uint_as_float(r[j]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int BN, int PLANES, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 tensor_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
@@ -183,69 +252,235 @@ tensor_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             ptx::mbar_wait(&tmem_full_bar[as], aphase);
             ptx::tc_fence_after();
 
-            const int m = m_blk * kBM + q * 32 + lane;
-            const bool m_ok = m < args.M;
-            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            epilogue_store<BN>(args, tmem_base, as, q, lane, g, m_blk, n_blk);
+            // hand the accumulator stage back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+        }
+    }
 
-            // per-row output bases
-            size_t row_base = 0;
-            int img = 0, pix = 0;
-            if (args.epilogue == EPI_ROWMAJOR) {
-                row_base = (static_cast<size_t>(g) * args.M + (m_ok ? m : 0)) * args.ldd;
-            } else if (args.epilogue == EPI_NCHW) {
-                const long long mg = args.m_offset + (m_ok ? m : 0);
-                img = static_cast<int>(mg / args.P);
-                pix = static_cast<int>(mg - static_cast<long long>(img) * args.P);
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// 3xTF32 kernel: A raw in global memory, split in-kernel into tensor memory, TS-form MMAs
+// --------------------------------------------------------------------------------------------
+// warp 0 TMA | warp 1 MMA | warps 2-5 epilogue | warps 6-9 and 10-13 splitter groups (alternate k-blocks)
+constexpr int kThreadsTs = 14 * 32;
+constexpr int kStagesTs = 4;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreadsTs, 1)
+tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmBlo, const GemmKernelArgs args) {
+    constexpr int STAGES = kStagesTs;
+    constexpr int kATile = kBM * kBK * 4;  // 16 KB raw A
+    constexpr int kBTile = BN * kBK * 4;
+    constexpr int kStage = kATile + 2 * kBTile;  // [A raw][B_hi][B_lo]
+    constexpr uint32_t kAccCols = 2 * BN;
+    constexpr uint32_t kAStageCols = 64;         // [A_hi 32 cols][A_lo 32 cols]
+    constexpr uint32_t kNeedCols = kAccCols + STAGES * kAStageCols;
+    constexpr uint32_t kTmemCols = kNeedCols <= 64 ? 64 : kNeedCols <= 128 ? 128 : kNeedCols <= 256 ? 256 : 512;
+    static_assert(kNeedCols <= 512, "TMEM budget");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    __shared__ uint64_t full_bar[STAGES];     // TMA landed A raw + B_hi + B_lo
+    __shared__ uint64_t a_ready_bar[STAGES];  // a splitter group parked A_hi/A_lo in TMEM
+    __shared__ uint64_t empty_bar[STAGES];    // MMAs reading the stage (smem B, TMEM A) retired
+    __shared__ uint64_t tmem_full_bar[2];
+    __shared__ uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_per_g = args.num_m * args.num_n;
+    const int total_tiles = tiles_per_g * args.G * args.split_k;
+    const int kb_per_split = (args.k_blocks_total + args.split_k - 1) / args.split_k;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&a_ready_bar[s], 4);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tmem_full_bar[s], 1);
+            ptx::mbar_init(&tmem_empty_bar[s], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+        ptx::prefetch_tensormap(&tmBlo);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t tmem_a0 = tmem_base + kAccCols;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        const bool leader = ptx::elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int ks = tile / (tiles_per_g * args.G);
+            const int rem = tile - ks * (tiles_per_g * args.G);
+            const int g = rem / tiles_per_g;
+            const int mn = rem - g * tiles_per_g;
+            const int m_blk = mn / args.num_n;
+            const int n_blk = mn - m_blk * args.num_n;
+            const int kb0 = ks * kb_per_split;
+            const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (leader) {
+                    uint8_t* st = smem + stage * kStage;
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kStage);
+                    ptx::tma_load_3d(st, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM, g);
+                    ptx::tma_load_3d(st + kATile, &tmB, &full_bar[stage], kb * kBK, n_blk * BN, g);
+                    ptx::tma_load_3d(st + kATile + kBTile, &tmBlo, &full_bar[stage], kb * kBK, n_blk * BN, g);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                const int n0 = n_blk * BN + c0;
-                if (n0 >= args.N) break;  // warp-uniform
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(taddr0 + c0, r);
-                ptx::tmem_ld_wait();
-                if (m_ok) {
-                    if (args.epilogue == EPI_ROWMAJOR) {
-                        float* dst = args.D + row_base + n0;
-                        if (n0 + 32 <= args.N && (args.ldd & 3) == 0) {
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_tf32(BN);
+        const bool leader = ptx::elect_one();
+        const uint64_t dB0 = make_smem_desc_sw128(ptx::smem_u32(smem) + kATile);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int ks = tile / (tiles_per_g * args.G);
+            const int kb0 = ks * kb_per_split;
+            const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(&a_ready_bar[stage], phase);  // implies full_bar: the splitters waited on it
+                ptx::tc_fence_after();
+                if (leader) {
+                    const uint64_t dB = dB0 + static_cast<uint64_t>(stage * (kStage >> 4));
+                    const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
+                    const uint32_t ta = tmem_a0 + stage * kAStageCols;
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                                *reinterpret_cast<float4*>(dst + j) = v;
-                            }
-                        } else {
+                    for (int k = 0; k < kBK / 8; ++k) {
+                        const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
+                        umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);   // A_lo * B_hi
+                        umma_tf32_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_hi * B_lo
+                        umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);           // A_hi * B_hi
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (leader) ptx::umma_commit(&tmem_full_bar[as]);
+            __syncwarp();
+        }
+    } else if (warp >= 6) {
+        // ===================== splitters: smem raw A row -> TF32 hi / fp32 lo -> tensor memory =====================
+        const int group = (warp - 6) >> 2;
+        const int q = warp & 3;  // TMEM lane quadrant == 32-row slice of the tile
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t row_off = static_cast<uint32_t>(row) * 128;
+        const uint32_t sw = static_cast<uint32_t>(row & 7);  // 128B swizzle: 16-byte chunk c lives at c ^ (row & 7)
+        int stage = 0, g_par = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int ks = tile / (tiles_per_g * args.G);
+            const int kb0 = ks * kb_per_split;
+            const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const bool mine = g_par == group;
+                const int my_stage = stage;
+                const uint32_t my_phase = phase;
+                g_par ^= 1;
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (!mine) continue;
+                ptx::mbar_wait(&full_bar[my_stage], my_phase);
+                const uint8_t* a = smem + my_stage * kStage + row_off;
+                const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (n0 + j < args.N) dst[j] = __uint_as_float(r[j]);
-                        }
-                    } else if (args.epilogue == EPI_NCHW) {
-                        // lanes hold consecutive pixels -> each column store is a coalesced 128-byte line
-                        float* dst = args.D + (static_cast<size_t>(img) * args.N + n0) * args.P + pix;
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t hi[16], lo[16];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (n0 + j < args.N) {
-                                float v = __uint_as_float(r[j]);
-                                if (args.bias) v += __ldg(args.bias + n0 + j);
-                                if (args.relu) v = fmaxf(v, 0.f);
-                                dst[static_cast<size_t>(j) * args.P] = v;
-                            }
-                        }
-                    } else {  // EPI_COLMAJOR_ATOMIC
-                        float* dst = args.D + static_cast<size_t>(n0) * args.ldd + m;
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t chunk = static_cast<uint32_t>(half * 4 + c) ^ sw;
+                        const float4 v = *reinterpret_cast<const float4*>(a + (chunk << 4));
+                        const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (n0 + j < args.N) {
-                                if (args.split_k > 1)
-                                    atomicAdd(dst + static_cast<size_t>(j) * args.ldd, __uint_as_float(r[j]));
-                                else
-                                    dst[static_cast<size_t>(j) * args.ldd] += __uint_as_float(r[j]);
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            hi[c * 4 + j] = __float_as_uint(x[j]) & 0xFFFFE000u;   // what the tensor core would read
+                            lo[c * 4 + j] = __float_as_uint(x[j] - __uint_as_float(hi[c * 4 + j]));  // exact remainder
                         }
                     }
+                    tmem_st_32x16(ta + half * 16, hi);
+                    tmem_st_32x16(ta + 32 + half * 16, lo);
                 }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&a_ready_bar[my_stage]);
             }
-            // hand the accumulator stage back to the MMA warp
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int ks = tile / (tiles_per_g * args.G);
+            const int rem = tile - ks * (tiles_per_g * args.G);
+            const int g = rem / tiles_per_g;
+            const int mn = rem - g * tiles_per_g;
+            const int m_blk = mn / args.num_n;
+            const int n_blk = mn - m_blk * args.num_n;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait_relaxed(&tmem_full_bar[as], aphase);
+            ptx::tc_fence_after();
+            epilogue_store<BN>(args, tmem_base, as, q, lane, g, m_blk, n_blk);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
@@ -353,8 +588,8 @@ bool tensor_gemm_supported(const GemmProblem& p) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.G <= 0) return false;
     if (p.K % 4 != 0) return false;
     auto aligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    if (!aligned(p.A_hi) || !aligned(p.B_hi)) return false;
-    if (p.planes == 2 && (!p.A_lo || !p.B_lo || !aligned(p.A_lo) || !aligned(p.B_lo))) return false;
+    if (!aligned(p.A) || !aligned(p.B_hi)) return false;
+    if (p.planes == 2 && (!p.B_lo || !aligned(p.B_lo))) return false;
     if (p.a_batch_stride % 4 != 0 || p.b_batch_stride % 4 != 0) return false;
     return true;
 }
@@ -367,10 +602,10 @@ static int launch(const GemmProblem& p, cudaStream_t stream) {
     const long long as = p.a_batch_stride ? p.a_batch_stride : static_cast<long long>(p.M) * p.K;
     const long long bs = p.b_batch_stride ? p.b_batch_stride : static_cast<long long>(p.N) * p.K;
     int rc;
-    if ((rc = make_map(&tmA, p.A_hi, p.K, p.M, p.G, as, kBM))) return rc;
+    if ((rc = make_map(&tmA, p.A, p.K, p.M, p.G, as, kBM))) return rc;
     if ((rc = make_map(&tmB, p.B_hi, p.K, p.N, p.G, bs, BN))) return rc;
     if (PLANES == 2) {
-        if ((rc = make_map(&tmAlo, p.A_lo, p.K, p.M, p.G, as, kBM))) return rc;
+        tmAlo = tmA;
         if ((rc = make_map(&tmBlo, p.B_lo, p.K, p.N, p.G, bs, BN))) return rc;
     } else {
         tmAlo = tmA;
@@ -417,14 +652,74 @@ static int launch(const GemmProblem& p, cudaStream_t stream) {
     return 0;
 }
 
+static void fill_kernel_args(const GemmProblem& p, int bn, GemmKernelArgs* a) {
+    a->D = p.D; a->bias = p.bias;
+    a->M = p.M; a->N = p.N; a->K = p.K; a->G = p.G;
+    a->epilogue = p.epilogue; a->ldd = p.ldd; a->P = p.P > 0 ? p.P : 1; a->relu = p.relu;
+    a->split_k = p.split_k > 0 ? p.split_k : 1;
+    a->m_offset = p.m_offset;
+    a->num_m = ceil_div(p.M, kBM);
+    a->num_n = ceil_div(p.N, bn);
+    a->k_blocks_total = ceil_div(p.K, kBK);
+    if (a->split_k > a->k_blocks_total) a->split_k = a->k_blocks_total;
+    // every k-split must own at least one k-block, otherwise its accumulator is never written
+    while (a->split_k > 1 && ceil_div(a->k_blocks_total, a->split_k) * (a->split_k - 1) >= a->k_blocks_total) --a->split_k;
+}
+
+template <int BN>
+static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
+    CUtensorMap tmA, tmB, tmBlo;
+    const long long as = p.a_batch_stride ? p.a_batch_stride : static_cast<long long>(p.M) * p.K;
+    const long long bs = p.b_batch_stride ? p.b_batch_stride : static_cast<long long>(p.N) * p.K;
+    int rc;
+    if ((rc = make_map(&tmA, p.A, p.K, p.M, p.G, as, kBM))) return rc;
+    if ((rc = make_map(&tmB, p.B_hi, p.K, p.N, p.G, bs, BN))) return rc;
+    if ((rc = make_map(&tmBlo, p.B_lo, p.K, p.N, p.G, bs, BN))) return rc;
+    GemmKernelArgs a;
+    fill_kernel_args(p, BN, &a);
+    const long long total = static_cast<long long>(a.num_m) * a.num_n * a.G * a.split_k;
+    if (total > 0x7fffffffLL) return -1;
+    const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+    constexpr int kStage = kBM * kBK * 4 + 2 * BN * kBK * 4;
+    static_assert(kStagesTs * kStage + 1024 <= 227 * 1024, "smem budget");
+    const int smem = kStagesTs * kStage + 1024;
+    auto kern = tensor_gemm_ts_kernel<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    ProfRec rec{};
+    if (g_prof_on) {
+        cudaEventCreate(&rec.e0);
+        cudaEventCreate(&rec.e1);
+        const double dense = 2.0 * p.M * static_cast<double>(p.N) * p.K * p.G;
+        rec.algo_flops = p.algo_flops > 0 ? p.algo_flops : dense;
+        rec.mma_flops = dense * 3.0;
+        cudaEventRecord(rec.e0, stream);
+    }
+    kern<<<grid, kThreadsTs, smem, stream>>>(tmA, tmB, tmBlo, a);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    if (g_prof_on) {
+        cudaEventRecord(rec.e1, stream);
+        g_prof.push_back(rec);
+    }
+    return 0;
+}
+
 int tensor_gemm(const GemmProblem& p, cudaStream_t stream) {
     if (!tensor_gemm_supported(p)) return -1;
     if (p.split_k > 1 && p.epilogue != EPI_COLMAJOR_ATOMIC) return -1;
-    const bool x3 = p.planes == 2;
-    // N tile: smallest supported tile that covers N (fewer wasted MMA columns), capped at 128/256.
-    if (p.N <= 32) return x3 ? launch<32, 2, 4>(p, stream) : launch<32, 1, 8>(p, stream);
-    if (p.N <= 64) return x3 ? launch<64, 2, 4>(p, stream) : launch<64, 1, 8>(p, stream);
-    if (p.N <= 128 || x3) return x3 ? launch<128, 2, 3>(p, stream) : launch<128, 1, 6>(p, stream);
+    if (p.planes == 2) {
+        if (p.N <= 32) return launch_ts<32>(p, stream);
+        if (p.N <= 64) return launch_ts<64>(p, stream);
+        return launch_ts<128>(p, stream);
+    }
+    // N tile: smallest supported tile that covers N (fewer wasted MMA columns), capped at 256.
+    if (p.N <= 32) return launch<32, 1, 8>(p, stream);
+    if (p.N <= 64) return launch<64, 1, 8>(p, stream);
+    if (p.N <= 128) return launch<128, 1, 6>(p, stream);
     return launch<256, 1, 4>(p, stream);
 }
 
@@ -504,8 +799,7 @@ int simt_gemm(const GemmProblem& p, cudaStream_t stream) {
     const long long as = p.a_batch_stride ? p.a_batch_stride : static_cast<long long>(p.M) * p.K;
     const long long bs = p.b_batch_stride ? p.b_batch_stride : static_cast<long long>(p.N) * p.K;
     dim3 grid(a.num_n, a.num_m, p.G);
-    simt_gemm_kernel<<<grid, 256, 0, stream>>>(p.A_hi, p.planes == 2 ? p.A_lo : nullptr, p.B_hi,
-                                               p.planes == 2 ? p.B_lo : nullptr, as, bs, a);
+    simt_gemm_kernel<<<grid, 256, 0, stream>>>(p.A, nullptr, p.B_hi, p.planes == 2 ? p.B_lo : nullptr, as, bs, a);
     FCUDA_CHECK_LAUNCH();
     return 0;
 }

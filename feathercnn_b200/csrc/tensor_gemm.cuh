@@ -4,11 +4,16 @@
 //
 //   for g in [0,G):   D_g[M x N] = A_g[M x K] * B_g[N x K]^T        (fp32 in, fp32 out)
 //
-// Both operands are K-major ("TN").  The contraction runs on the 5th-gen tensor cores as
-// kind::tf32 UMMA with fp32 accumulation in TMEM.  fp32 semantics are recovered with the
-// 3xTF32 split: every operand is stored as a TF32-exact "hi" plane plus an fp32 remainder
-// "lo" plane (hi + lo == x exactly), and each k-step issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
-// PLANES == 1 runs plain TF32 (one MMA per k-step) on the hi planes only.
+// Both operands are K-major ("TN").  The contraction runs on the 5th-gen tensor cores as kind::tf32 UMMA with
+// fp32 accumulation in TMEM.  fp32 semantics are recovered with the 3xTF32 split (x = hi + lo exactly, hi
+// TF32-representable): each k-step issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
+//   B (the small, reused operand: transformed filters / packed weights / FC activations) carries its hi and lo
+//     planes in global memory (made once by the producer kernel);
+//   A (the big streamed operand: Winograd V, im2col rows, FC weights) is stored ONCE as plain fp32: the kernel
+//     lands the raw tile in shared memory by TMA, four splitter warps turn each row into hi/lo and park it in
+//     TENSOR MEMORY (tcgen05.st), and the MMAs read A from TMEM ("TS" form).  That halves A's HBM traffic and takes
+//     the A reads off the shared-memory port.
+// planes == 1 runs plain TF32 (one MMA per k-step, operands straight from shared memory).
 #pragma once
 
 #include <cuda.h>
@@ -29,12 +34,12 @@ enum GemmEpilogue : int {
 };
 
 struct GemmProblem {
-    // operands (device pointers).  *_lo may be null when planes == 1.
-    const float* A_hi; const float* A_lo;   // [G][M][K]
-    const float* B_hi; const float* B_lo;   // [G][N][K]
+    // operands (device pointers)
+    const float* A;                         // [G][M][K] plain fp32
+    const float* B_hi; const float* B_lo;   // [G][N][K]; B_lo may be null when planes == 1
     float* D;
     int M, N, K, G;
-    int planes;        // 1 = TF32, 2 = 3xTF32 (hi/lo split)
+    int planes;        // 1 = TF32, 2 = 3xTF32 (A split in-kernel, B_hi/B_lo planes)
     int epilogue;      // GemmEpilogue
     int ldd;           // EPI_ROWMAJOR / EPI_COLMAJOR_ATOMIC leading dimension (floats)
     int P;             // EPI_NCHW: pixels per image

@@ -9,11 +9,12 @@
 //
 // Layouts (private to this backend — parity is defined on NCHW blobs only):
 //   U[e][oc][ic]   transformed filters, K-major rows for the TensorGEMM B operand
-//   V[e][t][ic]    transformed input tiles, t = chunk-local tile index, K-major rows for the A operand
+//   V[e][t][ic]    transformed input tiles, t = chunk-local tile index, K-major rows for the A operand (plain fp32:
+//                  the TensorGEMM makes the TF32 hi/lo split on chip)
 //   M[e][t][oc]    products
-// Each of U and V exists as a TF32-exact "hi" plane and (3xTF32 mode) an fp32-remainder "lo" plane.
+// U exists as a TF32-exact "hi" plane and (3xTF32 mode) an fp32-remainder "lo" plane.
 //
-// Data movement: a block stages a (32 channels) x (8 rows) x (4 tiles wide) slab through shared memory so that
+// Data movement: a block stages a (32 channels) x (8 rows) x (5 tiles wide) slab through shared memory so that
 // global reads are coalesced along x and global writes are coalesced along the channel (K) dimension;
 // zero padding is applied by the bounds check of the slab load (no padded copy of the input is made).
 #include "winograd.cuh"
@@ -144,17 +145,21 @@ wino_filter_kernel(const float* __restrict__ w, float* __restrict__ U_hi, float*
 // ------------------------------------------------------------------------------------------------
 // Input transform  V = B^T d B
 // ------------------------------------------------------------------------------------------------
-constexpr int kSegTiles = 4;  // tiles per block along x (one warp each)
-constexpr int kChBlock = 32;  // channels per block (one lane each)
+// Both transform kernels are issue-bound if written naively (first version: 3.4k instructions per thread, 60% of
+// them index arithmetic of a flat slab loop), so the block shape is chosen to make the data movement trivially
+// addressable: 5 tiles per block => an input slab row is exactly 32 floats (5*6+2) — one warp request per
+// (channel,row) line — and an output slab row is 30 floats.  One warp per tile, one lane per channel.
+constexpr int kSegTiles = 5;   // tiles per block along x (one warp each)
+constexpr int kChBlock = 32;   // channels per block (one lane each)
+constexpr int kXformThreads = kSegTiles * 32;
 
 template <int T>
-__global__ void __launch_bounds__(128)
-wino_input_kernel(const float* __restrict__ in, float* __restrict__ V_hi, float* __restrict__ V_lo, WinoGeom g,
-                  int R0, int Tc) {
+__global__ void __launch_bounds__(kXformThreads)
+wino_input_kernel(const float* __restrict__ in, float* __restrict__ V, WinoGeom g, int R0, int Tc) {
     using W = Wino<T>;
     constexpr int OT = W::kOut;
-    constexpr int COLS = OT * kSegTiles + (T - OT);
-    constexpr int CH_STRIDE = T * COLS + 1;  // odd => conflict-free when lanes index channels
+    constexpr int COLS = OT * kSegTiles + (T - OT);  // 32 for F(6,3)
+    constexpr int CH_STRIDE = T * COLS + 1;          // odd => conflict-free when lanes index channels
     __shared__ float slab[kChBlock * CH_STRIDE];
 
     const int segs = (g.tilesX + kSegTiles - 1) / kSegTiles;
@@ -165,21 +170,25 @@ wino_input_kernel(const float* __restrict__ in, float* __restrict__ V_hi, float*
     const int tx0 = seg * kSegTiles;
     const int c0 = blockIdx.y * kChBlock;
     const int gy0 = ty * OT - g.pad_top, gx0 = tx0 * OT - g.pad_left;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const float* img = in + static_cast<size_t>(n) * g.C_in * g.H * g.W;
-    for (int idx = threadIdx.x; idx < kChBlock * T * COLS; idx += 128) {
-        const int c = idx / (T * COLS);
-        const int rem = idx - c * (T * COLS);
-        const int r = rem / COLS, x = rem - r * COLS;
-        const int ic = c0 + c, gy = gy0 + r, gx = gx0 + x;
-        float v = 0.f;
-        if (ic < g.C_in && gy >= 0 && gy < g.H && gx >= 0 && gx < g.W)
-            v = __ldg(img + (static_cast<size_t>(ic) * g.H + gy) * g.W + gx);
-        slab[c * CH_STRIDE + r * COLS + x] = v;
+    // slab load: warp w takes the (channel,row) lines w, w+5, ...; lane = column.  All index math is per line and
+    // warp-uniform; the lane only adds its column.
+    {
+        const size_t plane = static_cast<size_t>(g.H) * g.W;
+        const float* img = in + static_cast<size_t>(n) * g.C_in * plane;
+        const int gx = gx0 + lane;
+        const bool x_ok = lane < COLS && gx >= 0 && gx < g.W;
+        for (int line = w; line < kChBlock * T; line += kSegTiles) {
+            const int c = line / T, r = line - c * T;  // T is a power of two
+            const int ic = c0 + c, gy = gy0 + r;
+            float v = 0.f;
+            if (x_ok && ic < g.C_in && gy >= 0 && gy < g.H) v = __ldg(img + ic * plane + static_cast<size_t>(gy) * g.W + gx);
+            if (lane < COLS) slab[c * CH_STRIDE + r * COLS + lane] = v;
+        }
     }
     __syncthreads();
 
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = tx0 + w, ic = c0 + lane;
     if (tx >= g.tilesX || ic >= g.C_in) return;
     const float* d = slab + lane * CH_STRIDE + w * OT;
@@ -196,23 +205,15 @@ wino_input_kernel(const float* __restrict__ in, float* __restrict__ V_hi, float*
     }
     const size_t tp = static_cast<size_t>(Rl) * g.tilesX + tx;  // chunk-local tile index
     const size_t plane = static_cast<size_t>(Tc) * g.C_in;     // floats per tile element
-    float* vh = V_hi + tp * g.C_in + ic;
-    float* vl = V_lo ? V_lo + tp * g.C_in + ic : nullptr;
+    float* vp = V + tp * g.C_in + ic;                          // plain fp32: the TensorGEMM splits hi/lo on chip
 #pragma unroll
     for (int a = 0; a < T; ++a) {
         float o[T];
         W::bt(t[a], o);
 #pragma unroll
         for (int b = 0; b < T; ++b) {
-            const size_t off = static_cast<size_t>(a * T + b) * plane;
-            if (vl) {
-                float hi, lo;
-                split_tf32(o[b], hi, lo);
-                vh[off] = hi;
-                vl[off] = lo;
-            } else {
-                vh[off] = o[b];
-            }
+            *vp = o[b];
+            vp += plane;
         }
     }
 }
@@ -221,12 +222,12 @@ wino_input_kernel(const float* __restrict__ in, float* __restrict__ V_hi, float*
 // Output transform  Y = A^T M A  (+bias, ReLU), clipped NCHW store
 // ------------------------------------------------------------------------------------------------
 template <int T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kXformThreads)
 wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const float* __restrict__ bias, WinoGeom g,
                    int R0, int Tc, int relu) {
     using W = Wino<T>;
     constexpr int OT = W::kOut;
-    constexpr int COLS = OT * kSegTiles;
+    constexpr int COLS = OT * kSegTiles;     // 30 for F(6,3)
     constexpr int CH_STRIDE = OT * COLS + 1;
     __shared__ float slab[kChBlock * CH_STRIDE];
 
@@ -244,12 +245,20 @@ wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const f
         const size_t tp = static_cast<size_t>(Rl) * g.tilesX + tx;
         const size_t plane = static_cast<size_t>(Tc) * g.C_out;
         const float* m = M + tp * g.C_out + oc;
+        float mm[T][T];
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+            for (int b = 0; b < T; ++b) {
+                mm[a][b] = __ldg(m);
+                m += plane;
+            }
         float tmp[OT][T];
 #pragma unroll
         for (int b = 0; b < T; ++b) {
             float col[T], s[OT];
 #pragma unroll
-            for (int a = 0; a < T; ++a) col[a] = __ldg(m + static_cast<size_t>(a * T + b) * plane);
+            for (int a = 0; a < T; ++a) col[a] = mm[a][b];
             W::at(col, s);
 #pragma unroll
             for (int i = 0; i < OT; ++i) tmp[i][b] = s[i];
@@ -270,15 +279,15 @@ wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const f
     }
     __syncthreads();
 
-    const int oy0 = ty * OT, ox0 = tx0 * OT;
-    float* img = out + static_cast<size_t>(n) * g.C_out * g.OH * g.OW;
-    for (int idx = threadIdx.x; idx < kChBlock * OT * COLS; idx += 128) {
-        const int c = idx / (OT * COLS);
-        const int rem = idx - c * (OT * COLS);
-        const int r = rem / COLS, x = rem - r * COLS;
-        const int o = c0 + c, oy = oy0 + r, ox = ox0 + x;
-        if (o < g.C_out && oy < g.OH && ox < g.OW)
-            img[(static_cast<size_t>(o) * g.OH + oy) * g.OW + ox] = slab[c * CH_STRIDE + r * COLS + x];
+    // store: warp w takes the (channel,row) lines w, w+5, ...; lane = column (30 of 32 lanes active)
+    const int oy0 = ty * OT, ox = tx0 * OT + lane;
+    const size_t oplane = static_cast<size_t>(g.OH) * g.OW;
+    float* img = out + static_cast<size_t>(n) * g.C_out * oplane;
+    const bool x_ok = lane < COLS && ox < g.OW;
+    for (int line = w; line < kChBlock * OT; line += kSegTiles) {
+        const int c = line / OT, r = line - c * OT;
+        const int o = c0 + c, oy = oy0 + r;
+        if (x_ok && o < g.C_out && oy < g.OH) img[o * oplane + static_cast<size_t>(oy) * g.OW + ox] = slab[c * CH_STRIDE + r * COLS + lane];
     }
 }
 
@@ -295,13 +304,12 @@ int wino_filter_transform(int tile, const float* w, float* U_hi, float* U_lo, in
     return 0;
 }
 
-int wino_input_transform(int tile, const float* in, float* V_hi, float* V_lo, const WinoGeom& g, int R0, int R1,
-                         cudaStream_t s) {
+int wino_input_transform(int tile, const float* in, float* V, const WinoGeom& g, int R0, int R1, cudaStream_t s) {
     const int segs = ceil_div(g.tilesX, kSegTiles);
     const int Tc = (R1 - R0) * g.tilesX;
     dim3 grid(static_cast<unsigned>(segs) * (R1 - R0), ceil_div(g.C_in, kChBlock));
-    if (tile == 8) wino_input_kernel<8><<<grid, 128, 0, s>>>(in, V_hi, V_lo, g, R0, Tc);
-    else wino_input_kernel<4><<<grid, 128, 0, s>>>(in, V_hi, V_lo, g, R0, Tc);
+    if (tile == 8) wino_input_kernel<8><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
+    else wino_input_kernel<4><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;
@@ -312,8 +320,8 @@ int wino_output_transform(int tile, const float* M, float* out, const float* bia
     const int segs = ceil_div(g.tilesX, kSegTiles);
     const int Tc = (R1 - R0) * g.tilesX;
     dim3 grid(static_cast<unsigned>(segs) * (R1 - R0), ceil_div(g.C_out, kChBlock));
-    if (tile == 8) wino_output_kernel<8><<<grid, 128, 0, s>>>(M, out, bias, g, R0, Tc, relu);
-    else wino_output_kernel<4><<<grid, 128, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+    if (tile == 8) wino_output_kernel<8><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+    else wino_output_kernel<4><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;

@@ -96,9 +96,10 @@ int fcuda_conv_forward(const FcudaConvParam* param, int algo, float* output, con
 
 /* The 64-way batched "TensorGEMM" itself (avx/winograd_kernels_F63.cpp:518-757), exposed for tests and
  * profiling:  for g < G:  D[g][m][n] = sum_k A[g][m][k] * B[g][n][k]   (row-major, K-major operands).
- * a_lo/b_lo are the fp32 remainders of the TF32 split (may be NULL => plain TF32). */
-int fcuda_tensor_gemm(float* d, const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo,
-                      int m, int n, int k, int g, void* stream);
+ * `a` is plain fp32 (split into TF32 hi + fp32 lo inside the kernel, in tensor memory); b_hi/b_lo are the planes of
+ * fcuda_split_tf32(b) (b_lo NULL => plain TF32 on a and b_hi). */
+int fcuda_tensor_gemm(float* d, const float* a, const float* b_hi, const float* b_lo, int m, int n, int k, int g,
+                      void* stream);
 /* Elementwise TF32 split used to prepare TensorGEMM operands: hi + lo == x exactly. */
 int fcuda_split_tf32(float* hi, float* lo, const float* x, size_t n, void* stream);
 

@@ -70,7 +70,8 @@ static int run_case(const Case& c, int planes, bool bench) {
     CK(cudaMemset(dR, 0, nD * 4));
 
     GemmProblem p{};
-    p.A_hi = dAh; p.A_lo = dAl; p.B_hi = dBh; p.B_lo = dBl; p.D = dD;
+    CK(cudaMemcpy(dAh, A.data(), nA * 4, cudaMemcpyHostToDevice));  // A goes in as plain fp32
+    p.A = dAh; p.B_hi = dBh; p.B_lo = dBl; p.D = dD;
     p.M = c.M; p.N = c.N; p.K = c.K; p.G = c.G; p.planes = planes; p.epilogue = c.epi; p.ldd = ldd;
     p.P = c.P; p.bias = (c.epi == EPI_NCHW) ? dbias : nullptr; p.relu = (c.epi == EPI_NCHW) ? 1 : 0;
     p.split_k = c.split_k;
@@ -114,7 +115,7 @@ static int run_case(const Case& c, int planes, bool bench) {
                 }
     }
     const double rel = max_err / (max_ref > 0 ? max_ref : 1);
-    const double tol = planes == 2 ? 2e-5 : 4e-3;
+    const double tol = planes == 2 ? 5e-5 : 4e-3;  // 3xTF32: fp32-level, summation order differs from the SIMT reference
     const bool ok = rel < tol && (max_err_host < 0 || max_err_host / (max_ref > 0 ? max_ref : 1) < tol);
     printf("M=%6d N=%4d K=%5d G=%3d epi=%d splitk=%d planes=%d : max|ref|=%.3g rel_err_vs_simt=%.3g host_abs_err=%.3g %s\n",
            c.M, c.N, c.K, c.G, c.epi, c.split_k, planes, max_ref, rel, max_err_host, ok ? "OK" : "FAIL");

@@ -86,7 +86,7 @@ def test_workspace_planning_is_host_only_and_consistent():
     s1, k1 = cb.GetBufferSize(p, 1)
     s64, k64 = cb.GetBufferSize(p, 64)
     assert k1 == k64 == 2 * 64 * 64 * 64          # hi + lo planes of U[64][OC][IC]
-    assert s1 == 64 * 100 * (2 * 64 + 64)          # V hi/lo + M for the 10x10 tiles of one image
+    assert s1 == 64 * 100 * (64 + 64)              # V (plain fp32, split on chip) + M for the 10x10 tiles of one image
     assert s64 >= s1
     booster.set_precision(booster.PRECISION_TF32)
     try:
