@@ -30,11 +30,29 @@
 
 namespace fcuda {
 
+// Optional timeline of CTA 0 (tests/cuda/igemm_trace.cu builds this file with -DFCUDA_IGEMM_TRACE): clock64() of the
+// hand-offs of the first 64 k-blocks, one row per event kind.
+#ifdef FCUDA_IGEMM_TRACE
+__device__ long long g_igemm_trace[16 * 64];
+#define IG_TRACE(slot, idx)                                                                              \
+    do {                                                                                                 \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (idx) < 64u) g_igemm_trace[(slot) * 64 + (idx)] = clock64(); \
+    } while (0)
+int igemm_trace_read(long long* host) {
+    return cudaMemcpyFromSymbol(host, g_igemm_trace, sizeof(long long) * 16 * 64) == cudaSuccess ? 0 : -1;
+}
+#else
+#define IG_TRACE(slot, idx) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int kGroups = 3;                                // producer groups, 4 warps (128 pixels) each
-constexpr int kThreadsIg = (8 + 4 * kGroups) * 32;        // warp 0 TMA(B), 1 MMA, 4-7 epilogue, 8.. producers
+constexpr int kWarpTma = 4 + 4 * kGroups;                  // warps 0-3 epilogue, 4.. producers (quadrant = warp % 4),
+constexpr int kWarpMma = kWarpTma + 1;                    // then one TMA(B) warp and one MMA warp: no idle warps, so
+constexpr int kThreadsIg = (kWarpMma + 1) * 32;           // 576 threads leave 112 registers for the producers
 constexpr int kStagesIg = 4;                              // ring depth shared by the smem B tiles and the TMEM A tiles
+constexpr int kMaxBStages = 8;                            // filter-tile ring: deeper than the A ring, as smem allows
 constexpr int kMaxTableK = 8192;                          // k-table entries that fit beside the B ring
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -67,6 +85,7 @@ struct IgemmArgs {
     int num_n;               // ceil(OC / BN)
     long long pixel_tiles;   // ceil(total_boxes / 4)
     int relu;
+    int bstages;             // depth of the filter-tile ring in shared memory (<= kMaxBStages)
 };
 
 struct BoxCoord { int n, oy, ox0; bool valid; };
@@ -104,6 +123,12 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int BN, int PLANES>
@@ -121,10 +146,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    int2* ktab = reinterpret_cast<int2*>(smem + STAGES * kStage);  // {element offset, tap index} per k
+    int2* ktab = reinterpret_cast<int2*>(smem + args.bstages * kStage);  // {element offset, tap index} per k
 
-    __shared__ uint64_t b_full_bar[STAGES];   // filters landed (TMA transaction bytes)
-    __shared__ uint64_t a_ready_bar[STAGES];  // the 4 producer warps of the owning group stored their TMEM quadrant
+    // A ring (tensor memory, STAGES slots): full = 4 arrivals of the owning producer group, empty = MMAs retired.
+    // B ring (shared memory, args.bstages slots, deeper: a filter tile is ~1.5k cycles away — relaxed wake-up of the
+    // TMA warp + L2 latency — while an A slot turns around in 3 k-blocks of MMA time).
+    __shared__ uint64_t full_bar[STAGES];
+    __shared__ uint64_t b_full_bar[kMaxBStages];
+    __shared__ uint64_t b_empty_bar[kMaxBStages];
     __shared__ uint64_t empty_bar[STAGES];    // MMAs that read the stage have retired
     __shared__ uint64_t tmem_full_bar[2];
     __shared__ uint64_t tmem_empty_bar[2];
@@ -138,9 +167,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            ptx::mbar_init(&b_full_bar[s], 1);
-            ptx::mbar_init(&a_ready_bar[s], 4);
+            ptx::mbar_init(&full_bar[s], 4);
             ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < kMaxBStages; ++s) {
+            ptx::mbar_init(&b_full_bar[s], 1);
+            ptx::mbar_init(&b_empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full_bar[s], 1);
@@ -148,7 +180,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) {
+    if (warp == kWarpTma && lane == 0) {
         ptx::prefetch_tensormap(&tmW);
         if (PLANES == 2) ptx::prefetch_tensormap(&tmWlo);
     }
@@ -163,7 +195,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             ktab[k] = e;
         }
     }
-    if (warp == 1) {
+    if (warp == kWarpMma) {
         ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
         ptx::tmem_relinquish();
     }
@@ -173,52 +205,63 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const uint32_t tmem_base = tmem_base_smem;
     const uint32_t tmem_a0 = tmem_base + kAccCols;
 
-    if (warp == 0) {
+    if (warp == kWarpTma) {
         // ===================== TMA producer for the filter tiles =====================
         const bool leader = ptx::elect_one();
-        int stage = 0;
-        uint32_t phase = 0;
+        int bs = 0;
+        uint32_t bphase = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n_blk = static_cast<int>(tile % args.num_n);
             for (int kb = 0; kb < kblocks; ++kb) {
-                ptx::mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+                ptx::mbar_wait(&b_empty_bar[bs], bphase ^ 1);
                 if (leader) {
-                    uint8_t* st = smem + stage * kStage;
-                    ptx::mbar_arrive_expect_tx(&b_full_bar[stage], PLANES * kBTile);
-                    ptx::tma_load_3d(st, &tmW, &b_full_bar[stage], kb * 32, n_blk * BN, 0);
-                    if (PLANES == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, &b_full_bar[stage], kb * 32, n_blk * BN, 0);
+                    uint8_t* st = smem + bs * kStage;
+                    ptx::mbar_arrive_expect_tx(&b_full_bar[bs], PLANES * kBTile);
+                    ptx::tma_load_3d(st, &tmW, &b_full_bar[bs], kb * 32, n_blk * BN, 0);
+                    if (PLANES == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, &b_full_bar[bs], kb * 32, n_blk * BN, 0);
                 }
                 __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (++bs == args.bstages) { bs = 0; bphase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kWarpMma) {
         // ===================== MMA issuer =====================
         // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.  Descriptors are
         // formed once: per k-block only the stage offset (in 16-byte units / TMEM columns) is added.
+        // The tensor pipe's queue is shallow (measured: issuing 12 MMAs takes as long as executing them, and anything
+        // the warp does after the last issue runs with ~1.5 MMAs of work left), so nothing slow may sit between two
+        // k-blocks: the barrier of the NEXT slot is probed half-way through the current slot's MMAs and the blocking
+        // wait is only the fallback.
         constexpr uint32_t idesc = make_idesc_tf32(BN);
         const bool leader = ptx::elect_one();
         const uint64_t dB0 = make_smem_desc_sw128(ptx::smem_u32(smem));
-        int stage = 0;
-        uint32_t phase = 0;
+        int stage = 0, bs = 0;
+        uint32_t phase = 0, bphase = 0;
         long long it = 0;
+        bool ready = false;  // full_bar[stage] and b_full_bar[bs] already observed complete
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int as = static_cast<int>(it & 1);
             const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
             ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-            ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * BN;
             for (int kb = 0; kb < kblocks; ++kb) {
-                ptx::mbar_wait(&a_ready_bar[stage], phase);
-                ptx::mbar_wait(&b_full_bar[stage], phase);
+                if (!ready) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::mbar_wait(&b_full_bar[bs], bphase);
+                }
+                IG_TRACE(5, static_cast<uint32_t>(it * kblocks + kb));
                 ptx::tc_fence_after();
-                if (leader) {
-                    const uint64_t dB = dB0 + static_cast<uint64_t>(stage * (kStage >> 4));
-                    const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
-                    const uint32_t ta = tmem_a0 + stage * kAStageCols;
+                const int nstage = (stage + 1) & (STAGES - 1);
+                const uint32_t nphase = nstage == 0 ? phase ^ 1u : phase;
+                const int nbs = bs + 1 == args.bstages ? 0 : bs + 1;
+                const uint32_t nbphase = nbs == 0 ? bphase ^ 1u : bphase;
+                const uint64_t dB = dB0 + static_cast<uint64_t>(bs * (kStage >> 4));
+                const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
+                const uint32_t ta = tmem_a0 + stage * kAStageCols;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // 8 k-values (TMEM columns / 32 smem bytes) per MMA
-                        const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+                for (int k = 0; k < 4; ++k) {  // 8 k-values (TMEM columns / 32 smem bytes) per MMA
+                    const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+                    if (leader) {
                         if (PLANES == 2) {
                             umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);   // A_lo * B_hi
                             umma_tf32_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_hi * B_lo
@@ -227,33 +270,68 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                             umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, first);
                         }
                     }
+                    if (k == 1) {  // results needed after the last MMA
+                        const bool a_ok = ptx::mbar_test(&full_bar[nstage], nphase);
+                        const bool b_ok = ptx::mbar_test(&b_full_bar[nbs], nbphase);
+                        ready = a_ok && b_ok;
+                    }
+                }
+                if (leader) {
                     ptx::umma_commit(&empty_bar[stage]);
+                    ptx::umma_commit(&b_empty_bar[bs]);
                 }
                 __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                IG_TRACE(7, static_cast<uint32_t>(it * kblocks + kb));
+                stage = nstage; phase = nphase;
+                bs = nbs; bphase = nbphase;
             }
             if (leader) ptx::umma_commit(&tmem_full_bar[as]);
             __syncwarp();
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 4) {
         // ===================== A producers: gather + 3xTF32 split -> tensor memory =====================
-        const int pw = warp - 8;
-        const int group = pw >> 2;
+        // k-block number g (running over all tiles of this CTA) belongs to group g % kGroups and ring slot
+        // g % STAGES; a group visits only its own k-blocks.  The group is latency-bound, not issue-bound (a gather
+        // is ~800 cycles from L2), so the loop is software-pipelined: the 32 loads of the group's NEXT k-block — which
+        // may belong to the next tile — are issued before it waits for the tensor-memory stores of the current one.
+        static_assert((STAGES & (STAGES - 1)) == 0, "ring slot = g & (STAGES-1)");
+        const int group = (warp - 4) >> 2;
         const int q = warp & 3;  // TMEM lane quadrant this warp may write == box index inside the tile
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-        // running k-block index over all tiles of this CTA, kept as three small wrapping counters
-        int g_mod = 0;        // g % kGroups
-        int stage = 0;        // g % STAGES
-        uint32_t phase = 0;   // (g / STAGES) & 1
-        const int cblocks = args.IC >> 5;  // fast path only
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int cblocks = args.IC >> 5;                              // fast path only
+        const uint32_t plane_bytes = static_cast<uint32_t>(plane) * 4u;  // host guarantees H*W < 2^30
+        const int kb_mod = kblocks % kGroups;
+
+        // cursor over this group's k-blocks
+        long long tile = blockIdx.x;
+        uint32_t g0 = 0;   // running index of the current tile's k-block 0
+        int g0_mod = 0;    // g0 % kGroups
+        int kb = 0;
+        int tap = 0, tu = 0, tv = 0, cb = 0;  // fast path: k-block kb = tap * cblocks + cb, tap = tu*KW + tv
+        const float* base = args.in;
+        unsigned long long tapmask = 0;  // bit (u*KW+v) set <=> that tap of this lane's pixel lies inside the image
+        bool have = false;
+
+        // position the cursor on the first owned k-block of tile `tile` or a later tile
+        auto enter_tile = [&]() {
+            have = false;
+            while (tile < total_tiles) {
+                kb = group - g0_mod;
+                if (kb < 0) kb += kGroups;
+                if (kb < kblocks) { have = true; break; }
+                tile += gridDim.x;
+                g0 += static_cast<uint32_t>(kblocks);
+                g0_mod += kb_mod;
+                if (g0_mod >= kGroups) g0_mod -= kGroups;
+            }
+            if (!have) return;
             const long long ptile = tile / args.num_n;
             const BoxCoord bx = decode_box(ptile * 4 + q, args);
             const int ox = bx.ox0 + lane;
             const bool pix_ok = bx.valid && ox < args.OW;
             const int iy0 = bx.oy * args.stride_h - args.pad_top;
             const int ix0 = ox * args.stride_w - args.pad_left;
-            unsigned long long tapmask = 0;  // bit (u*KW+v) set <=> that tap of this pixel lies inside the image
+            tapmask = 0;
             if (pix_ok) {
                 for (int u = 0; u < args.KH; ++u) {
                     if (iy0 + u < 0 || iy0 + u >= args.H) continue;
@@ -261,80 +339,103 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         if (ix0 + v >= 0 && ix0 + v < args.W) tapmask |= 1ull << (u * args.KW + v);
                 }
             }
-            const float* base = args.in + (static_cast<long long>(bx.valid ? bx.n : 0) * args.IC) * plane +
-                                static_cast<long long>(iy0) * args.W + ix0;
-            asm volatile("" : "+l"(base));  // opaque, see the fast path below
-            int tap = 0, tu = 0, tv = 0, cb = 0;  // fast path: k-block kb = tap * cblocks + cb, tap = tu*KW + tv
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const bool mine = g_mod == group;
-                const int my_stage = stage;
-                const uint32_t my_phase = phase;
-                const int my_tap = tap, my_u = tu, my_v = tv, my_cb = cb;
-                // advance the counters for the next k-block
-                if (++g_mod == kGroups) g_mod = 0;
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                if (++cb == cblocks) { cb = 0; ++tap; if (++tv == args.KW) { tv = 0; ++tu; } }
-                if (!mine) continue;
-                const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
-                bool waited = false;
-                // fast path (IC % 32 == 0): the whole k-block is one tap -> one predicate, pointer + r*plane
-                const float* kp = base;
-                bool kb_ok = false;
-                if (!args.use_table) {
-                    kp = base + (static_cast<long long>(my_cb * 32) * plane + my_u * args.W + my_v);
-                    kb_ok = ((tapmask >> my_tap) & 1ull) != 0;
-                    // keep the pointer opaque: otherwise nvcc re-derives every address from args.in with ~8 integer
-                    // instructions per load; bumped by `plane` it is one IMAD.WIDE per load
-                    asm volatile("" : "+l"(kp));
-                }
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float x[16];
-                    if (!args.use_table) {
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) {
-                            x[r] = kb_ok ? __ldg(kp) : 0.f;
-                            kp += plane;
-                        }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) {
-                            const int2 e = ktab[kb * 32 + half * 16 + r];
-                            x[r] = ((tapmask >> e.y) & 1ull) ? __ldg(base + e.x) : 0.f;
-                        }
-                    }
-                    if (!waited) {  // the loads are in flight while the ring slot drains
-                        ptx::mbar_wait(&empty_bar[my_stage], my_phase ^ 1);
-                        ptx::tc_fence_after();
-                        waited = true;
-                    }
-                    uint32_t hi[16];
-                    if (PLANES == 2) {
-                        uint32_t lo[16];
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) {
-                            // hi = x with the 13 sub-TF32 mantissa bits cleared (what the tensor core would read
-                            // anyway), lo = x - hi exactly: 2 instructions per element instead of 5 for round-to-nearest;
-                            // the residual after the hardware truncates lo is <= 2^-21 |x| either way
-                            hi[r] = __float_as_uint(x[r]) & 0xFFFFE000u;
-                            lo[r] = __float_as_uint(x[r] - __uint_as_float(hi[r]));
-                        }
-                        tmem_st_32x16(ta + half * 16, hi);
-                        tmem_st_32x16(ta + 32 + half * 16, lo);
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) hi[r] = __float_as_uint(x[r]);
-                        tmem_st_32x16(ta + half * 16, hi);
-                    }
-                }
-                tmem_st_wait();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&a_ready_bar[my_stage]);
+            base = args.in + (static_cast<long long>(bx.valid ? bx.n : 0) * args.IC) * plane +
+                   static_cast<long long>(iy0) * args.W + ix0;
+            asm volatile("" : "+l"(base));  // opaque: see gather()
+            tap = 0; tu = 0; tv = 0; cb = kb;
+        };
+        auto advance = [&]() {
+            kb += kGroups;
+            cb += kGroups;
+            if (kb >= kblocks) {
+                tile += gridDim.x;
+                g0 += static_cast<uint32_t>(kblocks);
+                g0_mod += kb_mod;
+                if (g0_mod >= kGroups) g0_mod -= kGroups;
+                enter_tile();
             }
+        };
+        // issue the 32 loads of the cursor's k-block
+        auto gather = [&](float (&x)[32]) {
+            if (!args.use_table) {
+                // IC % 32 == 0: the whole k-block is one tap -> one predicate; the 32 channel addresses are
+                // kp + r*plane_bytes, one IMAD.WIDE each off an opaque pointer (otherwise nvcc re-derives every
+                // address from args.in with ~8 integer instructions per load)
+                while (cb >= cblocks) {
+                    cb -= cblocks;
+                    ++tap;
+                    if (++tv == args.KW) { tv = 0; ++tu; }
+                }
+                const char* kp = reinterpret_cast<const char*>(base) +
+                                 (static_cast<long long>(cb * 32) * plane + tu * args.W + tv) * 4;
+                asm volatile("" : "+l"(kp));
+                const bool kb_ok = ((tapmask >> tap) & 1ull) != 0;
+                if (__all_sync(0xffffffffu, kb_ok)) {  // interior: no predication, no zero fill
+#pragma unroll
+                    for (int r = 0; r < 32; ++r)
+                        x[r] = __ldg(reinterpret_cast<const float*>(
+                            kp + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(r)));
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 32; ++r)
+                        x[r] = kb_ok ? __ldg(reinterpret_cast<const float*>(
+                                           kp + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(r)))
+                                     : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const int2 e = ktab[kb * 32 + r];
+                    x[r] = ((tapmask >> e.y) & 1ull) ? __ldg(base + e.x) : 0.f;
+                }
+            }
+        };
+
+        float x[32];
+        enter_tile();
+        if (have) gather(x);
+        while (have) {
+            const uint32_t g = g0 + static_cast<uint32_t>(kb);
+            const int my_stage = static_cast<int>(g & (STAGES - 1));
+            const uint32_t my_phase = (g / STAGES) & 1u;
+            const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
+            if (q == 0) IG_TRACE(0, g);
+            ptx::mbar_wait(&empty_bar[my_stage], my_phase ^ 1);
+            if (q == 0) IG_TRACE(1, g);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int part = 0; part < 4; ++part) {  // 8 k-values at a time keeps the live set inside 96 registers
+                uint32_t hi[8];
+                if (PLANES == 2) {
+                    uint32_t lo[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        // hi = x with the 13 sub-TF32 mantissa bits cleared (what the tensor core would read
+                        // anyway), lo = x - hi exactly: 2 instructions per element instead of 5 for round-to-nearest;
+                        // the residual after the hardware truncates lo is <= 2^-21 |x| either way
+                        hi[r] = __float_as_uint(x[part * 8 + r]) & 0xFFFFE000u;
+                        lo[r] = __float_as_uint(x[part * 8 + r] - __uint_as_float(hi[r]));
+                    }
+                    tmem_st_32x8(ta + part * 8, hi);
+                    tmem_st_32x8(ta + 32 + part * 8, lo);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) hi[r] = __float_as_uint(x[part * 8 + r]);
+                    tmem_st_32x8(ta + part * 8, hi);
+                }
+            }
+            if (q == 0) IG_TRACE(2, g);
+            advance();
+            if (have) gather(x);  // in flight across the store drain, the arrive and the next slot wait
+            if (q == 0) IG_TRACE(3, g);
+            tmem_st_wait();
+            if (q == 0) IG_TRACE(4, g);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&full_bar[my_stage]);
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue (warps 4..7) =====================
+    } else {
+        // ===================== epilogue (warps 0..3) =====================
         const int q = warp & 3;
         long long it = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -343,6 +444,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const int as = static_cast<int>(it & 1);
             const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
             ptx::mbar_wait_relaxed(&tmem_full_bar[as], aphase);
+            if (q == 0) IG_TRACE(9, static_cast<uint32_t>(it));
             ptx::tc_fence_after();
             const BoxCoord bx = decode_box(ptile * 4 + q, args);  // this warp's 32 TMEM lanes are box q
             const int ox = bx.ox0 + lane;
@@ -372,13 +474,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             }
             ptx::tc_fence_before();
             __syncwarp();
+            if (q == 0) IG_TRACE(10, static_cast<uint32_t>(it));
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
         }
     }
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kWarpMma) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
     }
@@ -448,8 +551,11 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
     constexpr int kStage = PLANES * BN * 32 * 4;
     const int table_bytes = a.use_table ? a.kblocks * 32 * 8 : 0;
-    const int smem = kStagesIg * kStage + table_bytes + 1024;
-    if (smem > 227 * 1024) return -1;
+    int bstages = (227 * 1024 - 2048 - table_bytes) / kStage;
+    if (bstages > kMaxBStages) bstages = kMaxBStages;
+    if (bstages < 2) return -1;
+    a.bstages = bstages;
+    const int smem = bstages * kStage + table_bytes + 1024;
     auto kern = conv_igemm_kernel<BN, PLANES>;
     static int attr_smem = 0;
     if (smem > attr_smem) {

@@ -47,14 +47,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must fail the launch (trap) instead of hanging the GPU.
+// Non-blocking probe (no suspend): lets an issuing warp look at the NEXT stage's barrier between two MMAs, so the
+// probe's latency hides under the tensor pipe instead of sitting between two k-blocks.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must fail the launch (trap) instead of hanging the GPU.  The clock is only read every
+// 64th failed poll: the polls themselves park in the hardware (suspend hint), and in the producer-bound kernels the
+// wait loops of the idle roles were 10% of all issued instructions when they read the clock every time.
+static __device__ __noinline__ void mbar_timeout_trap() {
+    printf("fcuda: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-            printf("fcuda tensor_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
+    long long t0 = 0;
+    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
+        if ((spins & 63u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) mbar_timeout_trap();  // ~2 s at 2 GHz
         }
     }
 }
@@ -63,12 +85,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // spinning warp does not compete for issue slots with the producer warps.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(128);
-        if (clock64() - t0 > 4000000000LL) {
-            printf("fcuda: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
+    long long t0 = 0;
+    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
+        __nanosleep(256);
+        if ((spins & 63u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) mbar_timeout_trap();
         }
     }
 }

@@ -387,6 +387,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
+        bool ready = false;  // a_ready_bar[stage] already observed complete for `phase`
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int ks = tile / (tiles_per_g * args.G);
             const int kb0 = ks * kb_per_split;
@@ -397,23 +398,29 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * BN;
             for (int kb = kb0; kb < kb1; ++kb) {
-                ptx::mbar_wait(&a_ready_bar[stage], phase);  // implies full_bar: the splitters waited on it
+                // a_ready implies full_bar (the splitters waited on it).  The tensor pipe's queue is shallow, so the
+                // NEXT slot's barrier is probed between this slot's MMAs; the blocking wait is the fallback.
+                if (!ready) ptx::mbar_wait(&a_ready_bar[stage], phase);
                 ptx::tc_fence_after();
-                if (leader) {
-                    const uint64_t dB = dB0 + static_cast<uint64_t>(stage * (kStage >> 4));
-                    const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
-                    const uint32_t ta = tmem_a0 + stage * kAStageCols;
+                const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
+                const uint32_t nphase = nstage == 0 ? phase ^ 1u : phase;
+                const uint64_t dB = dB0 + static_cast<uint64_t>(stage * (kStage >> 4));
+                const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
+                const uint32_t ta = tmem_a0 + stage * kAStageCols;
 #pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k) {
-                        const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
+                for (int k = 0; k < kBK / 8; ++k) {
+                    const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
+                    if (leader) {
                         umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);   // A_lo * B_hi
                         umma_tf32_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_hi * B_lo
                         umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);           // A_hi * B_hi
                     }
-                    ptx::umma_commit(&empty_bar[stage]);
+                    if (k == 1) ready = ptx::mbar_test(&a_ready_bar[nstage], nphase);
                 }
+                if (leader) ptx::umma_commit(&empty_bar[stage]);
                 __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                stage = nstage;
+                phase = nphase;
             }
             if (leader) ptx::umma_commit(&tmem_full_bar[as]);
             __syncwarp();
