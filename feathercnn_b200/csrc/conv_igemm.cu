@@ -38,21 +38,26 @@ __device__ long long g_igemm_trace[16 * 64];
     do {                                                                                                 \
         if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (idx) < 64u) g_igemm_trace[(slot) * 64 + (idx)] = clock64(); \
     } while (0)
+#define IG_TRACE_T(slot, idx)  /* already single-threaded */                                           \
+    do {                                                                                                 \
+        if (blockIdx.x == 0 && (idx) < 64u) g_igemm_trace[(slot) * 64 + (idx)] = clock64();               \
+    } while (0)
 int igemm_trace_read(long long* host) {
     return cudaMemcpyFromSymbol(host, g_igemm_trace, sizeof(long long) * 16 * 64) == cudaSuccess ? 0 : -1;
 }
 #else
 #define IG_TRACE(slot, idx) do {} while (0)
+#define IG_TRACE_T(slot, idx) do {} while (0)
 #endif
 
 namespace {
 
 constexpr int kGroups = 3;                                // producer groups, 4 warps (128 pixels) each
 constexpr int kWarpTma = 4 + 4 * kGroups;                  // warps 0-3 epilogue, 4.. producers (quadrant = warp % 4),
-constexpr int kWarpMma = kWarpTma + 1;                    // then one TMA(B) warp and one MMA warp: no idle warps, so
-constexpr int kThreadsIg = (kWarpMma + 1) * 32;           // 576 threads leave 112 registers for the producers
+constexpr int kWarpMma = kWarpTma + 1;                    // then one TMA(B) warp and TWO MMA-issuer warps (see the kernel)
+constexpr int kIssuers = 2;
+constexpr int kThreadsIg = (kWarpMma + kIssuers) * 32;
 constexpr int kStagesIg = 4;                              // ring depth shared by the smem B tiles and the TMEM A tiles
-constexpr int kMaxBStages = 8;                            // filter-tile ring: deeper than the A ring, as smem allows
 constexpr int kMaxTableK = 8192;                          // k-table entries that fit beside the B ring
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -81,24 +86,31 @@ struct IgemmArgs {
     int kblocks;             // ceil(K / 32)
     int use_table;           // 0 => IC % 32 == 0: every k-block is 32 channels of ONE tap, offsets are arithmetic
     int bpr;                 // 32-pixel boxes per output row
-    long long total_boxes;   // N * OH * bpr
+    int per_img;             // OH * bpr boxes per image
+    unsigned long long m_per_img, m_bpr, m_num_n;  // ceil(2^64 / d): n / d == umul64hi(n, m) for any 32-bit n (d > 1)
+    int oc_pad;              // num_n * BN: floats of the bias copy in shared memory
+    long long total_boxes;   // N * OH * bpr  (< 2^31, checked on the host)
     int num_n;               // ceil(OC / BN)
     long long pixel_tiles;   // ceil(total_boxes / 4)
     int relu;
-    int bstages;             // depth of the filter-tile ring in shared memory (<= kMaxBStages)
 };
 
 struct BoxCoord { int n, oy, ox0; bool valid; };
 
-__device__ __forceinline__ BoxCoord decode_box(long long b, const IgemmArgs& a) {
+// n / d for 32-bit n with the host-made multiplier m = ceil(2^64 / d); exact because n * d < 2^64.
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, unsigned long long m, int d) {
+    return d == 1 ? n : static_cast<uint32_t>(__umul64hi(static_cast<unsigned long long>(n), m));
+}
+
+__device__ __forceinline__ BoxCoord decode_box(uint32_t b, const IgemmArgs& a) {
     BoxCoord c;
-    c.valid = b < a.total_boxes;
-    const long long per_img = static_cast<long long>(a.OH) * a.bpr;
-    const long long n = b / per_img;
-    const int rem = static_cast<int>(b - n * per_img);
+    c.valid = b < static_cast<uint32_t>(a.total_boxes);
+    const uint32_t n = fast_div(b, a.m_per_img, a.per_img);
+    const uint32_t rem = b - n * static_cast<uint32_t>(a.per_img);
+    const uint32_t oy = fast_div(rem, a.m_bpr, a.bpr);
     c.n = static_cast<int>(n);
-    c.oy = rem / a.bpr;
-    c.ox0 = (rem - c.oy * a.bpr) * 32;
+    c.oy = static_cast<int>(oy);
+    c.ox0 = static_cast<int>(rem - oy * static_cast<uint32_t>(a.bpr)) * 32;
     return c;
 }
 
@@ -115,14 +127,6 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -146,18 +150,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    int2* ktab = reinterpret_cast<int2*>(smem + args.bstages * kStage);  // {element offset, tap index} per k
+    int2* ktab = reinterpret_cast<int2*>(smem + STAGES * kStage);  // {element offset, tap index} per k
 
-    // A ring (tensor memory, STAGES slots): full = 4 arrivals of the owning producer group, empty = MMAs retired.
-    // B ring (shared memory, args.bstages slots, deeper: a filter tile is ~1.5k cycles away — relaxed wake-up of the
-    // TMA warp + L2 latency — while an A slot turns around in 3 k-blocks of MMA time).
+    // one barrier per ring slot covers both operands: 4 arrivals of the owning producer group (A in tensor memory)
+    // + 1 arrive.expect_tx of the TMA warp (B bytes landed) -> the MMA thread makes ONE wait per k-block
     __shared__ uint64_t full_bar[STAGES];
-    __shared__ uint64_t b_full_bar[kMaxBStages];
-    __shared__ uint64_t b_empty_bar[kMaxBStages];
     __shared__ uint64_t empty_bar[STAGES];    // MMAs that read the stage have retired
     __shared__ uint64_t tmem_full_bar[2];
     __shared__ uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ volatile uint32_t issued_g;  // k-blocks whose MMAs have been issued (hand-off between the two issuers)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -166,13 +168,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int plane = args.H * args.W;
 
     if (threadIdx.x == 0) {
+        issued_g = 0;
         for (int s = 0; s < STAGES; ++s) {
-            ptx::mbar_init(&full_bar[s], 4);
+            ptx::mbar_init(&full_bar[s], 5);
             ptx::mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < kMaxBStages; ++s) {
-            ptx::mbar_init(&b_full_bar[s], 1);
-            ptx::mbar_init(&b_empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full_bar[s], 1);
@@ -195,6 +194,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             ktab[k] = e;
         }
     }
+    // bias copy (zeros when the layer has none): the epilogue reads it with broadcast LDS.128
+    float* bias_s = reinterpret_cast<float*>(smem + STAGES * kStage + (args.use_table ? kblocks * 32 * 8 : 0));
+    for (int i = threadIdx.x; i < args.oc_pad; i += kThreadsIg)
+        bias_s[i] = (args.bias != nullptr && i < args.OC) ? __ldg(args.bias + i) : 0.f;
     if (warp == kWarpMma) {
         ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
         ptx::tmem_relinquish();
@@ -208,85 +211,77 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     if (warp == kWarpTma) {
         // ===================== TMA producer for the filter tiles =====================
         const bool leader = ptx::elect_one();
-        int bs = 0;
-        uint32_t bphase = 0;
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t gb = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_blk = static_cast<int>(tile % args.num_n);
-            for (int kb = 0; kb < kblocks; ++kb) {
-                ptx::mbar_wait(&b_empty_bar[bs], bphase ^ 1);
+            const uint32_t pt = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+            const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - pt * static_cast<uint32_t>(args.num_n));
+            for (int kb = 0; kb < kblocks; ++kb, ++gb) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                IG_TRACE(8, gb);
                 if (leader) {
-                    uint8_t* st = smem + bs * kStage;
-                    ptx::mbar_arrive_expect_tx(&b_full_bar[bs], PLANES * kBTile);
-                    ptx::tma_load_3d(st, &tmW, &b_full_bar[bs], kb * 32, n_blk * BN, 0);
-                    if (PLANES == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, &b_full_bar[bs], kb * 32, n_blk * BN, 0);
+                    uint8_t* st = smem + stage * kStage;
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], PLANES * kBTile);
+                    ptx::tma_load_3d(st, &tmW, &full_bar[stage], kb * 32, n_blk * BN, 0);
+                    if (PLANES == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, &full_bar[stage], kb * 32, n_blk * BN, 0);
                 }
                 __syncwarp();
-                if (++bs == args.bstages) { bs = 0; bphase ^= 1; }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == kWarpMma) {
-        // ===================== MMA issuer =====================
-        // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.  Descriptors are
-        // formed once: per k-block only the stage offset (in 16-byte units / TMEM columns) is added.
-        // The tensor pipe's queue is shallow (measured: issuing 12 MMAs takes as long as executing them, and anything
-        // the warp does after the last issue runs with ~1.5 MMAs of work left), so nothing slow may sit between two
-        // k-blocks: the barrier of the NEXT slot is probed half-way through the current slot's MMAs and the blocking
-        // wait is only the fallback.
-        constexpr uint32_t idesc = make_idesc_tf32(BN);
-        const bool leader = ptx::elect_one();
-        const uint64_t dB0 = make_smem_desc_sw128(ptx::smem_u32(smem));
-        int stage = 0, bs = 0;
-        uint32_t phase = 0, bphase = 0;
-        long long it = 0;
-        bool ready = false;  // full_bar[stage] and b_full_bar[bs] already observed complete
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int as = static_cast<int>(it & 1);
-            const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
-            ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-            const uint32_t tmem_d = tmem_base + as * BN;
-            for (int kb = 0; kb < kblocks; ++kb) {
-                if (!ready) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::mbar_wait(&b_full_bar[bs], bphase);
-                }
-                IG_TRACE(5, static_cast<uint32_t>(it * kblocks + kb));
-                ptx::tc_fence_after();
-                const int nstage = (stage + 1) & (STAGES - 1);
-                const uint32_t nphase = nstage == 0 ? phase ^ 1u : phase;
-                const int nbs = bs + 1 == args.bstages ? 0 : bs + 1;
-                const uint32_t nbphase = nbs == 0 ? bphase ^ 1u : bphase;
-                const uint64_t dB = dB0 + static_cast<uint64_t>(bs * (kStage >> 4));
+    } else if (warp >= kWarpMma) {
+        // ===================== MMA issuers: two elected threads alternate k-blocks =====================
+        // Measured on B200 (tests/cuda/mma_rate.cu, tests/cuda/igemm_trace.cu): a TS-form kind::tf32 MMA of N columns
+        // executes in N/2 cycles; the pipe holds ~6 MMAs and ISSUE BLOCKS beyond that; a pipe that has run dry needs
+        // ~390 cycles before the next MMA completes; and the scalar work of one k-block (barrier wait, fence,
+        // descriptor arithmetic, commit, loop) is ~300-400 cycles of dependent single-thread issue.  One issuer therefore
+        // leaves the pipe idle about half of the time at N=64.  With two issuers, one thread's scalar work overlaps
+        // the other's (blocking) MMA issue; the hand-off is a shared-memory counter, ~50 cycles against the ~190
+        // cycles of work still queued when an issuer finishes.  k-block g (running over this CTA's tiles) belongs to
+        // issuer g & 1; MMAs into one accumulator execute in issue order, so the overwrite of the tile's first MMA and
+        // the commit of its last MMA cover both threads' work.
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = make_idesc_tf32(BN);
+            const uint64_t dB0 = make_smem_desc_sw128(ptx::smem_u32(smem));
+            uint32_t g = static_cast<uint32_t>(warp - kWarpMma);
+            long long tile = blockIdx.x;
+            int kb = static_cast<int>(g);
+            uint32_t it = 0;
+            for (;;) {
+                while (kb >= kblocks && tile < total_tiles) { kb -= kblocks; tile += gridDim.x; ++it; }
+                if (tile >= total_tiles) break;
+                const int stage = static_cast<int>(g & (STAGES - 1));
+                const uint32_t phase = (g / STAGES) & 1u;
+                const uint32_t as = it & 1u;
+                const uint32_t tmem_d = tmem_base + as * BN;
+                const uint64_t dB = dB0 + static_cast<uint64_t>(stage * (kStage >> 4));
                 const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
                 const uint32_t ta = tmem_a0 + stage * kAStageCols;
+                if (kb == 0) ptx::mbar_wait(&tmem_empty_bar[as], ((it >> 1) & 1u) ^ 1u);
+                ptx::mbar_wait(&full_bar[stage], phase);
+                IG_TRACE_T(5, g);
+                while (issued_g < g) {}  // the other issuer has put k-block g-1 into the pipe
+                IG_TRACE_T(6, g);
+                ptx::tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {  // 8 k-values (TMEM columns / 32 smem bytes) per MMA
                     const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
-                    if (leader) {
-                        if (PLANES == 2) {
-                            umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);   // A_lo * B_hi
-                            umma_tf32_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_hi * B_lo
-                            umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);           // A_hi * B_hi
-                        } else {
-                            umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, first);
-                        }
-                    }
-                    if (k == 1) {  // results needed after the last MMA
-                        const bool a_ok = ptx::mbar_test(&full_bar[nstage], nphase);
-                        const bool b_ok = ptx::mbar_test(&b_full_bar[nbs], nbphase);
-                        ready = a_ok && b_ok;
+                    if (PLANES == 2) {
+                        umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);   // A_lo * B_hi
+                        umma_tf32_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_hi * B_lo
+                        umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);           // A_hi * B_hi
+                    } else {
+                        umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, first);
                     }
                 }
-                if (leader) {
-                    ptx::umma_commit(&empty_bar[stage]);
-                    ptx::umma_commit(&b_empty_bar[bs]);
-                }
-                __syncwarp();
-                IG_TRACE(7, static_cast<uint32_t>(it * kblocks + kb));
-                stage = nstage; phase = nphase;
-                bs = nbs; bphase = nbphase;
+                issued_g = g + 1;
+                ptx::umma_commit(&empty_bar[stage]);
+                if (kb == kblocks - 1) ptx::umma_commit(&tmem_full_bar[as]);
+                IG_TRACE_T(7, g);
+                g += kIssuers;
+                kb += kIssuers;
             }
-            if (leader) ptx::umma_commit(&tmem_full_bar[as]);
-            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===================== A producers: gather + 3xTF32 split -> tensor memory =====================
@@ -325,19 +320,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 if (g0_mod >= kGroups) g0_mod -= kGroups;
             }
             if (!have) return;
-            const long long ptile = tile / args.num_n;
+            const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
             const BoxCoord bx = decode_box(ptile * 4 + q, args);
             const int ox = bx.ox0 + lane;
             const bool pix_ok = bx.valid && ox < args.OW;
             const int iy0 = bx.oy * args.stride_h - args.pad_top;
             const int ix0 = ox * args.stride_w - args.pad_left;
             tapmask = 0;
-            if (pix_ok) {
-                for (int u = 0; u < args.KH; ++u) {
-                    if (iy0 + u < 0 || iy0 + u >= args.H) continue;
-                    for (int v = 0; v < args.KW; ++v)
-                        if (ix0 + v >= 0 && ix0 + v < args.W) tapmask |= 1ull << (u * args.KW + v);
-                }
+            if (pix_ok) {  // row mask x column mask instead of KH*KW tests
+                unsigned long long cols = 0;
+                for (int v = 0; v < args.KW; ++v)
+                    if (static_cast<unsigned>(ix0 + v) < static_cast<unsigned>(args.W)) cols |= 1ull << v;
+                for (int u = 0; u < args.KH; ++u)
+                    if (static_cast<unsigned>(iy0 + u) < static_cast<unsigned>(args.H)) tapmask |= cols << (u * args.KW);
             }
             base = args.in + (static_cast<long long>(bx.valid ? bx.n : 0) * args.IC) * plane +
                    static_cast<long long>(iy0) * args.W + ix0;
@@ -437,44 +432,58 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     } else {
         // ===================== epilogue (warps 0..3) =====================
         const int q = warp & 3;
-        long long it = 0;
+        const float floor_v = args.relu ? 0.f : -INFINITY;
+        const uint32_t oplane_bytes = static_cast<uint32_t>(args.OH * args.OW) * 4u;  // host: OH*OW < 2^30
+        uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const long long ptile = tile / args.num_n;
-            const int n_blk = static_cast<int>(tile - ptile * args.num_n);
-            const int as = static_cast<int>(it & 1);
-            const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
-            ptx::mbar_wait_relaxed(&tmem_full_bar[as], aphase);
-            if (q == 0) IG_TRACE(9, static_cast<uint32_t>(it));
-            ptx::tc_fence_after();
+            const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+            const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - ptile * static_cast<uint32_t>(args.num_n));
+            const uint32_t as = it & 1u;
+            const uint32_t aphase = (it >> 1) & 1u;
             const BoxCoord bx = decode_box(ptile * 4 + q, args);  // this warp's 32 TMEM lanes are box q
             const int ox = bx.ox0 + lane;
             const bool ok = bx.valid && ox < args.OW;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
             const size_t oplane = static_cast<size_t>(args.OH) * args.OW;
-            float* dst0 = args.out + (static_cast<size_t>(ok ? bx.n : 0) * args.OC) * oplane +
-                          static_cast<size_t>(bx.oy) * args.OW + ox;
+            ptx::mbar_wait_relaxed(&tmem_full_bar[as], aphase);
+            if (q == 0) IG_TRACE(9, it);
+            ptx::tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const int oc0 = n_blk * BN + c0;
                 if (oc0 >= args.OC) break;
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(taddr0 + c0, r);
+                char* dst = reinterpret_cast<char*>(args.out + (static_cast<size_t>(ok ? bx.n : 0) * args.OC + oc0) * oplane +
+                                                    static_cast<size_t>(bx.oy) * args.OW + ox);
+                asm volatile("" : "+l"(dst));  // one IMAD.WIDE per store off an opaque base
+                const float4* b4 = reinterpret_cast<const float4*>(bias_s + oc0);
                 ptx::tmem_ld_wait();
                 if (ok) {
+                    if (oc0 + 32 <= args.OC) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (oc0 + j < args.OC) {
-                            float v = __uint_as_float(r[j]);
-                            if (args.bias) v += __ldg(args.bias + oc0 + j);
-                            if (args.relu) v = fmaxf(v, 0.f);
-                            dst0[static_cast<size_t>(oc0 + j) * oplane] = v;
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 bv = b4[j4];
+                            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int j = j4 * 4 + e;
+                                *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(j)) =
+                                    fmaxf(__uint_as_float(r[j]) + bb[e], floor_v);
+                            }
                         }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (oc0 + j < args.OC)
+                                *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(j)) =
+                                    fmaxf(__uint_as_float(r[j]) + bias_s[oc0 + j], floor_v);
                     }
                 }
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (q == 0) IG_TRACE(10, static_cast<uint32_t>(it));
+            if (q == 0) IG_TRACE(10, it);
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
         }
     }
@@ -543,19 +552,26 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     a.kblocks = ceil_div(K, 32);
     a.use_table = (p.IC % 32 == 0) ? 0 : 1;
     a.bpr = ceil_div(p.OW, 32);
+    a.per_img = p.OH * a.bpr;
     a.total_boxes = static_cast<long long>(p.N) * p.OH * a.bpr;
+    auto magic = [](int d) { return d > 1 ? ~0ull / static_cast<unsigned long long>(d) + 1ull : 0ull; };
+    a.m_per_img = magic(a.per_img);
+    a.m_bpr = magic(a.bpr);
     a.num_n = ceil_div(p.OC, BN);
+    a.m_num_n = magic(a.num_n);
+    a.oc_pad = a.num_n * BN;
     a.pixel_tiles = (a.total_boxes + 3) / 4;
+    // 32-bit box / tile arithmetic and 32-bit plane strides inside the kernel
+    if (a.total_boxes + 4 >= (1ll << 31) || a.pixel_tiles * a.num_n >= (1ll << 31) ||
+        static_cast<long long>(p.H) * p.W >= (1ll << 30) || static_cast<long long>(p.OH) * p.OW >= (1ll << 30))
+        return -1;
     a.relu = p.relu;
     const long long total = a.pixel_tiles * a.num_n;
     const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
     constexpr int kStage = PLANES * BN * 32 * 4;
     const int table_bytes = a.use_table ? a.kblocks * 32 * 8 : 0;
-    int bstages = (227 * 1024 - 2048 - table_bytes) / kStage;
-    if (bstages > kMaxBStages) bstages = kMaxBStages;
-    if (bstages < 2) return -1;
-    a.bstages = bstages;
-    const int smem = bstages * kStage + table_bytes + 1024;
+    const int smem = kStagesIg * kStage + table_bytes + a.oc_pad * 4 + 1024;
+    if (smem > 227 * 1024 - 2048) return -1;
     auto kern = conv_igemm_kernel<BN, PLANES>;
     static int attr_smem = 0;
     if (smem > attr_smem) {

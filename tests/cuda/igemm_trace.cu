@@ -40,12 +40,12 @@ int main(int argc, char** argv) {
     std::vector<long long> t(16 * 64);
     if (igemm_trace_read(t.data())) return 1;
     long long t0 = t[0];
-    for (int i = 0; i < 16 * 64; ++i) if (t[i] && t[i] < t0) t0 = t[i];
-    printf("  g grp | P:wait_start  empty_ok  st_issued  gather_issued  st_done | M:a_ready  b_full  issued | dA=a_ready(g)-a_ready(g-1)\n");
+    for (int i = 0; i < 12 * 64; ++i) if (t[i] && t[i] < t0) t0 = t[i];
+    printf("  g grp | P:wait_start  empty_ok  st_issued  gather_issued  st_done | M:full_ok  probe(next ready?)  issued | T:B issued | period\n");
     for (int g = 0; g < 64; ++g) {
         auto r = [&](int slot) { return t[slot * 64 + g] ? (long long)(t[slot * 64 + g] - t0) : -1LL; };
-        printf("%3d  %d  | %10lld %9lld %10lld %14lld %8lld | %9lld %7lld %7lld | %lld\n", g, g % 3, r(0), r(1), r(2), r(3), r(4),
-               r(5), r(6), r(7), g ? r(5) - (t[5 * 64 + g - 1] - t0) : 0LL);
+        printf("%3d  %d  | %10lld %9lld %10lld %14lld %8lld | %9lld %7lld(%lld) %7lld | %8lld | %lld\n", g, g % 3, r(0), r(1), r(2),
+               r(3), r(4), r(5), r(6), t[12 * 64 + g], r(7), r(8), g ? r(5) - (t[5 * 64 + g - 1] - t0) : 0LL);
     }
     printf("tile | E:tmem_full  done\n");
     for (int i = 0; i < 8; ++i) printf("%3d  | %10lld %8lld\n", i, t[9 * 64 + i] - t0, t[10 * 64 + i] - t0);
