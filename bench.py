@@ -11,8 +11,10 @@ Prints ONE JSON line on rank 0:
   value         whole-job images/s with the input batches already resident in HBM (CUDA events, max over ranks)
   e2e           same metric through the public API with pinned HOST buffers: H2D of the batch and D2H of the
                 softmax output inside the timed region, every step
-  roofline      TensorGEMM (tcgen05) launches of one Forward, timed per launch with CUDA events on the Net's stream:
-                achieved = algorithmic direct-conv FLOPs / summed duration, against MEASURED_PEAKS.json
+  roofline      every instrumented launch of one eager Forward, timed with CUDA events on the Net's stream and grouped by
+                kernel class; the object describes the class with the largest share of the step (achieved =
+                algorithmic direct-conv FLOPs, or algorithmic bytes for HBM-bound classes, / summed duration, against
+                MEASURED_PEAKS.json) and lists the others under other_kernels
   cpu_baseline  the unmodified reference (oracle/_ref) on the host cores, bounded sample, rank 0 / N=1 only
 `--impl reference` times only that CPU reference arm (no GPU work) and prints the same line shape.
 """
@@ -297,28 +299,52 @@ def main() -> None:
                 net.FeedInputDevice(d.data_ptr(), tuple(d.shape))
                 net.Forward()
             net.Synchronize()
-            ms_t, af, mf, nl = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
-            lib.fcuda_profile_collect(ctypes.byref(ms_t), ctypes.byref(af), ctypes.byref(mf), ctypes.byref(nl))
-            lib.fcuda_profile_tensor_gemm(0)
             peaks, how = measured_peaks()
-            peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-            if ms_t.value > 0 and nl.value > 0:
-                ach = af.value / (ms_t.value * 1e-3) / 1e12
-                pipe = mf.value / (ms_t.value * 1e-3) / 1e12
-                traffic = None
-                tr = ROOT / "profiles" / "r01_tensor_gemm_traffic.json"
+            # kernels timed inside a long step -> the sustained figures; fallbacks = /opt/skills/guides/B200_PROFILING.md
+            tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+            hbm_peak = float(peaks.get("hbm_gbs", 6500.0))
+            names = ["tensor_gemm_ts_kernel (tcgen05 kind::tf32, Winograd/im2col/FC GEMM)",
+                     "conv_igemm_kernel (tcgen05 kind::tf32 implicit-GEMM conv)", "wino_input_kernel",
+                     "wino_output_kernel", "pooling_kernel", "depthwise kernels", "element-wise kernels"]
+            classes = []
+            for kind, name in enumerate(names):
+                ms_t, af, mf, ab, nl = (ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double(),
+                                        ctypes.c_longlong())
+                lib.fcuda_profile_collect_kind(kind, ctypes.byref(ms_t), ctypes.byref(af), ctypes.byref(mf),
+                                               ctypes.byref(ab), ctypes.byref(nl))
+                if nl.value == 0 or ms_t.value <= 0:
+                    continue
+                sec = ms_t.value * 1e-3
+                tensor = kind <= 1
+                ach = af.value / sec / 1e12 if tensor else ab.value / sec / 1e9
+                peak = tf_peak if tensor else hbm_peak
+                c = {"kernel": name, "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
+                     "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak,
+                     "launches_per_step": nl.value / reps, "avg_launch_us": 1e3 * ms_t.value / nl.value,
+                     "share_of_step": (ms_t.value / reps) / (ms_dev / args.steps)}
+                if tensor:
+                    c["algorithmic_gflop_per_launch"] = af.value / nl.value / 1e9
+                    c["algorithmic_gb_per_launch"] = ab.value / nl.value / 1e9
+                    c["hbm_gbps_at_algorithmic_bytes"] = ab.value / sec / 1e9
+                    c["tensor_pipe_tflops_issued"] = mf.value / sec / 1e12  # 3 MMAs per product in 3xTF32 mode
+                    c["tensor_pipe_frac_of_tf32_peak"] = c["tensor_pipe_tflops_issued"] / (tf_peak / 2.0)
+                else:
+                    c["algorithmic_gb_per_launch"] = ab.value / nl.value / 1e9
+                classes.append(c)
+            lib.fcuda_profile_tensor_gemm(0)
+            if classes:
+                classes.sort(key=lambda c: -c["share_of_step"])
+                roof = dict(classes[0])
+                roof["peak_source"] = (f"{how}: " + ("bf16_tflops_sustained" if roof["bound"] == "tensor" else
+                                                    "hbm_gbs") + " (kernel timed inside a long step)")
+                tr = ROOT / "profiles" / "r01_kernel_traffic.json"
+                roof["traffic"] = None
                 if tr.exists():
                     try:
-                        traffic = json.loads(tr.read_text()).get(args.model)
+                        roof["traffic"] = json.loads(tr.read_text()).get(args.model, {}).get(roof["kernel"].split()[0])
                     except Exception:
-                        traffic = None
-                roof = {"bound": "tensor", "kernel": "tensor_gemm_kernel (tcgen05 kind::tf32)", "achieved": ach,
-                        "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                        "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
-                        "launches_per_step": nl.value / reps, "avg_launch_us": 1e3 * ms_t.value / nl.value,
-                        "algorithmic_gflop_per_launch": af.value / nl.value / 1e9,
-                        "tensor_pipe_tflops": pipe, "tensor_pipe_frac_of_tf32_peak": pipe / (peak / 2.0),
-                        "gemm_share_of_step": (ms_t.value / reps) / (ms_dev / args.steps)}
+                        pass
+                roof["other_kernels"] = classes[1:]
 
     total_images = world * B * args.steps
     value = total_images / (ms_dev * 1e-3)
@@ -345,7 +371,8 @@ def main() -> None:
         "config": {"workload": f"{args.model}_b{B}_{in_shape[1]}x{in_shape[2]}", "batch_per_gpu": B,
                    "global_batch": B * world, "parallelism": f"batch-shard x{world} (weights broadcast once over NCCL)",
                    "tensor_core_mode": "3xTF32 split (fp32-equivalent)" if args.precision == "tf32x3" else "TF32",
-                   "algorithms": "reference SelectAlgo: Winograd F(6,3)+TensorGEMM / im2col+TensorGEMM / depthwise",
+                   "algorithms": "tuned SelectAlgo (reference rule, then Winograd -> implicit GEMM when IC,OC <= 128 and OW >= 28, "
+                                 "im2col -> implicit GEMM): Winograd F(6,3)+TensorGEMM / SGECONV implicit GEMM / depthwise",
                    "fusion": not args.no_fusion, "cuda_graph": not args.no_graph,
                    "l2_policy": f"{n_rot} rotating input batches ({n_rot * batch_bytes / 2**20:.0f} MiB > L2); "
                                 f"activations per step far exceed the 126 MB L2",

@@ -79,6 +79,7 @@ def fcuda() -> ctypes.CDLL:
             "fcuda_copy_channels": (i, [vp, i, i, vp, i, sz, i, vp]),
             "fcuda_profile_tensor_gemm": (None, [i]),
             "fcuda_profile_collect": (i, [ctypes.POINTER(ctypes.c_double)] * 3 + [ctypes.POINTER(ctypes.c_longlong)]),
+            "fcuda_profile_collect_kind": (i, [i] + [ctypes.POINTER(ctypes.c_double)] * 4 + [ctypes.POINTER(ctypes.c_longlong)]),
             "fcuda_launch_count": (ctypes.c_ulonglong, []),
             "fcuda_reset_launch_count": (None, []),
         }

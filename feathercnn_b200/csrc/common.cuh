@@ -45,4 +45,12 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     lo = v - hi;
 }
 
+// Per-launch profiling (tensor_gemm.cu): kernel classes for bench.py's roofline legs.
+enum ProfKind { PROF_TENSOR_GEMM = 0, PROF_IGEMM = 1, PROF_WINO_INPUT = 2, PROF_WINO_OUTPUT = 3, PROF_POOL = 4,
+                PROF_DEPTHWISE = 5, PROF_ELEMENTWISE = 6, PROF_KINDS = 7 };
+int prof_begin(cudaStream_t s, int kind, double algo_flops, double mma_flops, double algo_bytes);  // -1 when off
+void prof_end(int idx, cudaStream_t s);
+void profile_collect_kind(int kind, double* total_ms, double* algo_flops, double* mma_flops, double* algo_bytes,
+                          long long* launches);
+
 }  // namespace fcuda

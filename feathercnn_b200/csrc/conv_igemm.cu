@@ -578,7 +578,14 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
         FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
+    // algorithmic work of the layer: direct-convolution FLOPs; input + filters read once, output written once
+    const double macs = static_cast<double>(p.N) * p.OC * p.OH * p.OW * p.IC * taps;
+    const double mma = 2.0 * static_cast<double>(a.pixel_tiles) * 128 * (a.num_n * BN) * (a.kblocks * 32) * (PLANES == 2 ? 3 : 1);
+    const int prof = prof_begin(stream, PROF_IGEMM, 2.0 * macs, mma,
+                                4.0 * (static_cast<double>(p.N) * p.IC * p.H * p.W + static_cast<double>(p.OC) * K +
+                                       static_cast<double>(p.N) * p.OC * p.OH * p.OW));
     kern<<<grid, kThreadsIg, smem, stream>>>(tmW, tmWlo, a);
+    prof_end(prof, stream);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;

@@ -124,6 +124,9 @@ int depthwise_forward(const float* in, const float* w, const float* bias, float*
                       int batch, cudaStream_t s) {
     const bool k3 = g.KH == 3 && g.KW == 3 && g.pad_top == 1 && g.pad_left == 1 && g.stride_h == g.stride_w &&
                     (g.stride_h == 1 || g.stride_h == 2) && g.OW >= 24;
+    const double planes = static_cast<double>(batch) * g.C;
+    const int prof = prof_begin(s, PROF_DEPTHWISE, 2.0 * planes * g.OH * g.OW * g.KH * g.KW, 0,
+                                4.0 * planes * (static_cast<double>(g.H) * g.W + static_cast<double>(g.OH) * g.OW));
     if (k3) {
         const int xstrips = ceil_div(g.OW, 32), ystrips = ceil_div(g.OH, kDwRows);
         const long long items = static_cast<long long>(batch) * g.C * xstrips * ystrips;
@@ -138,6 +141,7 @@ int depthwise_forward(const float* in, const float* w, const float* bias, float*
         const long long total = static_cast<long long>(batch) * g.C * g.OH * g.OW;
         dw_generic_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, w, bias, out, g, relu, total);
     }
+    prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;

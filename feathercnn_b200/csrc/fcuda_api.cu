@@ -519,6 +519,11 @@ int fcuda_copy_channels(float* dst, int dst_channels, int dst_channel_offset, co
 }
 
 void fcuda_profile_tensor_gemm(int enable) { gemm_profile_enable(enable != 0); }
+int fcuda_profile_collect_kind(int kind, double* total_ms, double* algo_flops, double* mma_flops, double* algo_bytes,
+                               long long* launches) {
+    profile_collect_kind(kind, total_ms, algo_flops, mma_flops, algo_bytes, launches);
+    return 0;
+}
 int fcuda_profile_collect(double* total_ms, double* algo_flops, double* mma_flops, long long* launches) {
     gemm_profile_collect(total_ms, algo_flops, mma_flops, launches);
     return 0;

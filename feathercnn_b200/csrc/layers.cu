@@ -195,6 +195,7 @@ fill_rows_kernel(float* __restrict__ out, const float* __restrict__ row, int row
 // ------------------------------------------------------------------------------------------------
 int pooling_forward(const float* in, float* out, const PoolGeom& g, int channels, int batch, cudaStream_t s) {
     const size_t planes = static_cast<size_t>(batch) * channels;
+    const int prof = prof_begin(s, PROF_POOL, 0, 0, 4.0 * planes * (static_cast<double>(g.H) * g.W + static_cast<double>(g.OH) * g.OW));
     if (g.OH == 1 && g.OW == 1 && g.KH >= g.H && g.KW >= g.W && g.pad_top + g.pad_bottom == 0 &&
         g.pad_left + g.pad_right == 0) {
         global_pool_kernel<<<static_cast<unsigned>(ceil_div_sz(planes * 32, 256)), 256, 0, s>>>(in, out, g.H * g.W,
@@ -203,6 +204,7 @@ int pooling_forward(const float* in, float* out, const PoolGeom& g, int channels
         const size_t total = planes * g.OH * g.OW;
         pooling_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, g, total);
     }
+    prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;
@@ -211,14 +213,18 @@ int pooling_forward(const float* in, float* out, const PoolGeom& g, int channels
 int channel_affine(const float* in, float* out, int channels, size_t hw, const float* mul, const float* add,
                    const float* mul2, const float* add2, int relu, int batch, cudaStream_t s) {
     const size_t total = static_cast<size_t>(batch) * channels * hw;
+    const int prof = prof_begin(s, PROF_ELEMENTWISE, 0, 0, 8.0 * total);
     channel_affine_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, channels, hw, mul, add, mul2, add2, relu, total);
+    prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;
 }
 
 int add_relu(const float* a, const float* b, float* out, size_t n, int relu, cudaStream_t s) {
+    const int prof = prof_begin(s, PROF_ELEMENTWISE, 0, 0, 12.0 * n);
     add_relu_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(a, b, out, n, relu);
+    prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;

@@ -529,7 +529,10 @@ unsigned long long launch_count() { return g_launches.load(std::memory_order_rel
 void reset_launch_count() { g_launches.store(0, std::memory_order_relaxed); }
 
 // ---- per-launch profiling ------------------------------------------------------------------------
-struct ProfRec { cudaEvent_t e0, e1; double algo_flops, mma_flops; };
+// Off by default.  When enabled every instrumented launch is bracketed by two CUDA events on its own stream and tagged
+// with its kernel class and ALGORITHMIC work (the FLOPs / bytes the operation needs, not what the kernel happens to
+// move), which is what bench.py divides by the measured time for the roofline object.
+struct ProfRec { cudaEvent_t e0, e1; int kind; double algo_flops, mma_flops, algo_bytes; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 
@@ -541,18 +544,45 @@ void gemm_profile_enable(bool on) {
     g_prof_on = on;
 }
 
-void gemm_profile_collect(double* total_ms, double* algo_flops, double* mma_flops, long long* launches) {
-    double ms = 0, af = 0, mf = 0;
+int prof_begin(cudaStream_t s, int kind, double algo_flops, double mma_flops, double algo_bytes) {
+    if (!g_prof_on) return -1;
+    ProfRec rec{};
+    rec.kind = kind; rec.algo_flops = algo_flops; rec.mma_flops = mma_flops; rec.algo_bytes = algo_bytes;
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    cudaEventRecord(rec.e0, s);
+    g_prof.push_back(rec);
+    return static_cast<int>(g_prof.size()) - 1;
+}
+void prof_end(int idx, cudaStream_t s) {
+    if (idx >= 0 && idx < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[idx].e1, s);
+}
+
+// kind < 0: all classes
+void profile_collect_kind(int kind, double* total_ms, double* algo_flops, double* mma_flops, double* algo_bytes,
+                          long long* launches) {
+    double ms = 0, af = 0, mf = 0, ab = 0;
+    long long n = 0;
     for (auto& r : g_prof) {
+        if (kind >= 0 && r.kind != kind) continue;
         float t = 0.f;
         if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) ms += t;
-        af += r.algo_flops;
-        mf += r.mma_flops;
+        af += r.algo_flops; mf += r.mma_flops; ab += r.algo_bytes; ++n;
     }
     if (total_ms) *total_ms = ms;
     if (algo_flops) *algo_flops = af;
     if (mma_flops) *mma_flops = mf;
-    if (launches) *launches = static_cast<long long>(g_prof.size());
+    if (algo_bytes) *algo_bytes = ab;
+    if (launches) *launches = n;
+}
+void gemm_profile_collect(double* total_ms, double* algo_flops, double* mma_flops, long long* launches) {
+    profile_collect_kind(PROF_TENSOR_GEMM, total_ms, algo_flops, mma_flops, nullptr, launches);
+}
+
+// A read once + B read once + D written once (fp32), the least a GEMM of these shapes must move
+static double gemm_algo_bytes(const GemmProblem& p) {
+    return 4.0 * p.G * (static_cast<double>(p.M) * p.K + static_cast<double>(p.N) * p.K * (p.planes == 2 ? 2 : 1) +
+                        static_cast<double>(p.M) * p.N);
 }
 
 int sm_count() {
@@ -640,22 +670,13 @@ static int launch(const GemmProblem& p, cudaStream_t stream) {
         FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    ProfRec rec{};
-    if (g_prof_on) {
-        cudaEventCreate(&rec.e0);
-        cudaEventCreate(&rec.e1);
-        const double dense = 2.0 * p.M * static_cast<double>(p.N) * p.K * p.G;
-        rec.algo_flops = p.algo_flops > 0 ? p.algo_flops : dense;
-        rec.mma_flops = dense * (PLANES == 2 ? 3.0 : 1.0);
-        cudaEventRecord(rec.e0, stream);
-    }
+    const double dense = 2.0 * p.M * static_cast<double>(p.N) * p.K * p.G;
+    const int prof = prof_begin(stream, PROF_TENSOR_GEMM, p.algo_flops > 0 ? p.algo_flops : dense,
+                                dense * (PLANES == 2 ? 3.0 : 1.0), gemm_algo_bytes(p));
     kern<<<grid, kThreads, smem, stream>>>(tmA, tmAlo, tmB, tmBlo, a);
     FCUDA_CHECK_LAUNCH();
     count_launch();
-    if (g_prof_on) {
-        cudaEventRecord(rec.e1, stream);
-        g_prof.push_back(rec);
-    }
+    prof_end(prof, stream);
     return 0;
 }
 
@@ -696,22 +717,13 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
         FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    ProfRec rec{};
-    if (g_prof_on) {
-        cudaEventCreate(&rec.e0);
-        cudaEventCreate(&rec.e1);
-        const double dense = 2.0 * p.M * static_cast<double>(p.N) * p.K * p.G;
-        rec.algo_flops = p.algo_flops > 0 ? p.algo_flops : dense;
-        rec.mma_flops = dense * 3.0;
-        cudaEventRecord(rec.e0, stream);
-    }
+    const double dense = 2.0 * p.M * static_cast<double>(p.N) * p.K * p.G;
+    const int prof = prof_begin(stream, PROF_TENSOR_GEMM, p.algo_flops > 0 ? p.algo_flops : dense, dense * 3.0,
+                                gemm_algo_bytes(p));
     kern<<<grid, kThreadsTs, smem, stream>>>(tmA, tmB, tmBlo, a);
     FCUDA_CHECK_LAUNCH();
     count_launch();
-    if (g_prof_on) {
-        cudaEventRecord(rec.e1, stream);
-        g_prof.push_back(rec);
-    }
+    prof_end(prof, stream);
     return 0;
 }
 

@@ -308,8 +308,13 @@ int wino_input_transform(int tile, const float* in, float* V, const WinoGeom& g,
     const int segs = ceil_div(g.tilesX, kSegTiles);
     const int Tc = (R1 - R0) * g.tilesX;
     dim3 grid(static_cast<unsigned>(segs) * (R1 - R0), ceil_div(g.C_in, kChBlock));
+    // algorithmic bytes: the rows of the input the chunk covers, read once, + V written once
+    const double imgs = static_cast<double>(R1 - R0) / g.tilesY;  // tile-rows of the chunk, in images
+    const int prof = prof_begin(s, PROF_WINO_INPUT, 0, 0,
+                                4.0 * (imgs * g.C_in * g.H * g.W + static_cast<double>(tile) * tile * Tc * g.C_in));
     if (tile == 8) wino_input_kernel<8><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
     else wino_input_kernel<4><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
+    prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;
@@ -320,8 +325,12 @@ int wino_output_transform(int tile, const float* M, float* out, const float* bia
     const int segs = ceil_div(g.tilesX, kSegTiles);
     const int Tc = (R1 - R0) * g.tilesX;
     dim3 grid(static_cast<unsigned>(segs) * (R1 - R0), ceil_div(g.C_out, kChBlock));
+    const double imgs = static_cast<double>(R1 - R0) / g.tilesY;  // tile-rows of the chunk, in images
+    const int prof = prof_begin(s, PROF_WINO_OUTPUT, 0, 0,
+                                4.0 * (imgs * g.C_out * g.OH * g.OW + static_cast<double>(tile) * tile * Tc * g.C_out));
     if (tile == 8) wino_output_kernel<8><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
     else wino_output_kernel<4><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+    prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;

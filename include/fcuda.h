@@ -146,6 +146,12 @@ int fcuda_copy_channels(float* dst, int dst_channels, int dst_channel_offset, co
  * InnerProduct), the tensor-pipe FLOPs actually issued (x3 in TF32X3 mode) and the launch count. */
 void fcuda_profile_tensor_gemm(int enable);
 int fcuda_profile_collect(double* total_ms, double* algo_flops, double* mma_flops, long long* launches);
+/* Same, per kernel class, for every instrumented launch (the enable switch above covers all of them):
+ * kind 0 TensorGEMM, 1 implicit-GEMM conv, 2 Winograd input transform, 3 Winograd output transform, 4 pooling,
+ * 5 depthwise, 6 element-wise (BN/Scale/Eltwise), < 0 all.  algo_bytes = the bytes the operation must move (inputs
+ * read once + outputs written once). */
+int fcuda_profile_collect_kind(int kind, double* total_ms, double* algo_flops, double* mma_flops, double* algo_bytes,
+                               long long* launches);
 
 /* Number of kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
 unsigned long long fcuda_launch_count(void);
