@@ -92,6 +92,48 @@ dw3x3_shuffle_kernel(const float* __restrict__ in, const float* __restrict__ w, 
     }
 }
 
+// 3x3 depthwise on small planes (MobileNet's 14x14 and 7x7 stages, where a 32-wide strip would idle most lanes): one warp
+// per (image, channel) plane.  The plane goes to shared memory with a zero halo of one pixel, then every lane computes
+// output pixels lane, lane+32, ...; row/column come from a 16-bit reciprocal multiply (exact for planes <= 34x34).
+template <int STRIDE>
+__global__ void __launch_bounds__(128)
+dw3x3_plane_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ out, int C, int H, int W, int OH, int OW, int pad_top, int pad_left, int relu,
+                   long long planes) {
+    extern __shared__ float dw_smem[];
+    const int PW = W + 2, PH = H + 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long plane = static_cast<long long>(blockIdx.x) * 4 + warp;
+    if (plane >= planes) return;
+    float* tile = dw_smem + warp * PH * PW;
+    const int c = static_cast<int>(plane % C);
+    const float* ip = in + plane * H * W;
+    const unsigned rcp_pw = (65536u + PW - 1) / PW, rcp_ow = (65536u + OW - 1) / OW;
+    for (unsigned i = lane; i < static_cast<unsigned>(PH * PW); i += 32) {
+        const unsigned y = (i * rcp_pw) >> 16, x = i - y * PW;
+        const int iy = static_cast<int>(y) - 1, ix = static_cast<int>(x) - 1;
+        tile[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(ip + iy * W + ix) : 0.f;
+    }
+    float k[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
+    const float bv = bias ? __ldg(bias + c) : 0.f;
+    __syncwarp();
+    float* op = out + plane * OH * OW;
+    for (unsigned o = lane; o < static_cast<unsigned>(OH * OW); o += 32) {
+        const unsigned oy = (o * rcp_ow) >> 16, ox = o - oy * OW;
+        // window start in image coordinates is (oy*S - pad_top, ox*S - pad_left); +1 for the halo
+        const float* t = tile + (oy * STRIDE + 1 - pad_top) * PW + (ox * STRIDE + 1 - pad_left);
+        float v = bv;
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) v = fmaf(k[u * 3 + x], t[u * PW + x], v);
+        if (relu) v = fmaxf(v, 0.f);
+        op[o] = v;
+    }
+}
+
 // Generic k x k / any stride / any padding depthwise: one thread per output element.
 __global__ void __launch_bounds__(256)
 dw_generic_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
@@ -137,6 +179,19 @@ int depthwise_forward(const float* in, const float* w, const float* bias, float*
         else
             dw3x3_shuffle_kernel<2><<<blocks, 128, 0, s>>>(in, w, bias, out, g.C, g.H, g.W, g.OH, g.OW, relu, items,
                                                             xstrips, ystrips);
+    } else if (g.KH == 3 && g.KW == 3 && (g.pad_top == 0 || g.pad_top == 1) && (g.pad_left == 0 || g.pad_left == 1) &&
+               g.stride_h == g.stride_w && (g.stride_h == 1 || g.stride_h == 2) && g.H <= 34 && g.W <= 34 &&
+               (g.OH - 1) * g.stride_h - g.pad_top + 2 <= g.H && (g.OW - 1) * g.stride_w - g.pad_left + 2 <= g.W) {
+        // (the last window may reach one pixel past the image: that is the zero halo)
+        const long long planes_ll = static_cast<long long>(batch) * g.C;
+        const unsigned blocks = static_cast<unsigned>((planes_ll + 3) / 4);
+        const int smem = 4 * (g.H + 2) * (g.W + 2) * static_cast<int>(sizeof(float));
+        if (g.stride_h == 1)
+            dw3x3_plane_kernel<1><<<blocks, 128, smem, s>>>(in, w, bias, out, g.C, g.H, g.W, g.OH, g.OW, g.pad_top,
+                                                             g.pad_left, relu, planes_ll);
+        else
+            dw3x3_plane_kernel<2><<<blocks, 128, smem, s>>>(in, w, bias, out, g.C, g.H, g.W, g.OH, g.OW, g.pad_top,
+                                                             g.pad_left, relu, planes_ll);
     } else {
         const long long total = static_cast<long long>(batch) * g.C * g.OH * g.OW;
         dw_generic_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, w, bias, out, g, relu, total);

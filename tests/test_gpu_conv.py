@@ -30,8 +30,11 @@ CASES = [
     ("dw_s1", 64, 64, 28, 28, 3, 1, 1, 64, False, False),
     ("dw_s2_relu", 32, 32, 56, 56, 3, 2, 1, 32, False, True),
     ("dw_s1_wide", 16, 16, 40, 70, 3, 1, 1, 16, False, False),           # > 2 x-strips in the shuffle kernel
-    ("dw_small_plane", 128, 128, 7, 7, 3, 1, 1, 128, False, False),      # generic kernel
+    ("dw_small_plane", 128, 128, 7, 7, 3, 1, 1, 128, False, False),      # one-warp-per-plane kernel
     ("dw_s2_odd", 24, 24, 15, 15, 3, 2, 1, 24, False, False),
+    ("dw_14_bias_relu", 40, 40, 14, 14, 3, 1, 1, 40, True, True),        # plane kernel (MobileNet 14x14 stage)
+    ("dw_14_s2", 40, 40, 14, 14, 3, 2, 1, 40, True, False),              # plane kernel, stride 2 -> 7x7
+    ("dw_9_nopad", 12, 12, 9, 11, 3, 1, 0, 12, False, True),             # plane kernel without padding
     ("dw_5x5", 8, 8, 12, 12, 5, 1, 2, 8, False, False),
     ("dw_global", 32, 32, 7, 7, 7, 1, 0, 32, False, False),              # kernel == input: globalDwConv
 ]

@@ -51,6 +51,10 @@ POOL_CASES = [
     (0, 7, 1, (0, 0, 0, 0), True, (5, 6, 9)),         # global max
     (0, 3, 2, (1, 1, 1, 1), False, (4, 16, 16)),      # padded: window start subtracts both pads (pooling_layer.h:56,67)
     (1, 3, 2, (1, 0, 1, 0), False, (3, 15, 15)),
+    (1, 2, 2, (0, 0, 0, 0), False, (8, 28, 28)),      # average through the 2x2 fast path
+    (0, 2, 2, (0, 0, 0, 0), False, (3, 10, 4)),       # fast path, one output pair per row
+    (0, 2, 2, (0, 0, 0, 0), False, (3, 10, 14)),      # W % 4 != 0 -> generic kernel
+    (0, 2, 2, (0, 0, 0, 0), False, (4, 9, 12)),       # odd H (ceil mode) -> generic kernel
 ]
 
 
