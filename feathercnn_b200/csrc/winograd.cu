@@ -172,19 +172,31 @@ wino_input_kernel(const float* __restrict__ in, float* __restrict__ V, WinoGeom 
     const int gy0 = ty * OT - g.pad_top, gx0 = tx0 * OT - g.pad_left;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // slab load: warp w takes the (channel,row) lines w, w+5, ...; lane = column.  All index math is per line and
-    // warp-uniform; the lane only adds its column.
+    // slab load: warp w takes channels w, w+5, ...; per channel the T rows are unrolled (T loads in flight per lane,
+    // one IMAD.WIDE + LDG + STS per line; the first version spent 31 instructions per line on index arithmetic and
+    // that loop was 64% of the kernel's instructions); lane = column.
     {
         const size_t plane = static_cast<size_t>(g.H) * g.W;
         const float* img = in + static_cast<size_t>(n) * g.C_in * plane;
         const int gx = gx0 + lane;
         const bool x_ok = lane < COLS && gx >= 0 && gx < g.W;
-        for (int line = w; line < kChBlock * T; line += kSegTiles) {
-            const int c = line / T, r = line - c * T;  // T is a power of two
-            const int ic = c0 + c, gy = gy0 + r;
-            float v = 0.f;
-            if (x_ok && ic < g.C_in && gy >= 0 && gy < g.H) v = __ldg(img + ic * plane + static_cast<size_t>(gy) * g.W + gx);
-            if (lane < COLS) slab[c * CH_STRIDE + r * COLS + lane] = v;
+        unsigned row_ok = 0;
+#pragma unroll
+        for (int r = 0; r < T; ++r)
+            if (static_cast<unsigned>(gy0 + r) < static_cast<unsigned>(g.H)) row_ok |= 1u << r;
+        for (int c = w; c < kChBlock; c += kSegTiles) {
+            const int ic = c0 + c;
+            const bool c_ok = x_ok && ic < g.C_in;
+            // may point outside the image when gy0 < 0: only dereferenced under row_ok
+            const float* p = img + static_cast<size_t>(ic) * plane + static_cast<long long>(gy0) * g.W + gx;
+            float* sp = slab + c * CH_STRIDE + lane;
+            float v[T];
+#pragma unroll
+            for (int r = 0; r < T; ++r) v[r] = (c_ok && ((row_ok >> r) & 1u)) ? __ldg(p + r * g.W) : 0.f;
+            if (lane < COLS) {
+#pragma unroll
+                for (int r = 0; r < T; ++r) sp[r * COLS] = v[r];
+            }
         }
     }
     __syncthreads();
@@ -204,17 +216,16 @@ wino_input_kernel(const float* __restrict__ in, float* __restrict__ V, WinoGeom 
         for (int y = 0; y < T; ++y) t[y][x] = o[y];
     }
     const size_t tp = static_cast<size_t>(Rl) * g.tilesX + tx;  // chunk-local tile index
-    const size_t plane = static_cast<size_t>(Tc) * g.C_in;     // floats per tile element
-    float* vp = V + tp * g.C_in + ic;                          // plain fp32: the TensorGEMM splits hi/lo on chip
+    // bytes per tile element plane; < 2^32 because all T*T planes live in HBM together
+    const uint32_t plane_bytes = static_cast<uint32_t>(Tc) * static_cast<uint32_t>(g.C_in) * 4u;
+    char* vp = reinterpret_cast<char*>(V + tp * g.C_in + ic);  // plain fp32: the TensorGEMM splits hi/lo on chip
 #pragma unroll
     for (int a = 0; a < T; ++a) {
         float o[T];
         W::bt(t[a], o);
 #pragma unroll
-        for (int b = 0; b < T; ++b) {
-            *vp = o[b];
-            vp += plane;
-        }
+        for (int b = 0; b < T; ++b)  // one IMAD.WIDE.U32 + STG per element
+            *reinterpret_cast<float*>(vp + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(a * T + b)) = o[b];
     }
 }
 
@@ -243,16 +254,15 @@ wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const f
     const int tx = tx0 + w, oc = c0 + lane;
     if (tx < g.tilesX && oc < g.C_out) {
         const size_t tp = static_cast<size_t>(Rl) * g.tilesX + tx;
-        const size_t plane = static_cast<size_t>(Tc) * g.C_out;
-        const float* m = M + tp * g.C_out + oc;
+        const uint32_t plane_bytes = static_cast<uint32_t>(Tc) * static_cast<uint32_t>(g.C_out) * 4u;
+        const char* m = reinterpret_cast<const char*>(M + tp * g.C_out + oc);
         float mm[T][T];
 #pragma unroll
         for (int a = 0; a < T; ++a)
 #pragma unroll
-            for (int b = 0; b < T; ++b) {
-                mm[a][b] = __ldg(m);
-                m += plane;
-            }
+            for (int b = 0; b < T; ++b)
+                mm[a][b] = __ldg(reinterpret_cast<const float*>(
+                    m + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(a * T + b)));
         float tmp[OT][T];
 #pragma unroll
         for (int b = 0; b < T; ++b) {
@@ -279,15 +289,23 @@ wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const f
     }
     __syncthreads();
 
-    // store: warp w takes the (channel,row) lines w, w+5, ...; lane = column (30 of 32 lanes active)
+    // store: warp w takes channels w, w+5, ...; the OT rows of a channel are unrolled; lane = column (30 of 32 lanes)
     const int oy0 = ty * OT, ox = tx0 * OT + lane;
     const size_t oplane = static_cast<size_t>(g.OH) * g.OW;
     float* img = out + static_cast<size_t>(n) * g.C_out * oplane;
     const bool x_ok = lane < COLS && ox < g.OW;
-    for (int line = w; line < kChBlock * OT; line += kSegTiles) {
-        const int c = line / OT, r = line - c * OT;
-        const int o = c0 + c, oy = oy0 + r;
-        if (x_ok && o < g.C_out && oy < g.OH) img[o * oplane + static_cast<size_t>(oy) * g.OW + ox] = slab[c * CH_STRIDE + r * COLS + lane];
+    unsigned row_ok = 0;
+#pragma unroll
+    for (int r = 0; r < OT; ++r)
+        if (oy0 + r < g.OH) row_ok |= 1u << r;
+    for (int c = w; c < kChBlock; c += kSegTiles) {
+        const int o = c0 + c;
+        if (!(x_ok && o < g.C_out)) continue;
+        float* p = img + static_cast<size_t>(o) * oplane + static_cast<size_t>(oy0) * g.OW + ox;
+        const float* sp = slab + c * CH_STRIDE + lane;
+#pragma unroll
+        for (int r = 0; r < OT; ++r)
+            if ((row_ok >> r) & 1u) p[r * g.OW] = sp[r * COLS];
     }
 }
 
