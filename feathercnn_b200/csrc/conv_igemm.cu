@@ -445,7 +445,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const bool ok = bx.valid && ox < args.OW;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
             const size_t oplane = static_cast<size_t>(args.OH) * args.OW;
-            ptx::mbar_wait_relaxed(&tmem_full_bar[as], aphase);
+            ptx::mbar_wait_relaxed<1000>(&tmem_full_bar[as], aphase);
             if (q == 0) IG_TRACE(9, it);
             ptx::tc_fence_after();
 #pragma unroll 1

@@ -81,13 +81,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// Same, for waiters that are not on the critical path (epilogue, TMA producer): back off between polls so the
-// spinning warp does not compete for issue slots with the producer warps.
+// Same, for waiters that are not on the critical path (epilogue, TMA producer, A producers with several slots of
+// slack): back off between polls.  The suspend hint of try_wait wakes on every barrier event of the CTA, so a waiting
+// warp still re-runs this loop a dozen times per k-block; in the implicit-GEMM conv those polls were 30% of all issued
+// instructions and competed with the (issue-bound) producer warps.  NS = sleep per failed poll.
+template <unsigned NS = 256>
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = 0;
     for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
-        __nanosleep(256);
+        __nanosleep(NS);
         if ((spins & 63u) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;

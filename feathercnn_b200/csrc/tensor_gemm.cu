@@ -272,6 +272,8 @@ tensor_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // 3xTF32 kernel: A raw in global memory, split in-kernel into tensor memory, TS-form MMAs
 // --------------------------------------------------------------------------------------------
 // warp 0 TMA | warp 1 MMA | warps 2-5 epilogue | warps 6-9 and 10-13 splitter groups (alternate k-blocks)
+constexpr int kWarpIssuer2 = 14;     // second MMA issuer of the ISSUERS == 2 variant (the first is warp 1)
+constexpr int kDefaultTsIssuers = 1;
 constexpr int kThreadsTs = 14 * 32;
 constexpr int kStagesTs = 4;
 
@@ -295,8 +297,8 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         : "memory");
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreadsTs, 1)
+template <int BN, int ISSUERS>
+__global__ void __launch_bounds__(kThreadsTs + 32 * (ISSUERS - 1), 1)
 tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmBlo, const GemmKernelArgs args) {
     constexpr int STAGES = kStagesTs;
@@ -318,6 +320,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __shared__ uint64_t tmem_full_bar[2];
     __shared__ uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ volatile uint32_t issued_g;  // ISSUERS == 2: k-blocks whose MMAs have been issued
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -326,6 +329,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int kb_per_split = (args.k_blocks_total + args.split_k - 1) / args.split_k;
 
     if (threadIdx.x == 0) {
+        issued_g = 0;
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&a_ready_bar[s], 4);
@@ -379,7 +383,47 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (ISSUERS == 2 && (warp == 1 || warp == kWarpIssuer2)) {
+        // ===================== two MMA issuers alternating k-blocks (see conv_igemm.cu) =====================
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = make_idesc_tf32(BN);
+            const uint32_t me = warp == 1 ? 0u : 1u;
+            const uint64_t dB0 = make_smem_desc_sw128(ptx::smem_u32(smem) + kATile);
+            uint32_t g = 0;  // running k-block index over this CTA's tiles
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int ks = tile / (tiles_per_g * args.G);
+                const int kb0 = ks * kb_per_split;
+                const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                const uint32_t tmem_d = tmem_base + as * BN;
+                const uint32_t g_end = g + static_cast<uint32_t>(kb1 - kb0);
+                for (uint32_t gg = g + ((g ^ me) & 1u); gg < g_end; gg += 2) {
+                    const int stage = static_cast<int>(gg & (STAGES - 1));
+                    const uint32_t phase = (gg / STAGES) & 1u;
+                    const uint64_t dB = dB0 + static_cast<uint64_t>(stage * (kStage >> 4));
+                    const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
+                    const uint32_t ta = tmem_a0 + stage * kAStageCols;
+                    if (gg == g) ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                    ptx::mbar_wait(&a_ready_bar[stage], phase);  // implies full_bar: the splitters waited on it
+                    while (issued_g < gg) {}                      // the other issuer has put k-block gg-1 into the pipe
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k) {
+                        const uint32_t first = (gg == g && k == 0) ? 0u : 1u;
+                        umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);   // A_lo * B_hi
+                        umma_tf32_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_hi * B_lo
+                        umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);           // A_hi * B_hi
+                    }
+                    issued_g = gg + 1;
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (gg + 1 == g_end) ptx::umma_commit(&tmem_full_bar[as]);
+                }
+                g = g_end;
+            }
+        }
+    } else if (ISSUERS == 1 && warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_tf32(BN);
         const bool leader = ptx::elect_one();
@@ -425,7 +469,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (leader) ptx::umma_commit(&tmem_full_bar[as]);
             __syncwarp();
         }
-    } else if (warp >= 6) {
+    } else if (warp >= 6 && warp < kWarpIssuer2) {
         // ===================== splitters: smem raw A row -> TF32 hi / fp32 lo -> tensor memory =====================
         const int group = (warp - 6) >> 2;
         const int q = warp & 3;  // TMEM lane quadrant == 32-row slice of the tile
@@ -472,7 +516,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (lane == 0) ptx::mbar_arrive(&a_ready_bar[my_stage]);
             }
         }
-    } else {
+    } else if (warp >= 2 && warp < 6) {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;
         int it = 0;
@@ -694,7 +738,16 @@ static void fill_kernel_args(const GemmProblem& p, int bn, GemmKernelArgs* a) {
     while (a->split_k > 1 && ceil_div(a->k_blocks_total, a->split_k) * (a->split_k - 1) >= a->k_blocks_total) --a->split_k;
 }
 
-template <int BN>
+static int ts_issuers() {  // FCUDA_TS_ISSUERS=1|2 (experiment switch)
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("FCUDA_TS_ISSUERS");
+        v = (e && e[0] == '2') ? 2 : (e && e[0] == '1') ? 1 : kDefaultTsIssuers;
+    }
+    return v;
+}
+
+template <int BN, int ISSUERS>
 static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
     CUtensorMap tmA, tmB, tmBlo;
     const long long as = p.a_batch_stride ? p.a_batch_stride : static_cast<long long>(p.M) * p.K;
@@ -711,7 +764,7 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
     constexpr int kStage = kBM * kBK * 4 + 2 * BN * kBK * 4;
     static_assert(kStagesTs * kStage + 1024 <= 227 * 1024, "smem budget");
     const int smem = kStagesTs * kStage + 1024;
-    auto kern = tensor_gemm_ts_kernel<BN>;
+    auto kern = tensor_gemm_ts_kernel<BN, ISSUERS>;
     static bool attr_set = false;
     if (!attr_set) {
         FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -720,7 +773,7 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
     const double dense = 2.0 * p.M * static_cast<double>(p.N) * p.K * p.G;
     const int prof = prof_begin(stream, PROF_TENSOR_GEMM, p.algo_flops > 0 ? p.algo_flops : dense, dense * 3.0,
                                 gemm_algo_bytes(p));
-    kern<<<grid, kThreadsTs, smem, stream>>>(tmA, tmB, tmBlo, a);
+    kern<<<grid, kThreadsTs + 32 * (ISSUERS - 1), smem, stream>>>(tmA, tmB, tmBlo, a);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     prof_end(prof, stream);
@@ -731,9 +784,14 @@ int tensor_gemm(const GemmProblem& p, cudaStream_t stream) {
     if (!tensor_gemm_supported(p)) return -1;
     if (p.split_k > 1 && p.epilogue != EPI_COLMAJOR_ATOMIC) return -1;
     if (p.planes == 2) {
-        if (p.N <= 32) return launch_ts<32>(p, stream);
-        if (p.N <= 64) return launch_ts<64>(p, stream);
-        return launch_ts<128>(p, stream);
+        if (ts_issuers() == 2) {
+            if (p.N <= 32) return launch_ts<32, 2>(p, stream);
+            if (p.N <= 64) return launch_ts<64, 2>(p, stream);
+            return launch_ts<128, 2>(p, stream);
+        }
+        if (p.N <= 32) return launch_ts<32, 1>(p, stream);
+        if (p.N <= 64) return launch_ts<64, 1>(p, stream);
+        return launch_ts<128, 1>(p, stream);
     }
     // N tile: smallest supported tile that covers N (fewer wasted MMA columns), capped at 256.
     if (p.N <= 32) return launch<32, 1, 8>(p, stream);
