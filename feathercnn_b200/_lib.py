@@ -63,6 +63,7 @@ def fcuda() -> ctypes.CDLL:
             "fcuda_conv_get_buffer_size": (i, [P, i, i, szp, szp]),
             "fcuda_conv_init": (i, [P, i, vp, vp, vp]),
             "fcuda_conv_forward": (i, [P, i, vp, vp, vp, vp, vp, i, vp]),
+            "fcuda_conv_forward_residual": (i, [P, i, vp, vp, vp, vp, vp, vp, i, i, vp]),
             "fcuda_tensor_gemm": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
             "fcuda_split_tf32": (i, [vp, vp, vp, sz, vp]),
             "fcuda_inner_product_get_buffer_size": (i, [i, i, i, szp, szp]),

@@ -104,6 +104,13 @@ class ConvBooster:
         _check("fcuda_conv_init",
                fcuda().fcuda_conv_init(ctypes.byref(param), self.algo, _ptr(processed_kernel), kp, _stream()))
 
+    def ForwardResidual(self, param: ConvParam, output, input, kernel, buffer, bias_arr, residual, relu_after_add,
+                        batch: int = 1) -> None:
+        _check("fcuda_conv_forward_residual",
+               fcuda().fcuda_conv_forward_residual(ctypes.byref(param), self.algo, _ptr(output), _ptr(input), _ptr(kernel),
+                                                   _ptr(buffer), _ptr(bias_arr), _ptr(residual), int(relu_after_add), batch,
+                                                   _stream()))
+
     def Forward(self, param: ConvParam, output, input, kernel, buffer, bias_arr, batch: int = 1) -> None:
         _check("fcuda_conv_forward",
                fcuda().fcuda_conv_forward(ctypes.byref(param), self.algo, _ptr(output), _ptr(input), _ptr(kernel),
@@ -111,8 +118,10 @@ class ConvBooster:
 
 
 def conv_forward(param: ConvParam, x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None = None,
-                 algo: int | None = None) -> tuple[torch.Tensor, int]:
-    """Whole ConvBooster protocol for a batch x (N, IC, H, W) -> (N, OC, OH, OW).  Returns (output, algo)."""
+                 algo: int | None = None, residual: torch.Tensor | None = None,
+                 relu_after_add: bool = False) -> tuple[torch.Tensor, int]:
+    """Whole ConvBooster protocol for a batch x (N, IC, H, W) -> (N, OC, OH, OW).  Returns (output, algo).
+    With `residual` (shaped like the output) the fused Eltwise-SUM entry point is used instead of Forward."""
     cb = ConvBooster()
     if algo is None:
         rc = cb.SelectAlgo(param)
@@ -126,7 +135,10 @@ def conv_forward(param: ConvParam, x: torch.Tensor, w: torch.Tensor, b: torch.Te
     scratch = torch.empty(max(scratch_n, 1), device=x.device, dtype=torch.float32)
     cb.Init(param, packed, w.contiguous())
     out = torch.empty((n, param.output_channels, param.output_h, param.output_w), device=x.device, dtype=torch.float32)
-    cb.Forward(param, out, x.contiguous(), packed, scratch, b, n)
+    if residual is None:
+        cb.Forward(param, out, x.contiguous(), packed, scratch, b, n)
+    else:
+        cb.ForwardResidual(param, out, x.contiguous(), packed, scratch, b, residual.contiguous(), relu_after_add, n)
     return out, cb.algo
 
 

@@ -14,6 +14,7 @@ struct IgemmProblem {
     int KH, KW, pad_top, pad_left, stride_h, stride_w;
     int planes;           // 1 = TF32, 2 = 3xTF32
     int relu;
+    const float* residual;  // optional (N, OC, OH, OW) tensor added before the activation (fused Eltwise SUM), or null
 };
 
 // KH*KW <= 63 and, unless IC % 32 == 0, KH*KW*IC <= 8192 (shared-memory k-table).

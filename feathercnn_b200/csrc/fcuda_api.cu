@@ -286,8 +286,31 @@ int fcuda_conv_init(const FcudaConvParam* p, int algo, float* packed, const floa
     return rc;
 }
 
+static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
+                             float* scratch, const float* bias, const float* residual, int relu_after_add, int batch,
+                             void* stream);
+
 int fcuda_conv_forward(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
                        float* scratch, const float* bias, int batch, void* stream) {
+    return conv_forward_impl(p, algo, output, input, packed, scratch, bias, nullptr, 0, batch, stream);
+}
+
+int fcuda_conv_forward_residual(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
+                                float* scratch, const float* bias, const float* residual, int relu_after_add, int batch,
+                                void* stream) {
+    if (!p || !residual) return -100;
+    if (algo == FCUDA_SGECONV && p->activation == FCUDA_ACT_NONE)  // fused into the implicit-GEMM epilogue
+        return conv_forward_impl(p, algo, output, input, packed, scratch, bias, residual, relu_after_add, batch, stream);
+    // every other algorithm: the convolution, then the reference's add_relu in place
+    int rc = conv_forward_impl(p, algo, output, input, packed, scratch, bias, nullptr, 0, batch, stream);
+    if (rc) return rc;
+    const size_t n = static_cast<size_t>(batch) * p->output_channels * p->output_h * p->output_w;
+    return add_relu(output, residual, output, n, relu_after_add, as_stream(stream));
+}
+
+static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
+                             float* scratch, const float* bias, const float* residual, int relu_after_add, int batch,
+                             void* stream) {
     ConvPlan pl;
     int rc = make_plan(p, algo, batch, &pl);
     if (rc) return rc;
@@ -356,7 +379,8 @@ int fcuda_conv_forward(const FcudaConvParam* p, int algo, float* output, const f
             } else {
                 g.H = p->input_h; g.W = p->input_w; g.OH = p->output_h; g.OW = p->output_w;
             }
-            g.planes = pl.np; g.relu = relu;
+            g.planes = pl.np; g.relu = residual ? relu_after_add : relu;
+            g.residual = residual;
             return conv_igemm_forward(g, s);
         }
         case FCUDA_NAIVE:

@@ -164,8 +164,19 @@ public:
     int Forward() {
         float* buffer = NULL;
         MEMPOOL_CHECK_RETURN(this->common_mempool->GetPtr(&buffer));
+        if (residual != NULL)
+            return conv_booster.ForwardResidual(&conv_param, tops[0]->data(), bottoms[0]->data(), processed_kernel, buffer,
+                                                bias_data, residual->data(), relu_after_add, bottoms[0]->num(), stream());
         return conv_booster.Forward(&conv_param, tops[0]->data(), bottoms[0]->data(), processed_kernel, buffer, bias_data,
                                     bottoms[0]->num(), stream());
+    }
+
+    // Net::ApplyFusion: absorb `Eltwise SUM(this->top, other) [+ReLU]` (a ResNet shortcut) into this layer's epilogue.
+    int FuseResidual(Blob<float>* other, int relu) {
+        if (residual != NULL) return 0;
+        residual = other;
+        relu_after_add = relu;
+        return 1;
     }
 
     int Fuse(Layer* next_layer) {  // conv_layer.h:174-185, extended to BatchNorm and Scale
@@ -216,6 +227,9 @@ protected:
     std::vector<float> fold_mul, fold_add;
     bool had_bias = false;
     Blob<float>* folded_bias = NULL;
+    // fused Eltwise SUM (Net::ApplyFusion)
+    Blob<float>* residual = NULL;
+    int relu_after_add = 0;
 
 };
 

@@ -56,6 +56,7 @@ public:
     }
 
     enum { Operation_PROD = 0, Operation_SUM = 1, Operation_MAX = 2 };
+    int fused_relu() const { return fuse_relu; }
 
 private:
     int op_type;

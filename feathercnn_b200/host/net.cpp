@@ -11,6 +11,8 @@
 
 #include <feather/layer_factory.h>
 
+#include "layers/conv_layer.h"
+#include "layers/eltwise_layer.h"
 #include "layers/misc_layers.h"
 
 namespace feather {
@@ -485,6 +487,37 @@ int Net::ApplyFusion() {
             b->tops.clear();
             b->bottoms.clear();
             b->_fused_away = true;
+        }
+    }
+    // Second pass: a two-input Eltwise SUM (+ReLU, absorbed above) whose one addend is a convolution's otherwise unread
+    // top becomes that convolution's epilogue (ResNet shortcuts: 16 add_relu passes over the activations in ResNet-50).
+    // The other addend must already exist when the convolution runs.
+    std::map<Blob<float>*, size_t> producer;
+    for (size_t i = 0; i < layers.size(); ++i)
+        for (size_t j = 0; j < layers[i]->tops.size(); ++j) producer[layers[i]->tops[j]] = i;
+    for (size_t j = 0; j < layers.size(); ++j) {
+        EltwiseLayer* e = dynamic_cast<EltwiseLayer*>(layers[j]);
+        if (!e || e->_fused_away || e->bottoms.size() != 2 || e->tops.size() != 1) continue;
+        for (int k = 1; k >= 0; --k) {
+            Blob<float>* mine = e->bottoms[k];
+            Blob<float>* other = e->bottoms[1 - k];
+            if (mine == other || readers[mine] != 1 || !producer.count(mine)) continue;
+            const size_t i = producer[mine];
+            ConvLayer* conv = dynamic_cast<ConvLayer*>(layers[i]);
+            if (!conv || i >= j || conv->_fused_away || conv->tops.size() != 1) continue;
+            if (producer.count(other) && producer[other] >= i) continue;  // not computed yet when the conv runs
+            if (conv->param().activation != booster::None) continue;      // its own ReLU would have to precede the sum
+            if (conv->FuseResidual(other, e->fused_relu()) != 1) continue;
+            Blob<float>* dead = conv->tops[0];
+            blob_map.erase(dead->name);
+            producer.erase(dead);
+            delete dead;
+            conv->tops[0] = e->tops[0];
+            producer[conv->tops[0]] = i;
+            e->tops.clear();
+            e->bottoms.clear();
+            e->_fused_away = true;
+            break;
         }
     }
     return 0;

@@ -140,6 +140,15 @@ int fcuda_dropout_forward(float* output, const float* input, size_t n, float sca
 int fcuda_copy_channels(float* dst, int dst_channels, int dst_channel_offset, const float* src, int channels,
                         size_t stride, int batch, void* stream);
 
+/* Convolution with a fused Eltwise SUM (+ReLU): output = act(conv(input) [+bias] + residual), `residual` shaped like the
+ * output.  Replaces ConvLayer::Forward followed by EltwiseLayer::Forward (src/layers/eltwise_layer.h:68-82 ->
+ * booster::add_relu<>) when the Eltwise is the only reader of the convolution's top (ResNet shortcuts).  SGECONV adds the
+ * residual in its epilogue; every other algorithm runs the convolution and then add_relu in place.  The convolution's
+ * own activation (param->activation) is applied before the sum, relu_after_add after it. */
+int fcuda_conv_forward_residual(const FcudaConvParam* param, int algo, float* output, const float* input,
+                                const float* packed_kernel, float* scratch, const float* bias, const float* residual,
+                                int relu_after_add, int batch, void* stream);
+
 /* Profiling aid for bench.py's roofline leg: while enabled, every TensorGEMM launch is bracketed by CUDA events
  * on its own stream.  fcuda_profile_collect synchronises and reports, since the last enable: summed device time
  * (ms), the algorithmic FLOPs those launches stand for (direct-conv count, booster.h:145-148; 2*in*out*batch for

@@ -54,6 +54,13 @@ public:
                 const float* bias_arr, int batch = 1, void* stream = nullptr) const {
         return fcuda_conv_forward(param, algo, output, input, kernel, buffer, bias_arr, batch, stream);
     }
+    // Forward + fused Eltwise SUM (+ReLU) of `residual` (same shape as the output)
+    int ForwardResidual(ConvParam* param, float* output, const float* input, const float* kernel, float* buffer,
+                        const float* bias_arr, const float* residual, int relu_after_add, int batch = 1,
+                        void* stream = nullptr) const {
+        return fcuda_conv_forward_residual(param, algo, output, input, kernel, buffer, bias_arr, residual, relu_after_add,
+                                           batch, stream);
+    }
     int GetAlgo() const { return algo; }
 
 private:

@@ -160,6 +160,37 @@ def test_sgeconv_implicit_gemm(cuda, oracle, restatement, geom, batch):
         assert rel_err(got1[n], restatement.conv(p, x[n], wt, b, f64=True)) < 2e-3, (geom, n)
 
 
+@pytest.mark.parametrize("algo_name,geom", [
+    ("SGECONV", (64, 32, 14, 14, 1, 1, 0, True)),      # ResNet bottleneck exit: pointwise, fused in the epilogue
+    ("SGECONV", (40, 24, 9, 13, 3, 1, 1, False)),      # OC tail (not a multiple of 32), no bias
+    ("SGECONV", (160, 64, 7, 7, 1, 1, 0, True)),       # two N tiles
+    ("WINOGRADF63", (32, 32, 12, 12, 3, 1, 1, True)),  # not SGECONV: convolution, then add_relu in place
+    ("IM2COL", (16, 8, 10, 10, 3, 2, 1, True)),
+])
+@pytest.mark.parametrize("relu", [False, True])
+def test_conv_forward_residual(cuda, oracle, restatement, algo_name, geom, relu):
+    """fcuda_conv_forward_residual == ConvLayer::Forward then EltwiseLayer::Forward (eltwise_layer.h:68-82)."""
+    from feathercnn_b200 import booster
+    booster.set_precision(booster.PRECISION_TF32X3)
+    oc, ic, h, w, k, stride, pad, bias = geom
+    case = ("residual", oc, ic, h, w, k, stride, pad, 1, bias, False)
+    p, x, wt, b = _data(oracle, case, 2, seed=21)
+    pp = booster.ConvParam.make(oc, ic, h, w, k, stride=stride, pad=pad, bias=bias)
+    rng = np.random.default_rng(5)
+    res = rng.uniform(-1, 1, (2, oc, pp.output_h, pp.output_w)).astype(np.float32)
+    xd, wd = cuda.from_numpy(x).cuda(), cuda.from_numpy(wt).cuda()
+    bd = cuda.from_numpy(b).cuda() if b is not None else None
+    out, used = booster.conv_forward(pp, xd, wd, bd, getattr(booster, algo_name), residual=cuda.from_numpy(res).cuda(),
+                                     relu_after_add=relu)
+    cuda.cuda.synchronize()
+    got = out.cpu().numpy()
+    for n in range(2):
+        want = restatement.conv(p, x[n], wt, b, f64=True) + res[n]
+        if relu:
+            want = np.maximum(want, 0)
+        assert rel_err(got[n], want) < 2e-4, (algo_name, geom, n)
+
+
 def test_plain_tf32_meets_north_star_bar_on_im2col(cuda, oracle, restatement):
     from feathercnn_b200 import booster
     case = CASES[8]

@@ -113,7 +113,10 @@ def test_benchmark_models_every_blob(cuda, oracle, model_dir, name, batch):
 @pytest.mark.parametrize("name", ["resnet50", "mobilenet_v1"])
 def test_benchmark_models_fused_final_output(cuda, oracle, model_dir, name):
     m, (param, binf) = _save(model_dir, name)
-    _compare_all_blobs(oracle, m, param, binf, 1, 2e-4, gpu_kw=dict(fusion=True, cuda_graph=True), blobs=["prob"])
+    _, net = _compare_all_blobs(oracle, m, param, binf, 1, 2e-4, gpu_kw=dict(fusion=True, cuda_graph=True), blobs=["prob"])
+    if name == "resnet50":
+        # 16 shortcuts: Eltwise SUM + ReLU absorbed into the preceding convolution's epilogue (Net::ApplyFusion)
+        assert net.launches_per_forward <= 72, net.launches_per_forward
 
 
 def test_batch_independence_bit_identical(cuda, oracle, model_dir):
