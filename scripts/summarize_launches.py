@@ -6,12 +6,21 @@ import sys
 from collections import defaultdict
 
 rows = []
+traffic = {}  # launch ID -> DRAM bytes (read + write), when the list was collected with the dram__bytes metrics too
+ids = []
 with open(sys.argv[1], newline="") as f:
     lines = [l for l in f if not l.startswith("==")]
 rd = csv.DictReader(lines)
 for r in rd:
+    if r.get("Metric Name", "").startswith("dram__bytes"):
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r.get("Metric Unit", "byte")
+        v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+        traffic[r["ID"]] = traffic.get(r["ID"], 0.0) + v
+        continue
     if r.get("Metric Name") != "gpu__time_duration.sum":
         continue
+    ids.append(r["ID"])
     name = re.sub(r"\(.*", "", r["Kernel Name"]).strip()
     name = re.sub(r"^void ", "", name)
     val = float(r["Metric Value"].replace(",", ""))
@@ -40,3 +49,18 @@ table(rows, "all launches")
 idx = [i for i, (n, _) in enumerate(rows) if "softmax_kernel" in n]
 if len(idx) >= 2:
     table(rows[idx[-2] + 1: idx[-1] + 1], "one Forward (between the last two softmax launches)")
+    if traffic:
+        # measured DRAM traffic per launch of the step, per kernel: what bench.py reports as roofline.traffic
+        import json
+        agg = defaultdict(lambda: [0, 0.0])
+        for i in range(idx[-2] + 1, idx[-1] + 1):
+            k = rows[i][0].split("<")[0].split("::")[-1]
+            agg[k][0] += 1
+            agg[k][1] += traffic.get(ids[i], 0.0)
+        print("== measured DRAM bytes (read+write) per launch, one Forward")
+        out = {}
+        for k, (c, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"{b / c / 1e6:10.1f} MB x {c:3d}  {k}")
+            out[k] = b / c
+        if len(sys.argv) > 2:
+            json.dump(out, open(sys.argv[2], "w"), indent=1)
