@@ -143,7 +143,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     constexpr int STAGES = kStagesIg;
     constexpr int kBTile = BN * 32 * 4;
     constexpr int kStage = PLANES * kBTile;                 // smem per stage: [B_hi][B_lo]
-    constexpr uint32_t kAccCols = 2 * BN;                   // accumulator ring
+    // accumulator ring: as deep as tensor memory allows next to the A ring (4 x 64 columns in 3xTF32 mode).  Tiles with few
+    // k-blocks (IC = 3, pointwise layers) are a latency chain gather -> MMA -> epilogue; with 2 slots conv1_1 of VGG
+    // spent 3.8k cycles per tile for ~1k cycles of work in any one role.
+    constexpr int ACC = BN <= 64 ? 4 : 2;
+    constexpr uint32_t kAccCols = ACC * BN;
     constexpr uint32_t kAStageCols = 32 * PLANES;           // [A_hi (32 cols)][A_lo (32 cols)]
     constexpr uint32_t kNeedCols = kAccCols + STAGES * kAStageCols;
     constexpr uint32_t kTmemCols = kNeedCols <= 32 ? 32 : kNeedCols <= 64 ? 64 : kNeedCols <= 128 ? 128 : kNeedCols <= 256 ? 256 : 512;
@@ -157,8 +161,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // + 1 arrive.expect_tx of the TMA warp (B bytes landed) -> the MMA thread makes ONE wait per k-block
     __shared__ uint64_t full_bar[STAGES];
     __shared__ uint64_t empty_bar[STAGES];    // MMAs that read the stage have retired
-    __shared__ uint64_t tmem_full_bar[2];
-    __shared__ uint64_t tmem_empty_bar[2];
+    __shared__ uint64_t tmem_full_bar[ACC];
+    __shared__ uint64_t tmem_empty_bar[ACC];
     __shared__ uint32_t tmem_base_smem;
     __shared__ volatile uint32_t issued_g;  // k-blocks whose MMAs have been issued (hand-off between the two issuers)
 
@@ -174,7 +178,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             ptx::mbar_init(&full_bar[s], 5);
             ptx::mbar_init(&empty_bar[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < ACC; ++s) {
             ptx::mbar_init(&tmem_full_bar[s], 1);
             ptx::mbar_init(&tmem_empty_bar[s], 4);
         }
@@ -254,12 +258,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 if (tile >= total_tiles) break;
                 const int stage = static_cast<int>(g & (STAGES - 1));
                 const uint32_t phase = (g / STAGES) & 1u;
-                const uint32_t as = it & 1u;
+                const uint32_t as = it & (ACC - 1);
                 const uint32_t tmem_d = tmem_base + as * BN;
                 const uint64_t dB = dB0 + static_cast<uint64_t>(stage * (kStage >> 4));
                 const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
                 const uint32_t ta = tmem_a0 + stage * kAStageCols;
-                if (kb == 0) ptx::mbar_wait(&tmem_empty_bar[as], ((it >> 1) & 1u) ^ 1u);
+                if (kb == 0) ptx::mbar_wait(&tmem_empty_bar[as], ((it / ACC) & 1u) ^ 1u);
                 ptx::mbar_wait(&full_bar[stage], phase);
                 IG_TRACE_T(5, g);
                 while (issued_g < g) {}  // the other issuer has put k-block g-1 into the pipe
@@ -439,8 +443,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
             const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - ptile * static_cast<uint32_t>(args.num_n));
-            const uint32_t as = it & 1u;
-            const uint32_t aphase = (it >> 1) & 1u;
+            const uint32_t as = it & (ACC - 1);
+            const uint32_t aphase = (it / ACC) & 1u;
             const BoxCoord bx = decode_box(ptile * 4 + q, args);  // this warp's 32 TMEM lanes are box q
             const int ox = bx.ox0 + lane;
             const bool ok = bx.valid && ox < args.OW;
