@@ -40,54 +40,93 @@ dw3x3_shuffle_kernel(const float* __restrict__ in, const float* __restrict__ w, 
     const int oy0 = ys * kDwRows;
     const int oy1 = min(oy0 + kDwRows, OH);
 
-    // returns the three horizontally adjacent inputs (left, centre, right) of this lane for input row iy
-    auto load_row = [&](int iy, float& l, float& m, float& r) {
-        const bool row_ok = iy >= 0 && iy < H;
-        const float* rp = ip + static_cast<long long>(iy) * W;
-        if (STRIDE == 1) {
-            const int ix = ox;  // centre column (pad_left == 1)
-            m = (row_ok && ix < W) ? __ldg(rp + ix) : 0.f;
+    // The op is latency-bound unless many row loads are in flight per warp (measured: one row at a time = 29 % of HBM
+    // bandwidth with 40 resident warps).  So input rows are fetched in batches — all global loads of a batch are issued
+    // before the first shuffle (a shuffle waits for its load and would serialise the loads behind it) — and the
+    // horizontal neighbours come from warp shuffles; only lanes 0 / 31 issue one extra (halo) load per row.
+    auto fma3 = [&](float v, int kr, float l, float m, float r) {
+        v = fmaf(k[kr * 3 + 0], l, v);
+        v = fmaf(k[kr * 3 + 1], m, v);
+        return fmaf(k[kr * 3 + 2], r, v);
+    };
+    if (STRIDE == 1) {
+        constexpr int NB = 4;  // output rows per batch == new input rows per batch
+        const int ix = ox;     // centre column (pad_left == 1)
+        const int hx = lane == 0 ? ix - 1 : ix + 1;  // halo column of the edge lanes
+        const bool m_ok = ix < W, h_ok = (lane == 0 || lane == 31) && hx >= 0 && hx < W;
+        auto fetch = [&](int iy, float& m, float& h) {
+            const bool row_ok = iy >= 0 && iy < H;
+            const float* rp = ip + static_cast<long long>(iy) * W;
+            m = (row_ok && m_ok) ? __ldg(rp + ix) : 0.f;
+            h = (row_ok && h_ok) ? __ldg(rp + hx) : 0.f;
+        };
+        auto spread = [&](float m, float h, float& l, float& r) {
             l = __shfl_up_sync(0xffffffffu, m, 1);
             r = __shfl_down_sync(0xffffffffu, m, 1);
-            if (lane == 0) l = (row_ok && ix - 1 >= 0 && ix - 1 < W) ? __ldg(rp + ix - 1) : 0.f;
-            if (lane == 31) r = (row_ok && ix + 1 < W) ? __ldg(rp + ix + 1) : 0.f;
-        } else {
-            const int ix = 2 * ox;  // centre column 2*ox - 1 + 1
-            m = (row_ok && ix < W) ? __ldg(rp + ix) : 0.f;
-            r = (row_ok && ix + 1 < W) ? __ldg(rp + ix + 1) : 0.f;
-            l = __shfl_up_sync(0xffffffffu, r, 1);
-            if (lane == 0) l = (row_ok && ix - 1 >= 0 && ix - 1 < W) ? __ldg(rp + ix - 1) : 0.f;
-        }
-    };
-
-    if (STRIDE == 1) {
-        float a0, a1, a2, b0, b1, b2, c0, c1, c2;
-        load_row(oy0 - 1, a0, a1, a2);
-        load_row(oy0, b0, b1, b2);
-        for (int oy = oy0; oy < oy1; ++oy) {
-            load_row(oy + 1, c0, c1, c2);
-            float v = bv;
-            v = fmaf(k[0], a0, v); v = fmaf(k[1], a1, v); v = fmaf(k[2], a2, v);
-            v = fmaf(k[3], b0, v); v = fmaf(k[4], b1, v); v = fmaf(k[5], b2, v);
-            v = fmaf(k[6], c0, v); v = fmaf(k[7], c1, v); v = fmaf(k[8], c2, v);
-            if (relu) v = fmaxf(v, 0.f);
-            if (ox < OW) op[static_cast<long long>(oy) * OW + ox] = v;
-            a0 = b0; a1 = b1; a2 = b2;
-            b0 = c0; b1 = c1; b2 = c2;
+            if (lane == 0) l = h;
+            if (lane == 31) r = h;
+        };
+        float am, ah, bm, bh, al, ar, bl, br;
+        fetch(oy0 - 1, am, ah);
+        fetch(oy0, bm, bh);
+        spread(am, ah, al, ar);
+        spread(bm, bh, bl, br);
+        for (int oy = oy0; oy < oy1; oy += NB) {
+            float cm[NB], ch[NB], cl[NB], cr[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) fetch(oy + 1 + i, cm[i], ch[i]);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) spread(cm[i], ch[i], cl[i], cr[i]);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                // window rows: (a, b, c0), (b, c0, c1), (c0, c1, c2), (c1, c2, c3)
+                const float tl = i == 0 ? al : i == 1 ? bl : cl[i - 2], tm = i == 0 ? am : i == 1 ? bm : cm[i - 2],
+                            tr = i == 0 ? ar : i == 1 ? br : cr[i - 2];
+                const float ml = i == 0 ? bl : cl[i - 1], mm = i == 0 ? bm : cm[i - 1], mr = i == 0 ? br : cr[i - 1];
+                float v = fma3(bv, 0, tl, tm, tr);
+                v = fma3(v, 1, ml, mm, mr);
+                v = fma3(v, 2, cl[i], cm[i], cr[i]);
+                if (relu) v = fmaxf(v, 0.f);
+                if (ox < OW && oy + i < oy1) op[static_cast<long long>(oy + i) * OW + ox] = v;
+            }
+            al = cl[NB - 2]; am = cm[NB - 2]; ar = cr[NB - 2];
+            bl = cl[NB - 1]; bm = cm[NB - 1]; br = cr[NB - 1];
         }
     } else {
-        float a0, a1, a2, b0, b1, b2, c0, c1, c2;
-        load_row(2 * oy0 - 1, a0, a1, a2);
-        for (int oy = oy0; oy < oy1; ++oy) {
-            load_row(2 * oy, b0, b1, b2);
-            load_row(2 * oy + 1, c0, c1, c2);
-            float v = bv;
-            v = fmaf(k[0], a0, v); v = fmaf(k[1], a1, v); v = fmaf(k[2], a2, v);
-            v = fmaf(k[3], b0, v); v = fmaf(k[4], b1, v); v = fmaf(k[5], b2, v);
-            v = fmaf(k[6], c0, v); v = fmaf(k[7], c1, v); v = fmaf(k[8], c2, v);
-            if (relu) v = fmaxf(v, 0.f);
-            if (ox < OW) op[static_cast<long long>(oy) * OW + ox] = v;
-            a0 = c0; a1 = c1; a2 = c2;
+        constexpr int NB = 2;  // output rows per batch (4 new input rows)
+        const int ix = 2 * ox;  // centre column 2*ox - 1 + 1
+        const bool m_ok = ix < W, r_ok = ix + 1 < W, h_ok = lane == 0 && ix - 1 >= 0 && ix - 1 < W;
+        auto fetch = [&](int iy, float& m, float& r, float& h) {
+            const bool row_ok = iy >= 0 && iy < H;
+            const float* rp = ip + static_cast<long long>(iy) * W;
+            m = (row_ok && m_ok) ? __ldg(rp + ix) : 0.f;
+            r = (row_ok && r_ok) ? __ldg(rp + ix + 1) : 0.f;
+            h = (row_ok && h_ok) ? __ldg(rp + ix - 1) : 0.f;
+        };
+        auto spread = [&](float r, float h, float& l) {
+            l = __shfl_up_sync(0xffffffffu, r, 1);
+            if (lane == 0) l = h;
+        };
+        float am, ar, ah, al;
+        fetch(2 * oy0 - 1, am, ar, ah);
+        spread(ar, ah, al);
+        for (int oy = oy0; oy < oy1; oy += NB) {
+            float cm[2 * NB], cr[2 * NB], ch[2 * NB], cl[2 * NB];
+#pragma unroll
+            for (int i = 0; i < 2 * NB; ++i) fetch(2 * oy + i, cm[i], cr[i], ch[i]);
+#pragma unroll
+            for (int i = 0; i < 2 * NB; ++i) spread(cr[i], ch[i], cl[i]);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                // output row oy+i reads input rows 2(oy+i)-1, 2(oy+i), 2(oy+i)+1 = (a | c[2i-1]), c[2i], c[2i+1]
+                const float tl = i == 0 ? al : cl[2 * i - 1], tm = i == 0 ? am : cm[2 * i - 1], tr = i == 0 ? ar : cr[2 * i - 1];
+                float v = fma3(bv, 0, tl, tm, tr);
+                v = fma3(v, 1, cl[2 * i], cm[2 * i], cr[2 * i]);
+                v = fma3(v, 2, cl[2 * i + 1], cm[2 * i + 1], cr[2 * i + 1]);
+                if (relu) v = fmaxf(v, 0.f);
+                if (ox < OW && oy + i < oy1) op[static_cast<long long>(oy + i) * OW + ox] = v;
+            }
+            al = cl[2 * NB - 1]; am = cm[2 * NB - 1]; ar = cr[2 * NB - 1];
         }
     }
 }
