@@ -73,21 +73,26 @@ def model_files(model: str, rank: int, barrier) -> tuple[str, str, float, tuple]
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe).
+
+    nvidia-smi needs ~0.1-0.5 s to deliver its first row, longer than a short timed region, so the poller is started
+    before the warm-up and only the rows received inside the marked windows (device-resident leg and end-to-end leg,
+    both under the same load) are used."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.rows: list[list[str]] = []
+        self.rows: list[tuple[float, list[str]]] = []
+        self.windows: list[list[float]] = []
         self.proc = None
         self.gpu = gpu_index
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -96,31 +101,48 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.windows.append([time.perf_counter(), float("inf")])
+
+    def end(self):
+        if self.windows:
+            self.windows[-1][1] = time.perf_counter()
 
     def stop(self) -> dict:
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 8:
-                continue
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+
+        def collect(slack: float):
+            sm, mx, reasons = [], [], set()
+            for t, r in self.rows:
+                if len(r) < 8 or not any(w0 - slack <= t <= w1 + slack for w0, w1 in self.windows):
+                    continue
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sm, mx, reasons
+
+        sm, mx, reasons = collect(0.0)
+        how = "inside the timed regions"
+        if not sm:  # a region shorter than the polling period: take the rows right around it
+            sm, mx, reasons = collect(0.12)
+            how = "within 120 ms of the timed regions"
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled": how,
+                "window_s": round(sum(min(w1, time.perf_counter()) - w0 for w0, w1 in self.windows), 3)}
 
 
 def cpu_reference_arm(param: str, binf: str, batch_hint: int, warmup: int, steps: int) -> dict:
@@ -231,6 +253,9 @@ def main() -> None:
         return float(t.item())
 
     # ---- device-resident leg ("value") -------------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     with torch.cuda.stream(stream):
         for i in range(args.warmup + n_rot):  # eager pass, then one graph capture per rotating buffer
             d = dev_batches[i % n_rot]
@@ -240,9 +265,8 @@ def main() -> None:
         launches = net.launches_per_forward
         barrier()
         torch.cuda.synchronize(dev)
-        sampler = ClockSampler(local_rank) if rank == 0 else None
         if sampler:
-            sampler.start()
+            sampler.begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(args.steps):
@@ -253,10 +277,13 @@ def main() -> None:
         e1.synchronize()
         torch.cuda.synchronize(dev)
         barrier()
+        if sampler:
+            sampler.end()
         ms_dev = max_over_ranks(e0.elapsed_time(e1))
-        clocks = sampler.stop() if sampler else None
 
         if args.lean:
+            if sampler:
+                sampler.stop()
             if rank == 0:
                 print(json.dumps({"lean": True, "value": world * B * args.steps / (ms_dev * 1e-3),
                                   "ms_per_step": ms_dev / args.steps, "launches_per_step": int(launches)}), flush=True)
@@ -272,6 +299,8 @@ def main() -> None:
             net.ExtractInto(out_name, host_out.data_ptr())
         barrier()
         torch.cuda.synchronize(dev)
+        if sampler:
+            sampler.begin()
         e0.record(stream)
         t_wall = time.perf_counter()
         for i in range(args.steps):
@@ -280,6 +309,9 @@ def main() -> None:
         e1.record(stream)
         e1.synchronize()
         t_wall = time.perf_counter() - t_wall
+        if sampler:
+            sampler.end()
+        clocks = sampler.stop() if sampler else None
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         d2h_bytes = host_out.numel() * 4

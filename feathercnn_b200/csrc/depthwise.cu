@@ -148,10 +148,23 @@ dw3x3_plane_kernel(const float* __restrict__ in, const float* __restrict__ w, co
     const int c = static_cast<int>(plane % C);
     const float* ip = in + plane * H * W;
     const unsigned rcp_pw = (65536u + PW - 1) / PW, rcp_ow = (65536u + OW - 1) / OW;
-    for (unsigned i = lane; i < static_cast<unsigned>(PH * PW); i += 32) {
-        const unsigned y = (i * rcp_pw) >> 16, x = i - y * PW;
-        const int iy = static_cast<int>(y) - 1, ix = static_cast<int>(x) - 1;
-        tile[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(ip + iy * W + ix) : 0.f;
+    // eight loads in flight per lane, then the eight shared-memory stores (a store right behind its load would make the
+    // next load wait for it)
+    const unsigned n_tile = static_cast<unsigned>(PH * PW);
+    for (unsigned base = 0; base < n_tile; base += 256) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned i = base + j * 32 + lane;
+            const unsigned y = (i * rcp_pw) >> 16, x = i - y * PW;
+            const int iy = static_cast<int>(y) - 1, ix = static_cast<int>(x) - 1;
+            v[j] = (i < n_tile && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(ip + iy * W + ix) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned i = base + j * 32 + lane;
+            if (i < n_tile) tile[i] = v[j];
+        }
     }
     float k[9];
 #pragma unroll
