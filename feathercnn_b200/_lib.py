@@ -124,6 +124,8 @@ def feather() -> ctypes.CDLL:
             "fnet_launches_per_forward": (ctypes.c_ulonglong, [vp]),
             "fnet_input_shape": (i, [vp, ip, ip, ip]),
             "fnet_blob_names": (sz, [vp, cp, sz]),
+            "fnet_fuse_now": (i, [vp]),
+            "fnet_layer_fused_away": (i, [vp, cp]),
             "fnet_input_name": (cp, [vp]),
         }
         for name, (res, args) in sigs.items():

@@ -15,6 +15,8 @@ void* fnet_create(void) { return new Net(); }
 void fnet_destroy(void* h) { delete static_cast<Net*>(h); }
 void fnet_set_fusion(void* h, int enable) { static_cast<Net*>(h)->SetFusion(enable != 0); }
 void fnet_set_cuda_graph(void* h, int enable) { static_cast<Net*>(h)->SetCudaGraph(enable != 0); }
+int fnet_fuse_now(void* h) { return static_cast<Net*>(h)->FuseNow(); }
+int fnet_layer_fused_away(void* h, const char* name) { return static_cast<Net*>(h)->LayerFusedAway(name ? name : ""); }
 void fnet_set_stream(void* h, void* stream) { static_cast<Net*>(h)->SetStream(stream); }
 int fnet_load_param(void* h, const char* path) { return static_cast<Net*>(h)->LoadParam(path); }
 int fnet_load_param_text(void* h, const char* text) { return static_cast<Net*>(h)->LoadParamFromText(text); }

@@ -523,6 +523,23 @@ int Net::ApplyFusion() {
     return 0;
 }
 
+int Net::FuseNow() {
+    if (!_param_loaded) return -1;
+    if (fusion_ && !fusion_applied_) {
+        ApplyFusion();
+        fusion_applied_ = true;
+    }
+    int n = 0;
+    for (size_t i = 0; i < layers.size(); ++i) n += layers[i]->_fused_away ? 1 : 0;
+    return n;
+}
+
+int Net::LayerFusedAway(const std::string& layer_name) const {
+    for (size_t i = 0; i < layers.size(); ++i)
+        if (layers[i]->name == layer_name) return layers[i]->_fused_away ? 1 : 0;
+    return -1;
+}
+
 void Net::ResetGraph() {
     for (auto& kv : graph_cache_) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(kv.second));
     graph_cache_.clear();

@@ -129,6 +129,13 @@ class Net:
                                                               ctypes.byref(c), ctypes.byref(h), ctypes.byref(w)))
         return p.value, (n.value, c.value, h.value, w.value)
 
+    def FuseNow(self) -> int:
+        """Run the SetFusion graph rewrite now (host only); returns the number of layers absorbed."""
+        return int(self._lib.fnet_fuse_now(self._h))
+
+    def LayerFusedAway(self, layer_name: str) -> int:
+        return int(self._lib.fnet_layer_fused_away(self._h, layer_name.encode()))
+
     def BlobNames(self) -> list[str]:
         need = self._lib.fnet_blob_names(self._h, None, 0)
         buf = ctypes.create_string_buffer(need)

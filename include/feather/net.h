@@ -76,6 +76,10 @@ public:
     const std::string& InputName() const { return input_name_; }
     void InputShape(int* c, int* h, int* w) const { *c = input_c_; *h = input_h_; *w = input_w_; }
     std::vector<std::string> BlobNames() const;
+    // Runs the SetFusion(true) graph rewrite now instead of at the first Forward (host only, no kernel; idempotent) and
+    // returns how many layers were absorbed into their producers.  LayerFusedAway: 1 / 0, -1 for an unknown layer.
+    int FuseNow();
+    int LayerFusedAway(const std::string& layer_name) const;
 
 private:
     int ParseParamText(const char* text);

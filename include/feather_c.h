@@ -14,6 +14,8 @@ void* fnet_create(void);                                         /* Net::Net(), 
 void fnet_destroy(void* net);
 void fnet_set_fusion(void* net, int enable);                     /* live TryFuse pass, layer.h:61-68 */
 void fnet_set_cuda_graph(void* net, int enable);
+int fnet_fuse_now(void* net);                                    /* run the fusion rewrite now; returns #layers absorbed */
+int fnet_layer_fused_away(void* net, const char* layer_name);    /* 1 / 0, -1 unknown layer */
 void fnet_set_stream(void* net, void* cuda_stream);
 int fnet_load_param(void* net, const char* param_path);          /* Net::LoadParam, net.cpp:54-170 */
 int fnet_load_param_text(void* net, const char* param_text);     /* same grammar from memory */

@@ -127,9 +127,9 @@ def test_tuned_select_algo_moves_bandwidth_bound_layers():
     assert tuned(32, 32, 56, 56, 3, stride=1, pad=1, group=32) == booster.DEPTHWISE
 
 
-def _net():
+def _net(**kw):
     from feathercnn_b200.net import Net
-    return Net()
+    return Net(**kw)
 
 
 def test_load_param_builds_the_blob_graph(tmp_path):
@@ -157,6 +157,54 @@ def test_load_param_rejects_like_the_reference(text, code):
     with pytest.raises(FeatherError) as e:
         _net().LoadParamFromText(text)
     assert e.value.code == code
+
+
+RESNET_BLOCK = """7767517
+9 10
+Input data 0 1 data 0=8 1=8 2=8
+Convolution conv_in 1 1 data conv_in 0=8 1=3 3=1 4=1 5=1 6=576
+ReLU relu_in 1 1 conv_in relu_in
+Split split 1 2 relu_in sa sb
+Convolution branch 1 1 sb branch 0=8 1=1 3=1 4=0 5=1 6=64
+Eltwise sum 2 1 sa branch sum 0=1
+ReLU relu_out 1 1 sum relu_out
+Convolution tail 1 1 relu_out tail 0=8 1=3 3=1 4=1 5=0 6=576
+ReLU tail_relu 1 1 tail tail_relu
+"""
+
+
+def test_fusion_pass_rewrites_the_graph_on_the_host():
+    """The live TryFuse pass (layer.h:61-68, dead in the reference) + the shortcut pass: conv+ReLU, Eltwise+ReLU, and the
+    Eltwise SUM itself absorbed into the convolution that produces its otherwise unread addend.  Host only."""
+    net = _net(fusion=True)
+    net.LoadParamFromText(RESNET_BLOCK)
+    assert net.FuseNow() == 4                      # relu_in, relu_out, sum, tail_relu
+    assert net.FuseNow() == 4                      # idempotent
+    for name, fused in [("relu_in", 1), ("relu_out", 1), ("sum", 1), ("tail_relu", 1),
+                        ("conv_in", 0), ("branch", 0), ("split", 0), ("tail", 0)]:
+        assert net.LayerFusedAway(name) == fused, name
+    assert net.LayerFusedAway("nope") == -1
+    names = set(net.BlobNames())
+    # the absorbed layers' intermediate blobs are gone; the surviving producer writes the last name of the chain
+    assert {"data", "relu_in", "sa", "sb", "relu_out", "tail_relu"} <= names
+    assert not ({"conv_in", "branch", "sum", "tail"} & names)
+    plain = _net()
+    plain.LoadParamFromText(RESNET_BLOCK)
+    assert plain.FuseNow() == 0                    # SetFusion(false): nothing is rewritten
+
+
+def test_residual_and_profile_entry_points_validate_arguments():
+    from feathercnn_b200 import booster
+    from feathercnn_b200._lib import fcuda
+    lib = fcuda()
+    p = booster.ConvParam.make(8, 8, 8, 8, 1)
+    assert lib.fcuda_conv_forward_residual(ctypes.byref(p), booster.SGECONV, None, None, None, None, None, None, 1, 1, None) == -100
+    ms, af, mf, ab = ctypes.c_double(-1), ctypes.c_double(-1), ctypes.c_double(-1), ctypes.c_double(-1)
+    n = ctypes.c_longlong(-1)
+    for kind in (-1, 0, 1, 6):
+        assert lib.fcuda_profile_collect_kind(kind, ctypes.byref(ms), ctypes.byref(af), ctypes.byref(mf), ctypes.byref(ab),
+                                              ctypes.byref(n)) == 0
+        assert (ms.value, af.value, ab.value, n.value) == (0.0, 0.0, 0.0, 0)
 
 
 def test_feathermodel_container_round_trip(tmp_path):
