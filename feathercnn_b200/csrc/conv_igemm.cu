@@ -12,17 +12,25 @@
 //                pixel <-> TMEM lane.
 //   A operand  = lives in TENSOR MEMORY.  Twelve producer warps (3 groups x 4; group g serves every third k-block) each
 //                own 32 pixels (= their TMEM lane quadrant): a thread gathers the 32 k-values of its pixel (loads
-//                coalesced across lanes along x; offsets and tap coordinates come from a small shared-memory table,
-//                validity from per-pixel row/column bit masks), splits them into TF32 hi + fp32 lo and writes them with
-//                tcgen05.st.  (TMA cannot gather: its innermost box coordinate must be 16-byte aligned — a +-1 pixel
-//                tap shift traps; an A tile in shared memory costs 3x the instructions and all of the smem bandwidth.)
-//   B operand  = filters re-packed once at Init to Wp[oc][k] (K-major), TF32 hi / fp32 lo planes, loaded by TMA.
-//   MMA        = one thread issues tcgen05.mma kind::tf32 with A from TMEM ("TS" form), 3 MMAs per k-step in 3xTF32
-//                mode, fp32 accumulators in a 2-deep TMEM ring next to the 4-deep A ring.
-//   epilogue   = tcgen05.ld -> +bias -> ReLU -> NCHW store; lanes hold consecutive pixels -> 128-byte coalesced rows.
+//                coalesced across lanes along x, the NEXT k-block's 32 loads in flight while the current one is split),
+//                splits them into TF32 hi + fp32 lo (2 instructions per element) and writes them with tcgen05.st into a
+//                4-deep ring.  IC % 32 == 0: a k-block is one tap x 32 channels -> one predicate, one IMAD.WIDE per
+//                address; otherwise offsets and taps come from a small shared-memory table and a per-pixel tap mask.
+//                (TMA cannot gather: its innermost box coordinate must be 16-byte aligned — a +-1 pixel tap shift
+//                traps; an A tile in shared memory costs 3x the instructions and +33 cycles per MMA.)
+//   B operand  = filters re-packed once at Init to Wp[oc][k] (K-major), TF32 hi / fp32 lo planes, loaded by TMA into a
+//                4-deep shared-memory ring; one barrier per ring slot counts the 4 producer arrivals and the TMA bytes.
+//   MMA        = tcgen05.mma kind::tf32 with A from TMEM ("TS" form), 3 MMAs per k-step in 3xTF32 mode, issued by TWO
+//                elected threads that alternate k-blocks (the pipe holds ~6 MMAs and issue blocks beyond that; one
+//                thread's barrier wait / descriptor arithmetic / commit overlaps the other's blocking issue); fp32
+//                accumulators in a 2- (BN = 128) or 4-deep (BN <= 64) TMEM ring next to the A ring.
+//   epilogue   = tcgen05.ld -> +bias (staged in smem) [-> + residual, prefetched: fused Eltwise SUM] -> ReLU -> NCHW
+//                store; lanes hold consecutive pixels -> 128-byte coalesced rows.
+//   roles      = 19 warps: 0-3 epilogue, 4-15 producers (TMEM quadrant = warp % 4), 16 TMA, 17-18 MMA issuers.
 //
 // Used where non-fused Winograd is bandwidth-bound (large images, <= 128 channels) and for every layer the reference
-// sends to im2col + SGEMM (1x1, strided, 7x7, IC = 3).
+// sends to im2col + SGEMM (1x1, strided, 7x7, IC = 3).  Measurements behind these choices: DESIGN.md section 3,
+// tests/cuda/mma_rate.cu, tests/cuda/igemm_trace.cu.
 #include "conv_igemm.cuh"
 
 #include "common.cuh"

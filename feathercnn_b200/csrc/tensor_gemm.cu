@@ -1,11 +1,24 @@
 // TensorGEMM on tcgen05 (sm_100a).  See tensor_gemm.cuh for the contract.
 //
-// Kernel anatomy (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer   : cp.async.bulk.tensor 3D boxes (K=32 fp32 = one 128B swizzle atom)
-//   warp 1      MMA issuer     : one thread issues tcgen05.mma kind::tf32, accumulators in TMEM
-//   warps 2..5  epilogue       : tcgen05.ld 32x32b -> registers -> fused store (row-major / NCHW+bias+ReLU / FC)
-// Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring
-// (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Two persistent kernels, one CTA per SM:
+//
+// tensor_gemm_ts_kernel<BN>  (3xTF32, the product path: Winograd's 64-way batched GEMM, im2col GEMM, InnerProduct)
+//   warp 0        TMA producer : per 32-wide k-block one raw fp32 A tile (128 rows) + the B_hi and B_lo tiles
+//                                (cp.async.bulk.tensor 3-D boxes, 128-byte swizzle) into a 4-deep smem ring
+//   warps 6..13   splitters    : two groups of 4 alternate k-blocks; a thread reads its (swizzled) A row from smem, splits
+//                                it into TF32 hi + fp32 lo (2 instructions per element) and parks both in tensor memory
+//                                (tcgen05.st), so A is ONE plane in HBM and the MMA takes it from TMEM (TS form: no 4 KB
+//                                smem read per instruction, measured 33 cycles each)
+//   warp 1        MMA issuer   : A_lo*B_hi + A_hi*B_lo + A_hi*B_hi per k-step into one fp32 TMEM accumulator; the next
+//                                slot's barrier is probed between MMAs because the pipe only queues ~6 of them
+//   warps 2..5    epilogue     : tcgen05.ld 32x32b -> fused store (row-major / NCHW+bias+ReLU / transposed split-K atomics)
+//   (a second issuer warp exists behind FCUDA_TS_ISSUERS=2; measured 2 % slower here, unlike in conv_igemm.cu)
+//
+// tensor_gemm_kernel<BN,PLANES,STAGES>  (plain TF32 mode and A/B tests: both operands from smem, "SS" form, 192 threads)
+//   warp 0 TMA, warp 1 MMA, warps 2..5 epilogue.
+//
+// Both: STAGES-deep operand ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring (tmem_full/tmem_empty) so
+// the epilogue of tile i overlaps the MMAs of tile i+1; bounded mbarrier waits trap instead of hanging the GPU.
 #include "tensor_gemm.cuh"
 #include "common.cuh"
 #include "tcgen05.cuh"
