@@ -124,6 +124,7 @@ def feather() -> ctypes.CDLL:
             "fnet_launches_per_forward": (ctypes.c_ulonglong, [vp]),
             "fnet_input_shape": (i, [vp, ip, ip, ip]),
             "fnet_blob_names": (sz, [vp, cp, sz]),
+            "fnet_modelbin_load_mem": (ctypes.c_long, [ctypes.c_char_p, i, i, ctypes.POINTER(ctypes.c_float)]),
             "fnet_fuse_now": (i, [vp]),
             "fnet_layer_fused_away": (i, [vp, cp]),
             "fnet_input_name": (cp, [vp]),

@@ -2,6 +2,7 @@
 // Declared in include/feather_c.h.
 #include <feather_c.h>
 
+#include <feather/ncnn/modelbin.h>
 #include <feather/net.h>
 #include <string.h>
 
@@ -15,6 +16,14 @@ void* fnet_create(void) { return new Net(); }
 void fnet_destroy(void* h) { delete static_cast<Net*>(h); }
 void fnet_set_fusion(void* h, int enable) { static_cast<Net*>(h)->SetFusion(enable != 0); }
 void fnet_set_cuda_graph(void* h, int enable) { static_cast<Net*>(h)->SetCudaGraph(enable != 0); }
+long fnet_modelbin_load_mem(const unsigned char* buf, int w, int type, float* out) {
+    const unsigned char* mem = buf;
+    ncnn::ModelBinFromMemory mb(mem);
+    ncnn::Mat m = mb.load(w, type);
+    if (m.empty() || !out) return -1;
+    memcpy(out, m.data, sizeof(float) * static_cast<size_t>(w));
+    return static_cast<long>(mem - buf);
+}
 int fnet_fuse_now(void* h) { return static_cast<Net*>(h)->FuseNow(); }
 int fnet_layer_fused_away(void* h, const char* name) { return static_cast<Net*>(h)->LayerFusedAway(name ? name : ""); }
 void fnet_set_stream(void* h, void* stream) { static_cast<Net*>(h)->SetStream(stream); }

@@ -14,6 +14,10 @@ void* fnet_create(void);                                         /* Net::Net(), 
 void fnet_destroy(void* net);
 void fnet_set_fusion(void* net, int enable);                     /* live TryFuse pass, layer.h:61-68 */
 void fnet_set_cuda_graph(void* net, int enable);
+/* Decodes one ncnn weight blob of `w` floats from an in-memory .bin image (ncnn::ModelBinFromMemory, the loader behind
+ * Net::InitFromBuffer; src/ncnn/modelbin.cpp:204-293: type 0 = tagged fp32 / fp16 / 256-entry LUT, type 1 = raw fp32).
+ * Host only.  Returns the bytes consumed, or -1 when the blob is rejected (int8, truncated, unknown type). */
+long fnet_modelbin_load_mem(const unsigned char* buf, int w, int type, float* out);
 int fnet_fuse_now(void* net);                                    /* run the fusion rewrite now; returns #layers absorbed */
 int fnet_layer_fused_away(void* net, const char* layer_name);    /* 1 / 0, -1 unknown layer */
 void fnet_set_stream(void* net, void* cuda_stream);

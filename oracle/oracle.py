@@ -194,6 +194,15 @@ class Reference:
         self.lib = ctypes.CDLL(str(_REF_SO))
         self.lib.ref_net_create.restype = ctypes.c_void_p
         self.lib.ref_net_time_forward.restype = ctypes.c_double
+        if hasattr(self.lib, "ref_modelbin_load_mem"):
+            self.lib.ref_modelbin_load_mem.restype = ctypes.c_long
+
+    def modelbin_load_mem(self, blob: bytes, w: int, type_: int):
+        """ncnn::ModelBinFromMemory::load of the reference (modelbin.cpp:204-293) -> (floats or None, bytes consumed)."""
+        out = np.zeros(max(w, 1), np.float32)
+        buf = ctypes.create_string_buffer(blob + b"\0" * 64, len(blob) + 64)
+        n = self.lib.ref_modelbin_load_mem(ctypes.cast(buf, ctypes.POINTER(ctypes.c_ubyte)), w, type_, _fp(out))
+        return (None, -1) if n < 0 else (out[:w].copy(), int(n))
 
     def conv(self, p: ConvParam, x, w, b=None, algo: int = -1, repeat: int = 1):
         x = np.ascontiguousarray(x, np.float32)

@@ -3,8 +3,10 @@
 // it contains no reference code — it only calls the reference's public API:
 //   booster::ConvBooster            /root/reference/src/booster/include/booster/booster.h:151-170
 //   feather::Net                    /root/reference/src/net.h:30-70
+//   ncnn::ModelBinFromMemory        /root/reference/src/ncnn/modelbin.h:55-65 (weight-blob decoder: fp32 / fp16 / LUT)
 // Used by tests/ (parity oracle), __graft_entry__.smoke() and bench.py's CPU baseline.
 #include <booster/booster.h>
+#include <ncnn/modelbin.h>
 #include <net.h>
 
 #include <fcntl.h>
@@ -180,6 +182,18 @@ double ref_net_time_forward(void* h, const char* input_name, const float* chw, i
     double t0 = now_s();
     for (int i = 0; i < iters; ++i) net->Forward();
     return (now_s() - t0) / (iters > 0 ? iters : 1);
+}
+
+// Decodes one weight blob of `w` floats from an in-memory .bin image with the reference's own loader
+// (modelbin.cpp:204-293).  Returns the number of bytes consumed, or -1 when the loader returned an empty Mat.
+long ref_modelbin_load_mem(const unsigned char* buf, int w, int type, float* out) {
+    Quiet q;
+    const unsigned char* mem = buf;
+    ncnn::ModelBinFromMemory mb(mem);
+    ncnn::Mat m = mb.load(w, type);
+    if (m.empty()) return -1;
+    memcpy(out, m.data, sizeof(float) * static_cast<size_t>(w));
+    return static_cast<long>(mem - buf);
 }
 
 }  // extern "C"

@@ -207,6 +207,49 @@ def test_residual_and_profile_entry_points_validate_arguments():
         assert (ms.value, af.value, ab.value, n.value) == (0.0, 0.0, 0.0, 0)
 
 
+def _modelbin_cases():
+    rng = np.random.default_rng(11)
+    w = 37  # odd on purpose: fp16 and LUT payloads are padded to 4 bytes (modelbin.cpp alignSize)
+    vals = rng.standard_normal(w).astype(np.float32)
+    half = vals.astype(np.float16)
+    table = rng.standard_normal(256).astype(np.float32)
+    idx = rng.integers(0, 256, w).astype(np.uint8)
+    pad = lambda b: b + b"\0" * (-len(b) % 4)
+    tag = lambda t: np.uint32(t).tobytes()
+    return [
+        ("raw fp32 (tag 0)", 0, tag(0) + vals.tobytes(), vals, 4 + 4 * w),
+        ("fp16 (tag 0x01306B47)", 0, tag(0x01306B47) + pad(half.tobytes()), half.astype(np.float32), 4 + len(pad(half.tobytes()))),
+        ("256-entry LUT", 0, tag(0x00000101) + table.tobytes() + pad(idx.tobytes()), table[idx], 4 + 1024 + len(pad(idx.tobytes()))),
+        ("raw fp32 via the 0x0002C056 tag", 0, tag(0x0002C056) + vals.tobytes(), vals, 4 + 4 * w),
+        ("type 1: untagged fp32", 1, vals.tobytes(), vals, 4 * w),
+    ]
+
+
+@pytest.mark.parametrize("case", _modelbin_cases(), ids=[c[0] for c in _modelbin_cases()])
+def test_weight_blob_decoder_matches_the_reference_loader(oracle, case):
+    """fp16 and LUT-quantised ncnn weight blobs and the from-memory loader
+    (src/ncnn/modelbin.cpp:77-160, 204-293) decode exactly like the reference's ModelBinFromMemory."""
+    from feathercnn_b200._lib import feather
+    name, type_, blob, want, nbytes = case
+    w = len(want)
+    out = np.zeros(w, np.float32)
+    n = feather().fnet_modelbin_load_mem(blob + b"\0" * 64, w, type_, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    assert n == nbytes, name
+    np.testing.assert_array_equal(out, want)
+    if oracle.reference_available():
+        ref_vals, ref_n = oracle.Reference().modelbin_load_mem(blob, w, type_)
+        assert ref_n == n, name
+        np.testing.assert_array_equal(ref_vals, out)
+
+
+def test_weight_blob_decoder_rejects_int8_like_the_layer_does():
+    from feathercnn_b200._lib import feather
+    blob = np.uint32(0x000D4B38).tobytes() + bytes(64)  # int8 weights: conv_layer.h:49-54 refuses them
+    out = np.zeros(8, np.float32)
+    assert feather().fnet_modelbin_load_mem(blob, 8, 0, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))) == -1
+    assert feather().fnet_modelbin_load_mem(blob, 8, 7, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))) == -1  # unknown type
+
+
 def test_feathermodel_container_round_trip(tmp_path):
     from feathercnn_b200.tools import feathermodel, modelgen
     param, binf = modelgen.single_conv(ic=4, oc=4, h=9, w=9).save(tmp_path / "m")
