@@ -319,64 +319,67 @@ def main() -> None:
         # ---- roofline leg: per-launch CUDA events around every TensorGEMM of one eager Forward ---------------
         roof = None
         if rank == 0:
-            import ctypes
-            lib = booster.fcuda()
-            net._lib.fnet_set_cuda_graph(net._h, 0)
-            net.FeedInputDevice(dev_batches[0].data_ptr(), tuple(dev_batches[0].shape))
-            net.Forward(); net.Synchronize()
-            lib.fcuda_profile_tensor_gemm(1)
-            reps = 2
-            for i in range(reps):
-                d = dev_batches[i % n_rot]
-                net.FeedInputDevice(d.data_ptr(), tuple(d.shape))
-                net.Forward()
-            net.Synchronize()
-            peaks, how = measured_peaks()
-            # kernels timed inside a long step -> the sustained figures; fallbacks = /opt/skills/guides/B200_PROFILING.md
-            tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-            hbm_peak = float(peaks.get("hbm_gbs", 6500.0))
-            names = ["tensor_gemm_ts_kernel (tcgen05 kind::tf32, Winograd/im2col/FC GEMM)",
-                     "conv_igemm_kernel (tcgen05 kind::tf32 implicit-GEMM conv)", "wino_input_kernel",
-                     "wino_output_kernel", "pooling_kernel", "depthwise kernels", "element-wise kernels"]
-            classes = []
-            for kind, name in enumerate(names):
-                ms_t, af, mf, ab, nl = (ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double(),
-                                        ctypes.c_longlong())
-                lib.fcuda_profile_collect_kind(kind, ctypes.byref(ms_t), ctypes.byref(af), ctypes.byref(mf),
-                                               ctypes.byref(ab), ctypes.byref(nl))
-                if nl.value == 0 or ms_t.value <= 0:
-                    continue
-                sec = ms_t.value * 1e-3
-                tensor = kind <= 1
-                ach = af.value / sec / 1e12 if tensor else ab.value / sec / 1e9
-                peak = tf_peak if tensor else hbm_peak
-                c = {"kernel": name, "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
-                     "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak,
-                     "launches_per_step": nl.value / reps, "avg_launch_us": 1e3 * ms_t.value / nl.value,
-                     "share_of_step": (ms_t.value / reps) / (ms_dev / args.steps)}
-                if tensor:
-                    c["algorithmic_gflop_per_launch"] = af.value / nl.value / 1e9
-                    c["algorithmic_gb_per_launch"] = ab.value / nl.value / 1e9
-                    c["hbm_gbps_at_algorithmic_bytes"] = ab.value / sec / 1e9
-                    c["tensor_pipe_tflops_issued"] = mf.value / sec / 1e12  # 3 MMAs per product in 3xTF32 mode
-                    c["tensor_pipe_frac_of_tf32_peak"] = c["tensor_pipe_tflops_issued"] / (tf_peak / 2.0)
-                else:
-                    c["algorithmic_gb_per_launch"] = ab.value / nl.value / 1e9
-                classes.append(c)
-            lib.fcuda_profile_tensor_gemm(0)
-            if classes:
-                classes.sort(key=lambda c: -c["share_of_step"])
-                roof = dict(classes[0])
-                roof["peak_source"] = (f"{how}: " + ("bf16_tflops_sustained" if roof["bound"] == "tensor" else
-                                                    "hbm_gbs") + " (kernel timed inside a long step)")
-                tr = ROOT / "profiles" / "r01_kernel_traffic.json"
-                roof["traffic"] = None
-                if tr.exists():
-                    try:
-                        roof["traffic"] = json.loads(tr.read_text()).get(args.model, {}).get(roof["kernel"].split()[0])
-                    except Exception:
-                        pass
-                roof["other_kernels"] = classes[1:]
+            try:
+                import ctypes
+                lib = booster.fcuda()
+                net._lib.fnet_set_cuda_graph(net._h, 0)
+                net.FeedInputDevice(dev_batches[0].data_ptr(), tuple(dev_batches[0].shape))
+                net.Forward(); net.Synchronize()
+                lib.fcuda_profile_tensor_gemm(1)
+                reps = 2
+                for i in range(reps):
+                    d = dev_batches[i % n_rot]
+                    net.FeedInputDevice(d.data_ptr(), tuple(d.shape))
+                    net.Forward()
+                net.Synchronize()
+                peaks, how = measured_peaks()
+                # kernels timed inside a long step -> the sustained figures; fallbacks = /opt/skills/guides/B200_PROFILING.md
+                tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+                hbm_peak = float(peaks.get("hbm_gbs", 6500.0))
+                names = ["tensor_gemm_ts_kernel (tcgen05 kind::tf32, Winograd/im2col/FC GEMM)",
+                         "conv_igemm_kernel (tcgen05 kind::tf32 implicit-GEMM conv)", "wino_input_kernel",
+                         "wino_output_kernel", "pooling_kernel", "depthwise kernels", "element-wise kernels"]
+                classes = []
+                for kind, name in enumerate(names):
+                    ms_t, af, mf, ab, nl = (ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double(),
+                                            ctypes.c_longlong())
+                    lib.fcuda_profile_collect_kind(kind, ctypes.byref(ms_t), ctypes.byref(af), ctypes.byref(mf),
+                                                   ctypes.byref(ab), ctypes.byref(nl))
+                    if nl.value == 0 or ms_t.value <= 0:
+                        continue
+                    sec = ms_t.value * 1e-3
+                    tensor = kind <= 1
+                    ach = af.value / sec / 1e12 if tensor else ab.value / sec / 1e9
+                    peak = tf_peak if tensor else hbm_peak
+                    c = {"kernel": name, "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
+                         "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak,
+                         "launches_per_step": nl.value / reps, "avg_launch_us": 1e3 * ms_t.value / nl.value,
+                         "share_of_step": (ms_t.value / reps) / (ms_dev / args.steps)}
+                    if tensor:
+                        c["algorithmic_gflop_per_launch"] = af.value / nl.value / 1e9
+                        c["algorithmic_gb_per_launch"] = ab.value / nl.value / 1e9
+                        c["hbm_gbps_at_algorithmic_bytes"] = ab.value / sec / 1e9
+                        c["tensor_pipe_tflops_issued"] = mf.value / sec / 1e12  # 3 MMAs per product in 3xTF32 mode
+                        c["tensor_pipe_frac_of_tf32_peak"] = c["tensor_pipe_tflops_issued"] / (tf_peak / 2.0)
+                    else:
+                        c["algorithmic_gb_per_launch"] = ab.value / nl.value / 1e9
+                    classes.append(c)
+                lib.fcuda_profile_tensor_gemm(0)
+                if classes:
+                    classes.sort(key=lambda c: -c["share_of_step"])
+                    roof = dict(classes[0])
+                    roof["peak_source"] = (f"{how}: " + ("bf16_tflops_sustained" if roof["bound"] == "tensor" else
+                                                        "hbm_gbs") + " (kernel timed inside a long step)")
+                    tr = ROOT / "profiles" / "r01_kernel_traffic.json"
+                    roof["traffic"] = None
+                    if tr.exists():
+                        try:
+                            roof["traffic"] = json.loads(tr.read_text()).get(args.model, {}).get(roof["kernel"].split()[0])
+                        except Exception:
+                            pass
+                    roof["other_kernels"] = classes[1:]
+            except Exception as e:  # the roofline leg explains the number, it must never cost the bench line
+                roof = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     total_images = world * B * args.steps
     value = total_images / (ms_dev * 1e-3)
