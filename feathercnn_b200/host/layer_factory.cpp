@@ -1,5 +1,6 @@
-// Built-in layer registrations — the same 13 ncnn type names as the reference
-// (/root/reference/src/layer_factory.cpp:53-68).
+// Built-in layer registrations: the 13 ncnn type names the reference serves (/root/reference/src/layer_factory.cpp:53-68)
+// mapped onto this host's layer classes.  A table of {type name, factory} pairs instead of one macro line per layer; the
+// DEFINE_LAYER_CREATOR / REGISTER_LAYER_CREATOR macros of <feather/layer_factory.h> remain the plugin API for user layers.
 #include <feather/layer_factory.h>
 
 #include "layers/batchnorm_layer.h"
@@ -14,33 +15,39 @@
 namespace feather {
 inline namespace b200 {  // ABI tag: keeps these symbols apart from the reference build when both are loaded
 
-DEFINE_LAYER_CREATOR(Input)
-DEFINE_LAYER_CREATOR(Conv)
-DEFINE_LAYER_CREATOR(Relu)
-DEFINE_LAYER_CREATOR(Pooling)
-DEFINE_LAYER_CREATOR(InnerProduct)
-DEFINE_LAYER_CREATOR(Dropout)
-DEFINE_LAYER_CREATOR(Softmax)
-DEFINE_LAYER_CREATOR(BatchNorm)
-DEFINE_LAYER_CREATOR(Scale)
-DEFINE_LAYER_CREATOR(Split)
-DEFINE_LAYER_CREATOR(Eltwise)
-DEFINE_LAYER_CREATOR(Concat)
+namespace {
+
+template <class L>
+Layer* make_layer(RuntimeParameter<float>* rt_param) {
+    return new L(rt_param);
+}
+
+struct BuiltIn {
+    const char* ncnn_type;
+    LayerRegistry::Creator create;
+};
+
+// "Convolution" and "ConvolutionDepthWise" share one class: group == channels selects the depthwise algorithm.
+const BuiltIn kBuiltIns[] = {
+    {"Input", make_layer<InputLayer>},
+    {"Convolution", make_layer<ConvLayer>},
+    {"ConvolutionDepthWise", make_layer<ConvLayer>},
+    {"InnerProduct", make_layer<InnerProductLayer>},
+    {"Pooling", make_layer<PoolingLayer>},
+    {"BatchNorm", make_layer<BatchNormLayer>},
+    {"Scale", make_layer<ScaleLayer>},
+    {"Eltwise", make_layer<EltwiseLayer>},
+    {"ReLU", make_layer<ReluLayer>},
+    {"Softmax", make_layer<SoftmaxLayer>},
+    {"Dropout", make_layer<DropoutLayer>},
+    {"Split", make_layer<SplitLayer>},
+    {"Concat", make_layer<ConcatLayer>},
+};
+
+}  // namespace
 
 void register_layer_creators() {
-    REGISTER_LAYER_CREATOR(Input, Input);
-    REGISTER_LAYER_CREATOR(Convolution, Conv);
-    REGISTER_LAYER_CREATOR(ConvolutionDepthWise, Conv);
-    REGISTER_LAYER_CREATOR(ReLU, Relu);
-    REGISTER_LAYER_CREATOR(Pooling, Pooling);
-    REGISTER_LAYER_CREATOR(InnerProduct, InnerProduct);
-    REGISTER_LAYER_CREATOR(Dropout, Dropout);
-    REGISTER_LAYER_CREATOR(Softmax, Softmax);
-    REGISTER_LAYER_CREATOR(BatchNorm, BatchNorm);
-    REGISTER_LAYER_CREATOR(Scale, Scale);
-    REGISTER_LAYER_CREATOR(Split, Split);
-    REGISTER_LAYER_CREATOR(Eltwise, Eltwise);
-    REGISTER_LAYER_CREATOR(Concat, Concat);
+    for (const BuiltIn& b : kBuiltIns) LayerRegistry::AddCreator(b.ncnn_type, b.create);
 }
 
 }  // inline namespace b200
