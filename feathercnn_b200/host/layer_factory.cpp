@@ -3,6 +3,8 @@
 // DEFINE_LAYER_CREATOR / REGISTER_LAYER_CREATOR macros of <feather/layer_factory.h> remain the plugin API for user layers.
 #include <feather/layer_factory.h>
 
+#include <stdio.h>
+
 #include "layers/batchnorm_layer.h"
 #include "layers/conv_layer.h"
 #include "layers/eltwise_layer.h"
@@ -45,6 +47,23 @@ const BuiltIn kBuiltIns[] = {
 };
 
 }  // namespace
+
+LayerRegistry::CreatorRegistry& LayerRegistry::Registry() {
+    static CreatorRegistry* table = new CreatorRegistry();  // never destroyed: layers may be created during exit
+    return *table;
+}
+
+void LayerRegistry::AddCreator(const std::string& type, Creator creator) { Registry()[type] = creator; }
+
+Layer* LayerRegistry::CreateLayer(std::string type, RuntimeParameter<float>* rt_param) {
+    const CreatorRegistry& table = Registry();
+    const CreatorRegistry::const_iterator hit = table.find(type);
+    if (hit == table.end()) {
+        fprintf(stderr, "Layer type %s is not supported in FeatherCNN...Aborting\n", type.c_str());
+        return NULL;
+    }
+    return hit->second(rt_param);
+}
 
 void register_layer_creators() {
     for (const BuiltIn& b : kBuiltIns) LayerRegistry::AddCreator(b.ncnn_type, b.create);

@@ -207,6 +207,48 @@ def test_residual_and_profile_entry_points_validate_arguments():
         assert (ms.value, af.value, ab.value, n.value) == (0.0, 0.0, 0.0, 0)
 
 
+PLUGIN_SRC = r"""
+// a user-defined layer written against the public headers only, as it would be against the reference's
+#include <feather/layer_factory.h>
+namespace feather {
+class NegateLayer : public Layer {
+public:
+    explicit NegateLayer(RuntimeParameter<float>* rt_param) : Layer(rt_param) {}
+    int LoadParam(const ncnn::ParamDict& pd) { factor = pd.get(0, -1.f); return 0; }
+    int Forward() { return 0; }
+    float factor = 0.f;
+};
+DEFINE_LAYER_CREATOR(Negate)
+REGISTER_LAYER_CREATOR(Negate, Negate)
+}  // namespace feather
+extern "C" int plugin_loaded() { return 1; }
+"""
+
+
+def test_user_layer_registers_through_the_plugin_macros(tmp_path):
+    """DEFINE_LAYER_CREATOR / REGISTER_LAYER_CREATOR (layer_factory.h:85-90): a layer compiled outside the library is
+    created by Net::LoadParam from its ncnn type name; unknown types are still refused with -200 (net.cpp:101-105)."""
+    import subprocess
+    from feathercnn_b200 import _lib
+    text = "7767517\n2 2\nInput data 0 1 data 0=4 1=4 2=2\nNegate neg 1 1 data neg 0=-2.5\n"
+    before = _net()
+    with pytest.raises(Exception) as e:
+        before.LoadParamFromText(text)
+    assert "-200" in str(e.value)
+    src = tmp_path / "plugin.cpp"
+    src.write_text(PLUGIN_SRC)
+    so = tmp_path / "libnegate_plugin.so"
+    libdir = ROOT / "feathercnn_b200" / "lib"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", f"-I{ROOT / 'include'}", "-I/usr/local/cuda/include",
+                    str(src), "-o", str(so), f"-L{libdir}", "-lfeather_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    _lib.feather()                      # the host library first: the plugin's static registrar calls into it
+    plugin = ctypes.CDLL(str(so), mode=ctypes.RTLD_GLOBAL)
+    assert plugin.plugin_loaded() == 1
+    net = _net()
+    net.LoadParamFromText(text)
+    assert sorted(net.BlobNames()) == ["data", "neg"]
+
+
 def _modelbin_cases():
     rng = np.random.default_rng(11)
     w = 37  # odd on purpose: fp16 and LUT payloads are padded to 4 bytes (modelbin.cpp alignSize)
