@@ -207,6 +207,46 @@ def test_residual_and_profile_entry_points_validate_arguments():
         assert (ms.value, af.value, ab.value, n.value) == (0.0, 0.0, 0.0, 0)
 
 
+def test_hot_kernels_are_tcgen05_and_tma_in_sass():
+    """B200_PROFILING.md: tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG.  The two product GEMM-class
+    kernels must contain them (and no legacy HMMA / mma.sync path); a kernel that silently fell back to CUDA cores or to
+    smem-staged operands would show here without a GPU."""
+    import collections
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    so = ROOT / "feathercnn_b200" / "lib" / "libfcuda.so"
+    sass = subprocess.run(["cuobjdump", "-sass", str(so)], capture_output=True, text=True, check=True).stdout
+    ops: dict[str, collections.Counter] = collections.defaultdict(collections.Counter)
+    cur = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+        if m and cur:
+            ops[cur][m.group(1)] += 1
+    assert "arch = sm_100a" in sass or "sm_100a" in sass
+
+    def only(pattern):
+        hit = [k for k in ops if re.search(pattern, k)]
+        assert hit, pattern
+        return hit
+
+    for k in only(r"conv_igemm_kernelILi(32|64|128)ELi2E"):     # 3xTF32 implicit-GEMM conv
+        c = ops[k]
+        assert c["UTCHMMA"] == 12 and c["STTM"] >= 4 and c["LDTM"] >= 1 and c["UTMALDG"] >= 2 and c["UTCBAR"] >= 2, (k, dict(c))
+        assert c["HMMA"] == 0 and c["FFMA"] == 0, k              # no tensor-core-less inner product hiding in there
+    for k in only(r"tensor_gemm_ts_kernelILi(32|64|128)E"):      # TensorGEMM, A split on chip into tensor memory
+        c = ops[k]
+        assert c["UTCHMMA"] == 12 and c["STTM"] >= 4 and c["LDTM"] >= 1 and c["UTMALDG"] >= 3, (k, dict(c))
+        assert c["HMMA"] == 0
+    for k in only(r"wino_(in|out)put_kernelILi8E"):              # transforms stay on CUDA cores, as designed
+        assert ops[k]["UTCHMMA"] == 0 and ops[k]["FFMA"] + ops[k]["FADD"] > 100
+
+
 PLUGIN_SRC = r"""
 // a user-defined layer written against the public headers only, as it would be against the reference's
 #include <feather/layer_factory.h>
