@@ -332,6 +332,28 @@ def test_weight_blob_decoder_rejects_int8_like_the_layer_does():
     assert feather().fnet_modelbin_load_mem(blob, 8, 7, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))) == -1  # unknown type
 
 
+def test_bench_reference_arm_prints_the_contract_line(oracle):
+    """`bench.py --impl reference` (the arm the driver runs next to ours) on BASELINE.json configs[0]: CPU only, same
+    metric / unit / config keys, rank != 0 exits silently."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if not oracle.reference_available():
+        pytest.skip("oracle/_ref not built")
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--model", "single_conv", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "images/sec" and line["unit"] == "images/s"
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["value"] > 0
+    assert line["config"]["workload"].startswith("single_conv_b64") and line["cpu_baseline"]["kind"] == "reference"
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=60, cwd=ROOT, env=env)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
 def test_feathermodel_container_round_trip(tmp_path):
     from feathercnn_b200.tools import feathermodel, modelgen
     param, binf = modelgen.single_conv(ic=4, oc=4, h=9, w=9).save(tmp_path / "m")
