@@ -332,6 +332,35 @@ def test_weight_blob_decoder_rejects_int8_like_the_layer_does():
     assert feather().fnet_modelbin_load_mem(blob, 8, 7, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))) == -1  # unknown type
 
 
+def test_clock_sampler_uses_only_rows_inside_the_timed_windows(tmp_path, monkeypatch):
+    """bench.py's `clocks` object: nvidia-smi is polled from before the warm-up, only rows received inside the marked
+    timed regions count, and throttle reasons are collected from them."""
+    import importlib.util
+    import os
+    import stat
+    import time
+    fake = tmp_path / "nvidia-smi"
+    # index, clocks.sm, clocks.max.sm, power, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap — one row every 20 ms;
+    # the first 10 rows (idle clocks) fall before the timed window
+    fake.write_text("#!/bin/bash\ni=0\nwhile true; do\n  if [ $i -lt 10 ]; then echo '0, 345, 1965, 140.0, Not Active, Not Active, Not Active, Not Active';\n"
+                    "  else echo '0, 1755, 1965, 990.0, Not Active, Not Active, Not Active, Active'; fi\n  i=$((i+1)); sleep 0.02\ndone\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", f"{tmp_path}{os.pathsep}{os.environ['PATH']}")
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.45)   # "warm-up": idle rows arrive, outside any window
+    s.begin()
+    time.sleep(0.3)
+    s.end()
+    out = s.stop()
+    assert out["samples"] >= 5 and out["sampled"] == "inside the timed regions"
+    assert out["sm_mhz"] == 1755.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    assert 0.25 <= out["window_s"] <= 0.6
+
+
 def test_bench_reference_arm_prints_the_contract_line(oracle):
     """`bench.py --impl reference` (the arm the driver runs next to ours) on BASELINE.json configs[0]: CPU only, same
     metric / unit / config keys, rank != 0 exits silently."""
