@@ -332,6 +332,38 @@ def test_weight_blob_decoder_rejects_int8_like_the_layer_does():
     assert feather().fnet_modelbin_load_mem(blob, 8, 7, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))) == -1  # unknown type
 
 
+def test_launch_list_summary_and_traffic_json(tmp_path):
+    """scripts/summarize_launches.py: shares of one Forward (between the last two softmax launches) and the per-kernel DRAM
+    bytes that bench.py reports as roofline.traffic."""
+    import json
+    import subprocess
+    import sys
+    hdr = '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"'
+    rows = [hdr]
+
+    def launch(i, name, us, rd_mb, wr_mb):
+        base = f'"{i}","1","python","box","{name}","1","7","(128, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics"'
+        rows.append(f'{base},"dram__bytes_read.sum","Mbyte","{rd_mb}"')
+        rows.append(f'{base},"dram__bytes_write.sum","Mbyte","{wr_mb}"')
+        rows.append(f'{base},"gpu__time_duration.sum","us","{us}"')
+
+    i = 0
+    for step in range(2):
+        launch(i, "void unnamed>::conv_igemm_kernel<64, 2>(CUtensorMap_st, CUtensorMap_st, unnamed>::IgemmArgs)", 300, 50, 750); i += 1
+        launch(i, "void unnamed>::conv_igemm_kernel<64, 2>(CUtensorMap_st, CUtensorMap_st, unnamed>::IgemmArgs)", 900, 800, 800); i += 1
+        launch(i, "void tensor_gemm_ts_kernel<128, 1>(CUtensorMap_st, CUtensorMap_st, CUtensorMap_st, GemmKernelArgs)", 200, 400, 0); i += 1
+        launch(i, "softmax_kernel(const float *, float *, unsigned long)", 5, 0.1, 0.1); i += 1
+    csv_path = tmp_path / "launches.csv"
+    csv_path.write_text("==PROF== Connected\n" + "\n".join(rows) + "\n")
+    out_json = tmp_path / "traffic.json"
+    r = subprocess.run([sys.executable, str(ROOT / "scripts" / "summarize_launches.py"), str(csv_path), str(out_json)],
+                       capture_output=True, text=True, check=True)
+    assert "one Forward (between the last two softmax launches): 4 launches" in r.stdout
+    assert "conv_igemm_kernel" in r.stdout and "85." in r.stdout        # 1200 of 1405 us
+    t = json.loads(out_json.read_text())
+    assert t["conv_igemm_kernel"] == pytest.approx(1.2e9) and t["tensor_gemm_ts_kernel"] == pytest.approx(4e8)
+
+
 def test_clock_sampler_uses_only_rows_inside_the_timed_windows(tmp_path, monkeypatch):
     """bench.py's `clocks` object: nvidia-smi is polled from before the warm-up, only rows received inside the marked
     timed regions count, and throttle reasons are collected from them."""
