@@ -64,6 +64,8 @@ def fcuda() -> ctypes.CDLL:
             "fcuda_conv_init": (i, [P, i, vp, vp, vp]),
             "fcuda_conv_forward": (i, [P, i, vp, vp, vp, vp, vp, i, vp]),
             "fcuda_conv_forward_residual": (i, [P, i, vp, vp, vp, vp, vp, vp, i, i, vp]),
+            "fcuda_conv_forward_ext": (i, [P, i, vp, vp, vp, vp, vp, vp, i, i, i, i, vp]),
+            "fcuda_eltwise_forward": (i, [vp, vp, vp, sz, i, ctypes.c_float, ctypes.c_float, i, vp]),
             "fcuda_tensor_gemm": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
             "fcuda_split_tf32": (i, [vp, vp, vp, sz, vp]),
             "fcuda_inner_product_get_buffer_size": (i, [i, i, i, szp, szp]),
@@ -117,6 +119,8 @@ def feather() -> ctypes.CDLL:
             "fnet_feed_input_device": (i, [vp, cp, vp, i, i, i, i]),
             "fnet_forward": (i, [vp]),
             "fnet_forward_batch": (i, [vp, vp, i]),
+            "fnet_submit_batch": (i, [vp, vp, i, cp, vp]),
+            "fnet_wait_batch": (i, [vp, i]),
             "fnet_synchronize": (i, [vp]),
             "fnet_blob_shape": (i, [vp, cp, ip, ip, ip, ip]),
             "fnet_extract_blob": (i, [vp, cp, vp]),

@@ -89,6 +89,12 @@ class ConvBooster:
         self.algo = a.value
         return rc
 
+    def SelectAlgoTuned(self, param: ConvParam) -> int:
+        a = ctypes.c_int(-1)
+        rc = fcuda().fcuda_conv_select_algo_tuned(ctypes.byref(param), ctypes.byref(a))
+        self.algo = a.value
+        return rc
+
     def ForceSelectAlgo(self, algo: int) -> int:
         self.algo = int(algo)
         return 0
@@ -119,12 +125,13 @@ class ConvBooster:
 
 def conv_forward(param: ConvParam, x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None = None,
                  algo: int | None = None, residual: torch.Tensor | None = None,
-                 relu_after_add: bool = False) -> tuple[torch.Tensor, int]:
+                 relu_after_add: bool = False, dilation: int = 1, tuned: bool = False) -> tuple[torch.Tensor, int]:
     """Whole ConvBooster protocol for a batch x (N, IC, H, W) -> (N, OC, OH, OW).  Returns (output, algo).
-    With `residual` (shaped like the output) the fused Eltwise-SUM entry point is used instead of Forward."""
+    With `residual` (shaped like the output) the fused Eltwise-SUM entry point is used instead of Forward.
+    `dilation` > 1 goes through fcuda_conv_forward_ext (the caller sets param.output_h/w for the dilated extent)."""
     cb = ConvBooster()
     if algo is None:
-        rc = cb.SelectAlgo(param)
+        rc = cb.SelectAlgoTuned(param) if tuned else cb.SelectAlgo(param)
         if rc != 0:
             raise FcudaError("fcuda_conv_select_algo", rc)
     else:
@@ -135,7 +142,12 @@ def conv_forward(param: ConvParam, x: torch.Tensor, w: torch.Tensor, b: torch.Te
     scratch = torch.empty(max(scratch_n, 1), device=x.device, dtype=torch.float32)
     cb.Init(param, packed, w.contiguous())
     out = torch.empty((n, param.output_channels, param.output_h, param.output_w), device=x.device, dtype=torch.float32)
-    if residual is None:
+    if dilation > 1:
+        _check("fcuda_conv_forward_ext",
+               fcuda().fcuda_conv_forward_ext(ctypes.byref(param), cb.algo, _ptr(out), _ptr(x.contiguous()), _ptr(packed),
+                                              _ptr(scratch), _ptr(b), _ptr(residual.contiguous()) if residual is not None else None,
+                                              int(relu_after_add), dilation, dilation, n, _stream()))
+    elif residual is None:
         cb.Forward(param, out, x.contiguous(), packed, scratch, b, n)
     else:
         cb.ForwardResidual(param, out, x.contiguous(), packed, scratch, b, residual.contiguous(), relu_after_add, n)
@@ -158,6 +170,15 @@ def inner_product(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, relu
     _check("fcuda_inner_product_forward",
            lib.fcuda_inner_product_forward(in_size, out_size, _ptr(out), _ptr(x.contiguous()), _ptr(packed), _ptr(b),
                                            _ptr(scratch), int(relu), n, _stream()))
+    return out
+
+
+def eltwise(a: torch.Tensor, b: torch.Tensor, op: int, ca: float = 1.0, cb: float = 1.0, relu: bool = False) -> torch.Tensor:
+    """op 0 PROD, 1 SUM (with coefficients), 2 MAX — ncnn Eltwise semantics (the reference only has plain SUM)."""
+    out = torch.empty_like(a)
+    _check("fcuda_eltwise_forward",
+           fcuda().fcuda_eltwise_forward(_ptr(out), _ptr(a.contiguous()), _ptr(b.contiguous()), a.numel(), op, ca, cb,
+                                         int(relu), _stream()))
     return out
 
 

@@ -32,8 +32,27 @@ void count_launch(int n = 1);
 unsigned long long launch_count();
 void reset_launch_count();
 
-// Number of SMs of the current device (148 on B200); cached per process.
+// Number of SMs of the current device (148 on B200); cached per device.
 int sm_count();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): a process that drives several GPUs must opt
+// in on each of them.  One cache object per call site (= per kernel instantiation), indexed by device ordinal.
+constexpr int kMaxDevices = 64;
+struct SmemAttrCache { int bytes[kMaxDevices] = {}; };
+static inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+template <class Kernel>
+static inline int ensure_dynamic_smem(Kernel kern, int bytes, SmemAttrCache& cache) {
+    const int dev = current_device();
+    if (bytes > cache.bytes[dev]) {
+        FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        cache.bytes[dev] = bytes;
+    }
+    return 0;
+}
 
 // Split an fp32 value into a TF32-representable "hi" (round-to-nearest on the 13 dropped
 // mantissa bits) and the exact fp32 remainder "lo".  hi + lo == v exactly; the tensor

@@ -91,6 +91,8 @@ struct IgemmArgs {
     const float* bias;
     int N, IC, H, W, OC, OH, OW;
     int KH, KW, pad_top, pad_left, stride_h, stride_w;
+    int dil_h, dil_w;        // tap spacing (1 = dense)
+    int in_img_c, out_img_c; // channels per image of the tensors `in` / `out` point into (>= IC / OC: channel slices)
     int K;                   // KH*KW*IC
     int kblocks;             // ceil(K / 32)
     int use_table;           // 0 => IC % 32 == 0: every k-block is 32 channels of ONE tap, offsets are arithmetic
@@ -202,7 +204,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             if (k < args.K) {
                 const int tap = k / args.IC, ic = k - tap * args.IC;
                 const int u = tap / args.KW, v = tap - u * args.KW;
-                e = make_int2(ic * plane + u * args.W + v, tap);
+                e = make_int2(ic * plane + u * args.dil_h * args.W + v * args.dil_w, tap);
             }
             ktab[k] = e;
         }
@@ -343,11 +345,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             if (pix_ok) {  // row mask x column mask instead of KH*KW tests
                 unsigned long long cols = 0;
                 for (int v = 0; v < args.KW; ++v)
-                    if (static_cast<unsigned>(ix0 + v) < static_cast<unsigned>(args.W)) cols |= 1ull << v;
+                    if (static_cast<unsigned>(ix0 + v * args.dil_w) < static_cast<unsigned>(args.W)) cols |= 1ull << v;
                 for (int u = 0; u < args.KH; ++u)
-                    if (static_cast<unsigned>(iy0 + u) < static_cast<unsigned>(args.H)) tapmask |= cols << (u * args.KW);
+                    if (static_cast<unsigned>(iy0 + u * args.dil_h) < static_cast<unsigned>(args.H)) tapmask |= cols << (u * args.KW);
             }
-            base = args.in + (static_cast<long long>(bx.valid ? bx.n : 0) * args.IC) * plane +
+            base = args.in + (static_cast<long long>(bx.valid ? bx.n : 0) * args.in_img_c) * plane +
                    static_cast<long long>(iy0) * args.W + ix0;
             asm volatile("" : "+l"(base));  // opaque: see gather()
             tap = 0; tu = 0; tv = 0; cb = kb;
@@ -375,7 +377,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     if (++tv == args.KW) { tv = 0; ++tu; }
                 }
                 const char* kp = reinterpret_cast<const char*>(base) +
-                                 (static_cast<long long>(cb * 32) * plane + tu * args.W + tv) * 4;
+                                 (static_cast<long long>(cb * 32) * plane + tu * args.dil_h * args.W + tv * args.dil_w) * 4;
                 asm volatile("" : "+l"(kp));
                 const bool kb_ok = ((tapmask >> tap) & 1ull) != 0;
                 if (__all_sync(0xffffffffu, kb_ok)) {  // interior: no predication, no zero fill
@@ -462,7 +464,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 // The fused Eltwise addend comes from HBM; a load issued after the accumulator is ready would put its
                 // ~1k-cycle latency on every 32-column chunk (measured: ResNet-50 8.3 -> 12.0 ms per step).  Each lane
                 // prefetches whole 128-byte channel rows of this warp's box while the MMAs of the tile are still running.
-                const char* rbase = reinterpret_cast<const char*>(args.residual + (static_cast<size_t>(bx.n) * args.OC) * oplane +
+                const char* rbase = reinterpret_cast<const char*>(args.residual + (static_cast<size_t>(bx.n) * args.out_img_c) * oplane +
                                                                  static_cast<size_t>(bx.oy) * args.OW + bx.ox0);
                 for (int c = lane; c < BN; c += 32) {
                     const int oc = n_blk * BN + c;
@@ -479,7 +481,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 if (oc0 >= args.OC) break;
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(taddr0 + c0, r);
-                char* dst = reinterpret_cast<char*>(args.out + (static_cast<size_t>(ok ? bx.n : 0) * args.OC + oc0) * oplane +
+                char* dst = reinterpret_cast<char*>(args.out + (static_cast<size_t>(ok ? bx.n : 0) * args.out_img_c + oc0) * oplane +
                                                     static_cast<size_t>(bx.oy) * args.OW + ox);
                 asm volatile("" : "+l"(dst));  // one IMAD.WIDE per store off an opaque base
                 // fused Eltwise SUM: the other addend sits at the same NCHW position
@@ -593,6 +595,9 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     a.N = p.N; a.IC = p.IC; a.H = p.H; a.W = p.W; a.OC = p.OC; a.OH = p.OH; a.OW = p.OW;
     a.KH = p.KH; a.KW = p.KW; a.pad_top = p.pad_top; a.pad_left = p.pad_left;
     a.stride_h = p.stride_h; a.stride_w = p.stride_w;
+    a.dil_h = p.dil_h > 1 ? p.dil_h : 1; a.dil_w = p.dil_w > 1 ? p.dil_w : 1;
+    a.in_img_c = p.in_c_total > 0 ? p.in_c_total : p.IC;
+    a.out_img_c = p.out_c_total > 0 ? p.out_c_total : p.OC;
     a.K = K;
     a.kblocks = ceil_div(K, 32);
     a.use_table = (p.IC % 32 == 0) ? 0 : 1;
@@ -618,11 +623,8 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     const int smem = kStagesIg * kStage + table_bytes + a.oc_pad * 4 + 1024;
     if (smem > 227 * 1024 - 2048) return -1;
     auto kern = conv_igemm_kernel<BN, PLANES>;
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
-        FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
+    static SmemAttrCache attr_cache;
+    if (int rc = ensure_dynamic_smem(kern, smem, attr_cache)) return rc;
     // algorithmic work of the layer: direct-convolution FLOPs; input + filters read once, output written once
     const double macs = static_cast<double>(p.N) * p.OC * p.OH * p.OW * p.IC * taps;
     const double mma = 2.0 * static_cast<double>(a.pixel_tiles) * 128 * (a.num_n * BN) * (a.kblocks * 32) * (PLANES == 2 ? 3 : 1);

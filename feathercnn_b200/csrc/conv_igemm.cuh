@@ -15,6 +15,10 @@ struct IgemmProblem {
     int planes;           // 1 = TF32, 2 = 3xTF32
     int relu;
     const float* residual;  // optional (N, OC, OH, OW) tensor added before the activation (fused Eltwise SUM), or null
+    // Extensions beyond the reference (it rejects both: conv_layer.h:43-47, avx/booster.cpp:304-308); 0 = default.
+    int dil_h, dil_w;       // dilation (0 or 1 = dense taps)
+    int in_c_total;         // channels per image of the INPUT tensor when `input` addresses a channel slice of it
+    int out_c_total;        // same for output / residual (grouped convolution = one launch per group on slices)
 };
 
 // KH*KW <= 63 and, unless IC % 32 == 0, KH*KW*IC <= 8192 (shared-memory k-table).

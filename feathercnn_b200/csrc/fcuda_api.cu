@@ -134,15 +134,19 @@ int make_plan(const FcudaConvParam* p, int algo, int batch, ConvPlan* plan) {
             return 0;
         }
         case FCUDA_SGECONV: {
-            // implicit GEMM straight from NCHW: any kernel / stride / padding, group 1
-            if (p->group != 1 || !conv_igemm_supported(IC, p->kernel_h, p->kernel_w)) return -1;
+            // implicit GEMM straight from NCHW: any kernel / stride / padding / dilation; group > 1 (an extension: the
+            // reference returns -1 for partial groups, avx/booster.cpp:304-308) runs one launch per group on channel
+            // slices, with input_channels / output_channels the TOTAL channel counts and weights (OC, IC/group, KH, KW)
+            const int G = p->group > 0 ? p->group : 1;
+            if (IC % G != 0 || OC % G != 0) return -1;
+            if (!conv_igemm_supported(IC / G, p->kernel_h, p->kernel_w)) return -1;
             pl.pg = pack_geom(p);
             pl.scratch_floats = 0;
-            pl.packed_floats = conv_igemm_packed_floats(OC, IC, p->kernel_h * p->kernel_w, pl.np);
+            pl.packed_floats = static_cast<size_t>(G) * conv_igemm_packed_floats(OC / G, IC / G, p->kernel_h * p->kernel_w, pl.np);
             return 0;
         }
         case FCUDA_DEPTHWISE: {
-            if (p->group != IC || OC != IC) return -1;
+            if (p->group != IC || OC != IC) return -1;  // channel multiplier > 1: use FCUDA_SGECONV (grouped)
             DwGeom& g = pl.dg;
             g.C = IC; g.H = p->input_h; g.W = p->input_w; g.KH = p->kernel_h; g.KW = p->kernel_w;
             g.OH = p->output_h; g.OW = p->output_w; g.stride_h = p->stride_h; g.stride_w = p->stride_w;
@@ -216,9 +220,29 @@ int fcuda_conv_select_algo(const FcudaConvParam* p, int* algo) {
 }
 
 int fcuda_conv_select_algo_tuned(const FcudaConvParam* p, int* algo) {
-    int rc = fcuda_conv_select_algo(p, algo);
-    if (rc != 0 || *algo == FCUDA_DEPTHWISE) return rc;
+    if (!p || !algo) return -100;
     const int IC = p->input_channels, OC = p->output_channels;
+    if (p->group > 1) {
+        // true depthwise (one filter per channel) -> the stencil kernels; partial groups and channel-multiplier
+        // depthwise (rejected by the reference, avx/booster.cpp:304-308) -> grouped implicit GEMM
+        if (p->group == IC && OC == IC) { *algo = FCUDA_DEPTHWISE; return 0; }
+        if (IC % p->group == 0 && OC % p->group == 0 && conv_igemm_supported(IC / p->group, p->kernel_h, p->kernel_w)) {
+            *algo = FCUDA_SGECONV;
+            return 0;
+        }
+        *algo = -1;
+        return -1;
+    }
+    int rc;
+    if (IC == 1) {
+        // group == 1 with ONE input channel (grayscale / LeNet conv1) is an ordinary convolution; the reference's
+        // `group == input_channels` test would turn it into a 1-output depthwise (avx/booster.cpp:285)
+        *algo = FCUDA_IM2COL;
+        rc = 0;
+    } else {
+        rc = fcuda_conv_select_algo(p, algo);
+    }
+    if (rc != 0 || *algo == FCUDA_DEPTHWISE) return rc;
     if (*algo == FCUDA_WINOGRADF63) {
         // non-fused Winograd moves 64/36 x (2*in + out) through HBM; below ~128 channels on large images that traffic
         // outweighs its 4.5x MMA saving and the single-kernel implicit GEMM wins
@@ -249,7 +273,8 @@ int fcuda_conv_init(const FcudaConvParam* p, int algo, float* packed, const floa
     cudaStream_t s = as_stream(stream);
     const int IC = p->input_channels, OC = p->output_channels;
     const size_t raw_n = algo == FCUDA_DEPTHWISE ? static_cast<size_t>(IC) * p->kernel_h * p->kernel_w
-                                                 : static_cast<size_t>(OC) * IC * p->kernel_h * p->kernel_w;
+                                                 : static_cast<size_t>(OC) * (IC / (p->group > 0 ? p->group : 1)) *
+                                                       p->kernel_h * p->kernel_w;
     const float* d_raw;
     float* tmp;
     if ((rc = stage_to_device(raw, raw_n, &d_raw, &tmp, s))) return rc;
@@ -267,8 +292,14 @@ int fcuda_conv_init(const FcudaConvParam* p, int algo, float* packed, const floa
         }
         case FCUDA_SGECONV: {
             const int taps = p->kernel_h * p->kernel_w;
-            const size_t plane = conv_igemm_packed_floats(OC, IC, taps, 1);
-            rc = conv_igemm_pack_weights(d_raw, packed, pl.np == 2 ? packed + plane : nullptr, OC, IC, taps, s);
+            const int G = p->group > 0 ? p->group : 1;
+            const int ICg = IC / G, OCg = OC / G;
+            const size_t plane = conv_igemm_packed_floats(OCg, ICg, taps, 1);
+            for (int g = 0; g < G && rc == 0; ++g) {  // per group: [hi plane][lo plane] of Wp[OCg][Kf]
+                float* dst = packed + static_cast<size_t>(g) * pl.np * plane;
+                rc = conv_igemm_pack_weights(d_raw + static_cast<size_t>(g) * OCg * ICg * taps, dst,
+                                             pl.np == 2 ? dst + plane : nullptr, OCg, ICg, taps, s);
+            }
             break;
         }
         case FCUDA_NAIVE:
@@ -288,7 +319,20 @@ int fcuda_conv_init(const FcudaConvParam* p, int algo, float* packed, const floa
 
 static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
                              float* scratch, const float* bias, const float* residual, int relu_after_add, int batch,
-                             void* stream);
+                             void* stream, int dil_h = 1, int dil_w = 1);
+
+int fcuda_conv_forward_ext(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
+                           float* scratch, const float* bias, const float* residual, int relu_after_add, int dilation_h,
+                           int dilation_w, int batch, void* stream) {
+    if (!p || dilation_h < 1 || dilation_w < 1) return -100;
+    if ((dilation_h > 1 || dilation_w > 1) && algo != FCUDA_SGECONV) return -200;  // only the implicit GEMM spaces its taps
+    if (residual && !(algo == FCUDA_SGECONV && p->activation == FCUDA_ACT_NONE)) {
+        if (dilation_h > 1 || dilation_w > 1) return -200;
+        return fcuda_conv_forward_residual(p, algo, output, input, packed, scratch, bias, residual, relu_after_add, batch, stream);
+    }
+    return conv_forward_impl(p, algo, output, input, packed, scratch, bias, residual, relu_after_add, batch, stream,
+                             dilation_h, dilation_w);
+}
 
 int fcuda_conv_forward(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
                        float* scratch, const float* bias, int batch, void* stream) {
@@ -310,7 +354,7 @@ int fcuda_conv_forward_residual(const FcudaConvParam* p, int algo, float* output
 
 static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
                              float* scratch, const float* bias, const float* residual, int relu_after_add, int batch,
-                             void* stream) {
+                             void* stream, int dil_h, int dil_w) {
     ConvPlan pl;
     int rc = make_plan(p, algo, batch, &pl);
     if (rc) return rc;
@@ -366,22 +410,35 @@ static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, c
         }
         case FCUDA_SGECONV: {
             const int taps = p->kernel_h * p->kernel_w;
-            IgemmProblem g{};
-            g.input = input; g.w_hi = packed;
-            g.w_lo = pl.np == 2 ? packed + conv_igemm_packed_floats(OC, IC, taps, 1) : nullptr;
-            g.bias = b; g.output = output;
-            g.N = batch; g.IC = IC; g.OC = OC;
-            g.KH = p->kernel_h; g.KW = p->kernel_w; g.pad_top = p->pad_top; g.pad_left = p->pad_left;
-            g.stride_h = p->stride_h; g.stride_w = p->stride_w;
-            if (taps == 1 && p->pad_top == 0 && p->pad_left == 0 && p->stride_h == 1 && p->stride_w == 1) {
-                // pointwise stride 1: address each image as one H*W-long row (fuller 32-pixel boxes)
-                g.H = 1; g.W = p->input_h * p->input_w; g.OH = 1; g.OW = p->output_h * p->output_w;
-            } else {
-                g.H = p->input_h; g.W = p->input_w; g.OH = p->output_h; g.OW = p->output_w;
+            const int G = p->group > 0 ? p->group : 1;
+            const int ICg = IC / G, OCg = OC / G;
+            const size_t wplane = conv_igemm_packed_floats(OCg, ICg, taps, 1);
+            const size_t in_plane = static_cast<size_t>(p->input_h) * p->input_w;
+            const size_t out_plane = static_cast<size_t>(p->output_h) * p->output_w;
+            for (int gi = 0; gi < G; ++gi) {  // one launch per group on channel slices (G == 1: the whole tensor)
+                IgemmProblem g{};
+                const float* wg = packed + static_cast<size_t>(gi) * pl.np * wplane;
+                g.input = input + static_cast<size_t>(gi) * ICg * in_plane;
+                g.w_hi = wg;
+                g.w_lo = pl.np == 2 ? wg + wplane : nullptr;
+                g.bias = b ? b + static_cast<size_t>(gi) * OCg : nullptr;
+                g.output = output + static_cast<size_t>(gi) * OCg * out_plane;
+                g.residual = residual ? residual + static_cast<size_t>(gi) * OCg * out_plane : nullptr;
+                g.N = batch; g.IC = ICg; g.OC = OCg;
+                g.in_c_total = IC; g.out_c_total = OC;
+                g.KH = p->kernel_h; g.KW = p->kernel_w; g.pad_top = p->pad_top; g.pad_left = p->pad_left;
+                g.stride_h = p->stride_h; g.stride_w = p->stride_w;
+                g.dil_h = dil_h; g.dil_w = dil_w;
+                if (taps == 1 && p->pad_top == 0 && p->pad_left == 0 && p->stride_h == 1 && p->stride_w == 1) {
+                    // pointwise stride 1: address each image as one H*W-long row (fuller 32-pixel boxes)
+                    g.H = 1; g.W = p->input_h * p->input_w; g.OH = 1; g.OW = p->output_h * p->output_w;
+                } else {
+                    g.H = p->input_h; g.W = p->input_w; g.OH = p->output_h; g.OW = p->output_w;
+                }
+                g.planes = pl.np; g.relu = residual ? relu_after_add : relu;
+                if ((rc = conv_igemm_forward(g, s))) return rc;
             }
-            g.planes = pl.np; g.relu = residual ? relu_after_add : relu;
-            g.residual = residual;
-            return conv_igemm_forward(g, s);
+            return 0;
         }
         case FCUDA_NAIVE:
             return conv_direct(input, packed, b, output, pl.pg, OC, relu, batch, s);
@@ -411,13 +468,28 @@ int fcuda_split_tf32(float* hi, float* lo, const float* x, size_t n, void* strea
 // ---------------------------------------------------------------------------------------------
 static bool fc_tensor_path(int input_size) { return input_size % 4 == 0; }
 
+// weight streaming is HBM-bound: split K until there are ~2 CTAs per SM; every split owns >= 8 k-blocks
+static int fc_split(int input_size, int output_size, int batch) {
+    if (!fc_tensor_path(input_size)) return 1;
+    const int num_m = ceil_div(output_size, 128) * ceil_div(batch, 128);
+    int split = ceil_div(2 * sm_count(), num_m);
+    const int kb = ceil_div(input_size, 32);
+    if (split > kb / 8) split = kb / 8;
+    if (split > 64) split = 64;
+    if (split < 1) split = 1;
+    return tensor_gemm_effective_split(input_size, split);
+}
+
 int fcuda_inner_product_get_buffer_size(int input_size, int output_size, int batch, size_t* scratch_floats,
                                         size_t* packed_kernel_floats) {
     if (input_size <= 0 || output_size <= 0 || batch < 1) return -100;
     const int np = fc_tensor_path(input_size) ? planes() : 1;
-    // W (the streamed operand) is kept once as plain fp32; only the small activation matrix gets hi/lo planes
+    // W (the streamed operand) is kept once as plain fp32; only the small activation matrix gets hi/lo planes.
+    // scratch = [X_hi | X_lo] (3xTF32 mode) + one partial-sum plane (batch x out) per k-split
     if (packed_kernel_floats) *packed_kernel_floats = static_cast<size_t>(output_size) * input_size;
-    if (scratch_floats) *scratch_floats = np == 2 ? 2 * static_cast<size_t>(batch) * input_size : 0;
+    if (scratch_floats)
+        *scratch_floats = (np == 2 ? 2 * static_cast<size_t>(batch) * input_size : 0) +
+                          static_cast<size_t>(fc_split(input_size, output_size, batch)) * batch * output_size;
     return 0;
 }
 
@@ -440,14 +512,13 @@ int fcuda_inner_product_init(int input_size, int output_size, float* packed, con
 int fcuda_inner_product_forward(int input_size, int output_size, float* output, const float* input,
                                 const float* packed, const float* bias, float* scratch, int relu, int batch,
                                 void* stream) {
-    if (input_size <= 0 || output_size <= 0 || batch < 1 || !output || !input || !packed) return -100;
+    if (input_size <= 0 || output_size <= 0 || batch < 1 || !output || !input || !packed || !scratch) return -100;
     cudaStream_t s = as_stream(stream);
     const bool tc = fc_tensor_path(input_size);
     const int np = tc ? planes() : 1;
-    if (np == 2 && !scratch) return -100;
     const size_t xn = static_cast<size_t>(batch) * input_size;
-    int rc = fill_rows(output, bias, output_size, batch, s);  // out[b][o] = bias[o]; the GEMM accumulates on top
-    if (rc) return rc;
+    float* part = scratch + (np == 2 ? 2 * xn : 0);  // [split][batch][out]
+    int rc;
     GemmProblem g{};
     g.A = packed;  // A = W (out x in), plain fp32: output features on the 128-row M side
     g.B_hi = input; g.B_lo = nullptr;                           // B = X (batch x in)
@@ -455,23 +526,17 @@ int fcuda_inner_product_forward(int input_size, int output_size, float* output, 
         if ((rc = split_tf32_planes(input, scratch, scratch + xn, xn, s))) return rc;
         g.B_hi = scratch; g.B_lo = scratch + xn;
     }
-    g.D = output;
+    g.D = part;
     g.M = output_size; g.N = batch; g.K = input_size; g.G = 1;
-    g.planes = np; g.epilogue = EPI_COLMAJOR_ATOMIC; g.ldd = output_size;
-    // weight streaming is HBM-bound: split K until there are ~2 CTAs per SM
-    const int num_m = ceil_div(output_size, 128) * ceil_div(batch, 128);
-    int split = ceil_div(2 * sm_count(), num_m);
-    const int kb = ceil_div(input_size, 32);
-    if (split > kb / 8) split = kb / 8;
-    if (split > 64) split = 64;
-    if (split < 1) split = 1;
-    g.split_k = split;
+    g.planes = np; g.epilogue = EPI_COLMAJOR_PARTIAL; g.ldd = output_size;
+    g.split_stride = static_cast<long long>(batch) * output_size;
+    g.split_k = fc_split(input_size, output_size, batch);
     g.algo_flops = 2.0 * output_size * static_cast<double>(input_size) * batch;
     if (tc && tensor_gemm_supported(g)) rc = tensor_gemm(g, s);
     else { g.split_k = 1; rc = simt_gemm(g, s); count_launch(); }
     if (rc) return rc;
-    if (relu) rc = scale_relu(output, output, static_cast<size_t>(batch) * output_size, 1.f, 1, s);
-    return rc;
+    // fixed-order sum of the k-split planes + bias + ReLU: deterministic (sgemv.cpp:334-395 is a plain ordered dot product)
+    return fc_reduce(output, part, bias, g.split_k, output_size, batch, relu, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -517,6 +582,14 @@ int fcuda_scale_forward(float* output, const float* input, int channels, size_t 
 int fcuda_eltwise_add_forward(float* output, const float* a, const float* b, size_t n, int relu, void* stream) {
     if (!output || !a || !b) return -100;
     return add_relu(a, b, output, n, relu, as_stream(stream));
+}
+
+int fcuda_eltwise_forward(float* output, const float* a, const float* b, size_t n, int op, float coeff_a, float coeff_b,
+                          int relu, void* stream) {
+    if (!output || !a || !b) return -100;
+    if (op < 0 || op > 2) return -200;
+    if (op == 1 && coeff_a == 1.f && coeff_b == 1.f) return add_relu(a, b, output, n, relu, as_stream(stream));
+    return eltwise(a, b, output, n, op, coeff_a, coeff_b, relu, as_stream(stream));
 }
 
 int fcuda_relu_forward(float* output, const float* input, size_t n, void* stream) {

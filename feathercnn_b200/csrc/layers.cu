@@ -133,6 +133,19 @@ add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
     }
 }
 
+// Eltwise beyond the reference's SUM (eltwise_layer.h:57-66 rejects PROD / MAX / coefficients; semantics follow ncnn's
+// Eltwise): op 0 = a*b, 1 = ca*a + cb*b, 2 = max(a, b); optional ReLU.
+__global__ void __launch_bounds__(256)
+eltwise_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n, int op,
+               float ca, float cb, int relu) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float x = a[i], y = b[i];
+        float r = op == 0 ? x * y : op == 1 ? fmaf(ca, x, cb * y) : fmaxf(x, y);
+        out[i] = relu ? fmaxf(r, 0.f) : r;
+    }
+}
+
 // ReluLayer::Forward (relu_layer.h:29-41) and DropoutLayer::Forward (dropout_layer.h:36-57): y = act(x * scale).
 __global__ void __launch_bounds__(256)
 scale_relu_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, float scale, int relu) {
@@ -215,6 +228,19 @@ fill_rows_kernel(float* __restrict__ out, const float* __restrict__ row, int row
         out[idx] = row ? __ldg(row + idx % row_len) : 0.f;
 }
 
+// out[r][j] = act(bias[j] + part[0][r][j] + part[1][r][j] + ...): the k-split partial planes of the InnerProduct GEMM
+// summed in a fixed order (deterministic, unlike atomics), bias and ReLU fused
+__global__ void __launch_bounds__(256)
+fc_reduce_kernel(float* __restrict__ out, const float* __restrict__ part, const float* __restrict__ bias, int splits,
+                 size_t plane, int row_len, int relu) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < plane; idx += stride) {
+        float v = bias ? __ldg(bias + idx % row_len) : 0.f;
+        for (int s = 0; s < splits; ++s) v += __ldg(part + static_cast<size_t>(s) * plane + idx);
+        out[idx] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 int pooling_forward(const float* in, float* out, const PoolGeom& g, int channels, int batch, cudaStream_t s) {
     const size_t planes = static_cast<size_t>(batch) * channels;
@@ -260,6 +286,15 @@ int add_relu(const float* a, const float* b, float* out, size_t n, int relu, cud
     return 0;
 }
 
+int eltwise(const float* a, const float* b, float* out, size_t n, int op, float ca, float cb, int relu, cudaStream_t s) {
+    const int prof = prof_begin(s, PROF_ELEMENTWISE, 0, 0, 12.0 * n);
+    eltwise_kernel<<<grid_for(n, 256), 256, 0, s>>>(a, b, out, n, op, ca, cb, relu);
+    prof_end(prof, s);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
 int scale_relu(const float* in, float* out, size_t n, float scale, int relu, cudaStream_t s) {
     scale_relu_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(in, out, n, scale, relu);
     FCUDA_CHECK_LAUNCH();
@@ -278,6 +313,15 @@ int copy_channels(const float* src, float* dst, size_t per_image, size_t dst_ima
                   cudaStream_t s) {
     const size_t total = per_image * batch;
     copy_channels_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, dst, per_image, dst_image, dst_offset, total);
+    FCUDA_CHECK_LAUNCH();
+    count_launch();
+    return 0;
+}
+
+int fc_reduce(float* out, const float* part, const float* bias, int splits, int row_len, int rows, int relu,
+              cudaStream_t s) {
+    const size_t plane = static_cast<size_t>(row_len) * rows;
+    fc_reduce_kernel<<<grid_for(plane, 256), 256, 0, s>>>(out, part, bias, splits, plane, row_len, relu);
     FCUDA_CHECK_LAUNCH();
     count_launch();
     return 0;

@@ -43,6 +43,7 @@ struct GemmKernelArgs {
     int epilogue, ldd, P, relu, split_k;
     int num_m, num_n, k_blocks_total;
     long long m_offset;
+    long long split_stride;
 };
 
 template <int BN, int PLANES>
@@ -56,7 +57,7 @@ struct SmemLayout {
 // args.epilogue.  Shared by the smem-operand kernel and the TMEM-A (3xTF32) kernel.
 template <int BN>
 __device__ __forceinline__ void epilogue_store(const GemmKernelArgs& args, uint32_t tmem_base, int as, int q, int lane,
-                                               int g, int m_blk, int n_blk) {
+                                               int g, int m_blk, int n_blk, int ks) {
     const int m = m_blk * kBM + q * 32 + lane;
     const bool m_ok = m < args.M;
     const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -105,17 +106,11 @@ __device__ __forceinline__ void epilogue_store(const GemmKernelArgs& args, uint3
                         dst[static_cast<size_t>(j) * args.P] = v;
                     }
                 }
-            } else {  // EPI_COLMAJOR_ATOMIC
-                float* dst = args.D + static_cast<size_t>(n0) * args.ldd + m;
+            } else {  // EPI_COLMAJOR_PARTIAL: this k-split's plane, plain stores (lanes = consecutive m -> coalesced)
+                float* dst = args.D + static_cast<size_t>(ks) * args.split_stride + static_cast<size_t>(n0) * args.ldd + m;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (n0 + j < args.N) {
-                        if (args.split_k > 1)
-                            atomicAdd(dst + static_cast<size_t>(j) * args.ldd, __uint_as_float(r[j]));
-                        else
-                            dst[static_cast<size_t>(j) * args.ldd] += __uint_as_float(r[j]);
-                    }
-                }
+                for (int j = 0; j < 32; ++j)
+                    if (n0 + j < args.N) dst[static_cast<size_t>(j) * args.ldd] = __uint_as_float(r[j]);
             }
         }
     }
@@ -265,7 +260,7 @@ tensor_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             ptx::mbar_wait(&tmem_full_bar[as], aphase);
             ptx::tc_fence_after();
 
-            epilogue_store<BN>(args, tmem_base, as, q, lane, g, m_blk, n_blk);
+            epilogue_store<BN>(args, tmem_base, as, q, lane, g, m_blk, n_blk, ks);
             // hand the accumulator stage back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
@@ -544,7 +539,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait_relaxed(&tmem_full_bar[as], aphase);
             ptx::tc_fence_after();
-            epilogue_store<BN>(args, tmem_base, as, q, lane, g, m_blk, n_blk);
+            epilogue_store<BN>(args, tmem_base, as, q, lane, g, m_blk, n_blk, ks);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
@@ -643,15 +638,14 @@ static double gemm_algo_bytes(const GemmProblem& p) {
 }
 
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
-        n = prop.multiProcessorCount;
+    static int n[kMaxDevices] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        n[dev] = v;
     }
-    return n;
+    return n[dev];
 }
 
 // 3D map over [G][rows][K] fp32 with a (32 x box_rows x 1) box and 128B swizzle.
@@ -709,24 +703,19 @@ static int launch(const GemmProblem& p, cudaStream_t stream) {
     a.D = p.D; a.bias = p.bias;
     a.M = p.M; a.N = p.N; a.K = p.K; a.G = p.G;
     a.epilogue = p.epilogue; a.ldd = p.ldd; a.P = p.P > 0 ? p.P : 1; a.relu = p.relu;
-    a.split_k = p.split_k > 0 ? p.split_k : 1;
     a.m_offset = p.m_offset;
+    a.split_stride = p.split_stride;
     a.num_m = ceil_div(p.M, kBM);
     a.num_n = ceil_div(p.N, BN);
     a.k_blocks_total = ceil_div(p.K, kBK);
-    if (a.split_k > a.k_blocks_total) a.split_k = a.k_blocks_total;
-    // every k-split must own at least one k-block, otherwise its accumulator is never written
-    while (a.split_k > 1 && ceil_div(a.k_blocks_total, a.split_k) * (a.split_k - 1) >= a.k_blocks_total) --a.split_k;
+    a.split_k = tensor_gemm_effective_split(p.K, p.split_k);
     const long long total = static_cast<long long>(a.num_m) * a.num_n * a.G * a.split_k;
     if (total > 0x7fffffffLL) return -1;
     const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
     const int smem = STAGES * L::kStage + 1024;
     auto kern = tensor_gemm_kernel<BN, PLANES, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    static SmemAttrCache attr_cache;
+    if (int rc = ensure_dynamic_smem(kern, smem, attr_cache)) return rc;
     const double dense = 2.0 * p.M * static_cast<double>(p.N) * p.K * p.G;
     const int prof = prof_begin(stream, PROF_TENSOR_GEMM, p.algo_flops > 0 ? p.algo_flops : dense,
                                 dense * (PLANES == 2 ? 3.0 : 1.0), gemm_algo_bytes(p));
@@ -741,14 +730,21 @@ static void fill_kernel_args(const GemmProblem& p, int bn, GemmKernelArgs* a) {
     a->D = p.D; a->bias = p.bias;
     a->M = p.M; a->N = p.N; a->K = p.K; a->G = p.G;
     a->epilogue = p.epilogue; a->ldd = p.ldd; a->P = p.P > 0 ? p.P : 1; a->relu = p.relu;
-    a->split_k = p.split_k > 0 ? p.split_k : 1;
     a->m_offset = p.m_offset;
+    a->split_stride = p.split_stride;
     a->num_m = ceil_div(p.M, kBM);
     a->num_n = ceil_div(p.N, bn);
     a->k_blocks_total = ceil_div(p.K, kBK);
-    if (a->split_k > a->k_blocks_total) a->split_k = a->k_blocks_total;
-    // every k-split must own at least one k-block, otherwise its accumulator is never written
-    while (a->split_k > 1 && ceil_div(a->k_blocks_total, a->split_k) * (a->split_k - 1) >= a->k_blocks_total) --a->split_k;
+    a->split_k = tensor_gemm_effective_split(p.K, p.split_k);
+}
+
+int tensor_gemm_effective_split(int K, int split_k) {
+    const int kb = ceil_div(K, kBK);
+    int s = split_k > 0 ? split_k : 1;
+    if (s > kb) s = kb;
+    // every k-split must own at least one k-block, otherwise its partial plane is never written
+    while (s > 1 && ceil_div(kb, s) * (s - 1) >= kb) --s;
+    return s;
 }
 
 static int ts_issuers() {  // FCUDA_TS_ISSUERS=1|2 (experiment switch)
@@ -778,11 +774,8 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
     static_assert(kStagesTs * kStage + 1024 <= 227 * 1024, "smem budget");
     const int smem = kStagesTs * kStage + 1024;
     auto kern = tensor_gemm_ts_kernel<BN, ISSUERS>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FCUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    static SmemAttrCache attr_cache;
+    if (int rc = ensure_dynamic_smem(kern, smem, attr_cache)) return rc;
     const double dense = 2.0 * p.M * static_cast<double>(p.N) * p.K * p.G;
     const int prof = prof_begin(stream, PROF_TENSOR_GEMM, p.algo_flops > 0 ? p.algo_flops : dense, dense * 3.0,
                                 gemm_algo_bytes(p));
@@ -795,7 +788,7 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
 
 int tensor_gemm(const GemmProblem& p, cudaStream_t stream) {
     if (!tensor_gemm_supported(p)) return -1;
-    if (p.split_k > 1 && p.epilogue != EPI_COLMAJOR_ATOMIC) return -1;
+    if (p.split_k > 1 && p.epilogue != EPI_COLMAJOR_PARTIAL) return -1;
     if (p.planes == 2) {
         if (ts_issuers() == 2) {
             if (p.N <= 32) return launch_ts<32, 2>(p, stream);
@@ -874,7 +867,7 @@ simt_gemm_kernel(const float* __restrict__ A_hi, const float* __restrict__ A_lo,
                 if (args.relu) v = fmaxf(v, 0.f);
                 args.D[(static_cast<size_t>(img) * args.N + n) * args.P + pix] = v;
             } else {
-                args.D[static_cast<size_t>(n) * args.ldd + m] += v;
+                args.D[static_cast<size_t>(n) * args.ldd + m] = v;
             }
         }
     }
@@ -884,7 +877,7 @@ int simt_gemm(const GemmProblem& p, cudaStream_t stream) {
     GemmKernelArgs a;
     a.D = p.D; a.bias = p.bias;
     a.M = p.M; a.N = p.N; a.K = p.K; a.G = p.G;
-    a.epilogue = p.epilogue; a.ldd = p.ldd; a.P = p.P > 0 ? p.P : 1; a.relu = p.relu; a.split_k = 1; a.m_offset = p.m_offset;
+    a.epilogue = p.epilogue; a.ldd = p.ldd; a.P = p.P > 0 ? p.P : 1; a.relu = p.relu; a.split_k = 1; a.m_offset = p.m_offset; a.split_stride = 0;
     a.num_m = ceil_div(p.M, 64); a.num_n = ceil_div(p.N, 64); a.k_blocks_total = 0;
     const long long as = p.a_batch_stride ? p.a_batch_stride : static_cast<long long>(p.M) * p.K;
     const long long bs = p.b_batch_stride ? p.b_batch_stride : static_cast<long long>(p.N) * p.K;

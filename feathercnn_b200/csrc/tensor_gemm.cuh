@@ -28,9 +28,10 @@ enum GemmEpilogue : int {
     EPI_ROWMAJOR = 0,
     // m = img * P + pix ;  out[(img * N + n) * P + pix] = act(acc + bias[n])      (NCHW conv output)
     EPI_NCHW = 1,
-    // out[n * ldd + m] (+)= acc   — m = output feature, n = batch row (InnerProduct).
-    // With split_k > 1 partial sums are combined with fp32 atomics into a pre-initialised out.
-    EPI_COLMAJOR_ATOMIC = 2,
+    // part[ks][n * ldd + m] = acc  — m = output feature, n = batch row (InnerProduct), ks = k-split index; plane stride
+    // = split_stride floats.  Plain stores: the partial planes are summed in a fixed order by fc_reduce (layers.cu), so
+    // the result does not depend on scheduling (round 1 used fp32 atomics here and was not run-to-run deterministic).
+    EPI_COLMAJOR_PARTIAL = 2,
 };
 
 struct GemmProblem {
@@ -41,12 +42,13 @@ struct GemmProblem {
     int M, N, K, G;
     int planes;        // 1 = TF32, 2 = 3xTF32 (A split in-kernel, B_hi/B_lo planes)
     int epilogue;      // GemmEpilogue
-    int ldd;           // EPI_ROWMAJOR / EPI_COLMAJOR_ATOMIC leading dimension (floats)
+    int ldd;           // EPI_ROWMAJOR / EPI_COLMAJOR_PARTIAL leading dimension (floats)
     int P;             // EPI_NCHW: pixels per image
     long long m_offset;  // EPI_NCHW: global pixel index of row 0 (chunked im2col); image = (m_offset + m) / P
     const float* bias; // EPI_NCHW: per-n bias or null
     int relu;          // EPI_NCHW: fuse max(0, .)
-    int split_k;       // >=1; only with EPI_COLMAJOR_ATOMIC
+    int split_k;       // >=1; only with EPI_COLMAJOR_PARTIAL
+    long long split_stride;  // EPI_COLMAJOR_PARTIAL: floats between the partial planes of consecutive k-splits
     long long a_batch_stride;  // floats between consecutive g in A; 0 => dense (M*K)
     long long b_batch_stride;  // floats between consecutive g in B; 0 => dense (N*K)
     double algo_flops;         // algorithmic FLOPs this launch stands for (profiling only; 0 => 2*M*N*K*G)
@@ -60,6 +62,9 @@ int tensor_gemm(const GemmProblem& p, cudaStream_t stream);
 // bracketed by CUDA events on its own stream.  collect() synchronises and returns totals since enable.
 void gemm_profile_enable(bool on);
 void gemm_profile_collect(double* total_ms, double* algo_flops, double* mma_flops, long long* launches);
+
+// Number of k-splits tensor_gemm will really use for (K, requested split): every split owns at least one 32-wide k-block.
+int tensor_gemm_effective_split(int K, int split_k);
 
 // True when the problem satisfies the TMA alignment rules above.
 bool tensor_gemm_supported(const GemmProblem& p);

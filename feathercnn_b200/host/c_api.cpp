@@ -6,9 +6,23 @@
 #include <feather/net.h>
 #include <string.h>
 
+#include <stdio.h>
+
+#include <exception>
 #include <string>
 
 using feather::Net;
+
+// No C++ exception may cross the C boundary (a corrupt model must produce an error code, not std::terminate).
+#define FNET_GUARD(expr)                                   \
+    try {                                                  \
+        return (expr);                                     \
+    } catch (const std::exception& e) {                    \
+        fprintf(stderr, "feather: %s\n", e.what());        \
+        return FEATHER_ERR_WEIGHTS;                        \
+    } catch (...) {                                        \
+        return FEATHER_ERR_WEIGHTS;                        \
+    }
 
 extern "C" {
 
@@ -27,11 +41,11 @@ long fnet_modelbin_load_mem(const unsigned char* buf, int w, int type, float* ou
 int fnet_fuse_now(void* h) { return static_cast<Net*>(h)->FuseNow(); }
 int fnet_layer_fused_away(void* h, const char* name) { return static_cast<Net*>(h)->LayerFusedAway(name ? name : ""); }
 void fnet_set_stream(void* h, void* stream) { static_cast<Net*>(h)->SetStream(stream); }
-int fnet_load_param(void* h, const char* path) { return static_cast<Net*>(h)->LoadParam(path); }
-int fnet_load_param_text(void* h, const char* text) { return static_cast<Net*>(h)->LoadParamFromText(text); }
-int fnet_load_weights(void* h, const char* path) { return static_cast<Net*>(h)->LoadWeights(path); }
-int fnet_init_from_path(void* h, const char* path) { return static_cast<Net*>(h)->InitFromPath(path); }
-int fnet_init_from_buffer(void* h, const void* buf, size_t size) { return static_cast<Net*>(h)->InitFromBuffer(buf, size); }
+int fnet_load_param(void* h, const char* path) { FNET_GUARD(static_cast<Net*>(h)->LoadParam(path)) }
+int fnet_load_param_text(void* h, const char* text) { FNET_GUARD(static_cast<Net*>(h)->LoadParamFromText(text)) }
+int fnet_load_weights(void* h, const char* path) { FNET_GUARD(static_cast<Net*>(h)->LoadWeights(path)) }
+int fnet_init_from_path(void* h, const char* path) { FNET_GUARD(static_cast<Net*>(h)->InitFromPath(path)) }
+int fnet_init_from_buffer(void* h, const void* buf, size_t size) { FNET_GUARD(static_cast<Net*>(h)->InitFromBuffer(buf, size)) }
 int fnet_prepare_weight_arena(void* h) { return static_cast<Net*>(h)->PrepareWeightArena(); }
 int fnet_weight_arena(void* h, float** device_ptr, size_t* floats) {
     Net* n = static_cast<Net*>(h);
@@ -46,8 +60,12 @@ int fnet_feed_input_batch(void* h, const char* name, const float* host, int n, i
 int fnet_feed_input_device(void* h, const char* name, const float* dev, int n, int c, int hh, int w) {
     return static_cast<Net*>(h)->FeedInputDevice(name, dev, n, c, hh, w);
 }
-int fnet_forward(void* h) { return static_cast<Net*>(h)->Forward(); }
-int fnet_forward_batch(void* h, const float* host_nchw, int batch) { return static_cast<Net*>(h)->ForwardBatch(host_nchw, batch); }
+int fnet_forward(void* h) { FNET_GUARD(static_cast<Net*>(h)->Forward()) }
+int fnet_forward_batch(void* h, const float* host_nchw, int batch) { FNET_GUARD(static_cast<Net*>(h)->ForwardBatch(host_nchw, batch)) }
+int fnet_submit_batch(void* h, const float* host_nchw, int batch, const char* blob, float* host_out) {
+    FNET_GUARD(static_cast<Net*>(h)->SubmitBatch(host_nchw, batch, blob, host_out))
+}
+int fnet_wait_batch(void* h, int ticket) { return static_cast<Net*>(h)->WaitBatch(ticket); }
 int fnet_synchronize(void* h) { return static_cast<Net*>(h)->Synchronize(); }
 int fnet_blob_shape(void* h, const char* name, int* n, int* c, int* hh, int* w) {
     Net* net = static_cast<Net*>(h);

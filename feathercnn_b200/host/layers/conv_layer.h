@@ -24,12 +24,10 @@ public:
     }
 
     int LoadParam(const ncnn::ParamDict& pd) {
-        const int dilation_w = pd.get(2, 1);
-        const int dilation_h = pd.get(12, dilation_w);
-        if (dilation_w > 1 || dilation_h > 1) {
-            LOGE("Dilated convolution is not supported in FeatherCNN.");
-            return FEATHER_ERR_UNSUPPORTED;  // conv_layer.h:41-47
-        }
+        // The reference rejects dilation > 1 (conv_layer.h:41-47); here the implicit-GEMM kernel spaces its taps (§8f rank 4)
+        dilation_w = pd.get(2, 1);
+        dilation_h = pd.get(12, dilation_w);
+        if (dilation_w < 1 || dilation_h < 1) return FEATHER_ERR_UNSUPPORTED;
         if (pd.get(8, 0)) {
             LOGE("int8 convolution is not supported in FeatherCNN.");
             return FEATHER_ERR_UNSUPPORTED;  // conv_layer.h:49-54
@@ -55,9 +53,21 @@ public:
         conv_param.output_channels /= conv_param.group;
         if (conv_param.output_channels <= 0 || conv_param.kernel_h <= 0 || conv_param.kernel_w <= 0) return FEATHER_ERR_WEIGHTS;
         conv_param.input_channels = weight_data_size / conv_param.output_channels / conv_param.kernel_h / conv_param.kernel_w;
-
-        weights.push_back(NewWeightBlob(this->name + "_weights", conv_param.output_channels, conv_param.input_channels,
-                                        conv_param.kernel_h, conv_param.kernel_w));
+        this->weight_data_size = weight_data_size;
+        // Depthwise proper = one filter per channel.  `group == input_channels` alone (the reference's test, booster.h:121,
+        // avx/booster.cpp:285) also matches an ordinary convolution over ONE input channel and truncates a depthwise
+        // with a channel multiplier; those, and partial groups (rejected upstream, avx/booster.cpp:304-308), run as
+        // grouped implicit GEMM with the TOTAL channel counts in conv_param.
+        is_depthwise = conv_param.group > 1 && conv_param.group == conv_param.input_channels && num_output == conv_param.group;
+        if (conv_param.group > 1 && !is_depthwise) {
+            if (conv_param.input_channels % conv_param.group) return FEATHER_ERR_UNSUPPORTED;
+            conv_param.output_channels = num_output;
+            weights.push_back(NewWeightBlob(this->name + "_weights", num_output, conv_param.input_channels / conv_param.group,
+                                            conv_param.kernel_h, conv_param.kernel_w));
+        } else {
+            weights.push_back(NewWeightBlob(this->name + "_weights", conv_param.output_channels, conv_param.input_channels,
+                                            conv_param.kernel_h, conv_param.kernel_w));
+        }
         if (conv_param.bias_term) {
             // The reference sizes the bias by output_channels/group (conv_layer.h:86), which is wrong for
             // depthwise-with-bias; the file holds num_output values, so read those.
@@ -67,8 +77,6 @@ public:
     }
 
     int LoadWeights(const ncnn::ModelBin& mb) {
-        const int weight_data_size =
-            conv_param.input_channels * conv_param.output_channels * conv_param.kernel_h * conv_param.kernel_w;
         ncnn::Mat weight_data = mb.load(weight_data_size, 0);
         if (weight_data.empty() || this->weights.empty()) return FEATHER_ERR_WEIGHTS;
         int rc = this->weights[0]->CopyDataFromMat(weight_data);
@@ -90,8 +98,17 @@ public:
                  this->name.c_str(), conv_param.input_channels, bottom_blob->channels());
             return FEATHER_ERR_TOPOLOGY;
         }
-        if (conv_param.group == conv_param.input_channels) conv_param.output_channels = conv_param.input_channels;
+        const int out_channels = is_depthwise ? conv_param.input_channels : num_output;
+        conv_param.output_channels = out_channels;
         conv_param.AssignOutputDim();
+        conv_param.output_channels = out_channels;  // AssignOutputDim applies the reference's group == IC rule (booster.h:121)
+        if (dilation_h > 1 || dilation_w > 1) {
+            conv_param.output_h = (conv_param.input_h + conv_param.pad_top + conv_param.pad_bottom -
+                                   dilation_h * (conv_param.kernel_h - 1) - 1) / conv_param.stride_h + 1;
+            conv_param.output_w = (conv_param.input_w + conv_param.pad_left + conv_param.pad_right -
+                                   dilation_w * (conv_param.kernel_w - 1) - 1) / conv_param.stride_w + 1;
+            if (conv_param.output_h <= 0 || conv_param.output_w <= 0) return FEATHER_ERR_WEIGHTS;
+        }
         const int batch = bottom_blob->num();
         tops[0]->ReshapeWithRealloc(batch, conv_param.output_channels, conv_param.output_h, conv_param.output_w);
         // FEATHER_ALGO_POLICY=reference keeps avx/booster.cpp:283-310 verbatim; default is the B200 cost model
@@ -99,9 +116,16 @@ public:
             const char* e = getenv("FEATHER_ALGO_POLICY");
             return e && e[0] == 'r';
         }();
-        int rc = reference_policy ? conv_booster.SelectAlgo(&this->conv_param) : conv_booster.SelectAlgoTuned(&this->conv_param);
+        const bool extension = dilation_h > 1 || dilation_w > 1 || (conv_param.group > 1 && !is_depthwise) ||
+                               (conv_param.group == 1 && conv_param.input_channels == 1);
+        int rc = (reference_policy && !extension) ? conv_booster.SelectAlgo(&this->conv_param)
+                                                  : conv_booster.SelectAlgoTuned(&this->conv_param);
         if (rc) return rc;
-        if (const char* force = getenv("FEATHER_FORCE_CONV_ALGO")) {  // ForceSelectAlgo hook, avx/booster.cpp:313-317
+        if (dilation_h > 1 || dilation_w > 1) {
+            if (conv_param.group > 1 && is_depthwise) return FEATHER_ERR_UNSUPPORTED;  // dilated depthwise: not built
+            conv_booster.ForceSelectAlgo(booster::SGECONV);
+        }
+        if (const char* force = extension ? NULL : getenv("FEATHER_FORCE_CONV_ALGO")) {  // ForceSelectAlgo hook, avx/booster.cpp:313-317
             booster::ConvBooster forced;
             forced.ForceSelectAlgo(static_cast<booster::ConvAlgo>(atoi(force)));
             size_t a = 0, b = 0;
@@ -164,6 +188,10 @@ public:
     int Forward() {
         float* buffer = NULL;
         MEMPOOL_CHECK_RETURN(this->common_mempool->GetPtr(&buffer));
+        if (dilation_h > 1 || dilation_w > 1)
+            return fcuda_conv_forward_ext(&conv_param, conv_booster.GetAlgo(), tops[0]->data(), bottoms[0]->data(),
+                                          processed_kernel, buffer, bias_data, residual ? residual->data() : NULL,
+                                          relu_after_add, dilation_h, dilation_w, bottoms[0]->num(), stream());
         if (residual != NULL)
             return conv_booster.ForwardResidual(&conv_param, tops[0]->data(), bottoms[0]->data(), processed_kernel, buffer,
                                                 bias_data, residual->data(), relu_after_add, bottoms[0]->num(), stream());
@@ -223,6 +251,9 @@ protected:
     Blob<float>* processed_weights;
     int init_algo;
     int num_output = 0;
+    int weight_data_size = 0;
+    int dilation_h = 1, dilation_w = 1;
+    bool is_depthwise = false;
     // BN / Scale folding (Net::SetFusion): per-output-channel multiplier and offset applied at Init
     std::vector<float> fold_mul, fold_add;
     bool had_bias = false;

@@ -1,8 +1,11 @@
-// EltwiseLayer (mirrors /root/reference/src/layers/eltwise_layer.h:21-90: SUM only, no coefficients).
+// EltwiseLayer (mirrors /root/reference/src/layers/eltwise_layer.h:21-90, which is SUM only without coefficients; PROD,
+// MAX and SUM coefficients are this engine's extension).
 #pragma once
 
 #include <fcuda.h>
 #include <feather/layer.h>
+
+#include <vector>
 
 namespace feather {
 inline namespace b200 {  // ABI tag: keeps these symbols apart from the reference build when both are loaded
@@ -23,27 +26,41 @@ public:
         return 0;
     }
 
+    // The reference accepts SUM without coefficients only (eltwise_layer.h:57-66); PROD / MAX / coefficients follow ncnn.
     int LoadParam(const ncnn::ParamDict& pd) {
         op_type = pd.get(0, 0);
-        ncnn::Mat coeffs = pd.get(1, ncnn::Mat());
-        if (!coeffs.empty()) {
-            LOGE("FeatherCNN doesn't support coeffs in eltwise layer. Please refer to ncnn.");
+        ncnn::Mat c = pd.get(1, ncnn::Mat());
+        coeffs.clear();
+        for (int i = 0; i < c.w; ++i) coeffs.push_back(c[i]);
+        if (op_type < Operation_PROD || op_type > Operation_MAX) {
+            LOGE("Eltwise layer %s: unknown operation %d", this->name.c_str(), op_type);
             return FEATHER_ERR_WEIGHTS;
         }
-        if (op_type != Operation_SUM) {
-            LOGE("FeatherCNN doesn't support ops rather than SUM. Please refer to ncnn.");
-            return FEATHER_ERR_WEIGHTS;
-        }
+        if (!coeffs.empty() && op_type != Operation_SUM) return FEATHER_ERR_WEIGHTS;
         return 0;
     }
 
+    bool plain_sum() const { return op_type == Operation_SUM && coeffs.empty(); }
+
     int Forward() {
-        // the reference adds bottoms 0 and 1 only (eltwise_layer.h:70-73); further bottoms are accumulated here
-        int rc = fcuda_eltwise_add_forward(tops[0]->data(), bottoms[0]->data(), bottoms[1]->data(), bottoms[0]->data_size(),
-                                           (fuse_relu && bottoms.size() == 2) ? 1 : 0, stream());
+        if (!coeffs.empty() && coeffs.size() != bottoms.size()) return FEATHER_ERR_WEIGHTS;
+        const size_t n = bottoms[0]->data_size();
+        if (plain_sum()) {
+            // the reference adds bottoms 0 and 1 only (eltwise_layer.h:70-73); further bottoms are accumulated here
+            int rc = fcuda_eltwise_add_forward(tops[0]->data(), bottoms[0]->data(), bottoms[1]->data(), n,
+                                               (fuse_relu && bottoms.size() == 2) ? 1 : 0, stream());
+            for (size_t i = 2; i < bottoms.size() && rc == 0; ++i)
+                rc = fcuda_eltwise_add_forward(tops[0]->data(), tops[0]->data(), bottoms[i]->data(), n,
+                                               (fuse_relu && i + 1 == bottoms.size()) ? 1 : 0, stream());
+            return rc;
+        }
+        const float c0 = coeffs.empty() ? 1.f : coeffs[0], c1 = coeffs.empty() ? 1.f : coeffs[1];
+        int rc = fcuda_eltwise_forward(tops[0]->data(), bottoms[0]->data(), bottoms[1]->data(), n, op_type, c0, c1,
+                                       (fuse_relu && bottoms.size() == 2) ? 1 : 0, stream());
         for (size_t i = 2; i < bottoms.size() && rc == 0; ++i)
-            rc = fcuda_eltwise_add_forward(tops[0]->data(), tops[0]->data(), bottoms[i]->data(), bottoms[0]->data_size(),
-                                           (fuse_relu && i + 1 == bottoms.size()) ? 1 : 0, stream());
+            rc = fcuda_eltwise_forward(tops[0]->data(), tops[0]->data(), bottoms[i]->data(), n, op_type, 1.f,
+                                       coeffs.empty() ? 1.f : coeffs[i], (fuse_relu && i + 1 == bottoms.size()) ? 1 : 0,
+                                       stream());
         return rc;
     }
 
@@ -61,6 +78,7 @@ public:
 private:
     int op_type;
     int fuse_relu;
+    std::vector<float> coeffs;
 };
 
 }  // inline namespace b200

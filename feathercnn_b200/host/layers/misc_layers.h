@@ -42,32 +42,43 @@ public:
         this->axis = pd.get(0, 0);
         return 0;
     }
+    // ncnn axis of a 3-D blob: 0 = channels, 1 = height, 2 = width.  The reference handles axis 0 only
+    // (concat_layer.h:50-54); 1 and 2 are this engine's extension.
     int Reshape() {
         const Blob<float>* first_blob = this->bottoms[0];
-        size_t channels = first_blob->channels();
-        const size_t width = first_blob->width(), height = first_blob->height(), num = first_blob->num();
+        if (axis < 0 || axis > 2) {
+            LOGE("Concat layer %s: unsupported axis %d", this->name.c_str(), axis);
+            return FEATHER_ERR_WEIGHTS;
+        }
+        size_t dims[3] = {first_blob->channels(), first_blob->height(), first_blob->width()};
+        const size_t num = first_blob->num();
         for (size_t i = 1; i < bottoms.size(); ++i) {
             const Blob<float>* p_blob = bottoms[i];
-            if (this->axis != 0) {
-                LOGE("FeatherCNN only supports concat at axis = 0.");
-                return FEATHER_ERR_WEIGHTS;
-            }
-            if (!(width == p_blob->width() && height == p_blob->height() && num == p_blob->num())) {
-                LOGE("Images of different shapes cannot be concatenated together");
-                return FEATHER_ERR_WEIGHTS;
-            }
-            channels += p_blob->channels();
+            const size_t d[3] = {p_blob->channels(), p_blob->height(), p_blob->width()};
+            for (int a = 0; a < 3; ++a)
+                if (a != axis && d[a] != dims[a]) {
+                    LOGE("Images of different shapes cannot be concatenated together");
+                    return FEATHER_ERR_WEIGHTS;
+                }
+            if (num != p_blob->num()) return FEATHER_ERR_WEIGHTS;
+            dims[axis] += d[axis];
         }
-        tops[0]->ReshapeWithRealloc(num, channels, height, width);
+        tops[0]->ReshapeWithRealloc(num, dims[0], dims[1], dims[2]);
         return 0;
     }
     int Forward() {
+        // [outer][mid][inner] copy: outer = everything before the axis, mid = the axis, inner = everything after it
         int offset = 0, rc = 0;
-        const size_t stride = tops[0]->height() * tops[0]->width();
+        const Blob<float>* t = tops[0];
         for (size_t i = 0; i < bottoms.size() && rc == 0; ++i) {
-            rc = fcuda_copy_channels(tops[0]->data(), tops[0]->channels(), offset, bottoms[i]->data(), bottoms[i]->channels(),
-                                     stride, bottoms[i]->num(), stream());
-            offset += bottoms[i]->channels();
+            const Blob<float>* b = bottoms[i];
+            size_t outer, mid, dst_mid, inner;
+            if (axis == 0) { outer = b->num(); mid = b->channels(); dst_mid = t->channels(); inner = t->height() * t->width(); }
+            else if (axis == 1) { outer = b->num() * b->channels(); mid = b->height(); dst_mid = t->height(); inner = t->width(); }
+            else { outer = b->num() * b->channels() * b->height(); mid = b->width(); dst_mid = t->width(); inner = 1; }
+            rc = fcuda_copy_channels(t->data(), static_cast<int>(dst_mid), offset, b->data(), static_cast<int>(mid), inner,
+                                     static_cast<int>(outer), stream());
+            offset += static_cast<int>(mid);
         }
         return rc;
     }

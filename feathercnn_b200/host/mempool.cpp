@@ -12,7 +12,11 @@ bool CommonMemPool<PTR_TYPE>::Request(size_t size_byte) {
 template <typename PTR_TYPE>
 bool CommonMemPool<PTR_TYPE>::Alloc() {
     if (allocated_size >= common_size && (common_memory || common_size == 0)) return true;
-    if (common_memory) cudaFree(common_memory);
+    if (common_memory && cudaFree(common_memory) != cudaSuccess) {
+        // e.g. called inside a stream capture: keep the old pool instead of leaking it
+        fprintf(stderr, "CommonMemPool: cudaFree failed (%s); pool not resized\n", cudaGetErrorString(cudaGetLastError()));
+        return false;
+    }
     common_memory = nullptr;
     allocated_size = 0;
     if (common_size == 0) return true;

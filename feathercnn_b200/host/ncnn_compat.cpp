@@ -138,8 +138,14 @@ struct FileReader : Reader {
 };
 struct MemReader : Reader {
     const unsigned char*& mem;
-    explicit MemReader(const unsigned char*& m) : mem(m) {}
-    bool read(void* dst, size_t n) override { memcpy(dst, mem, n); mem += n; return true; }
+    const unsigned char* end;  // one past the buffer, or NULL when the caller gave no size (the reference's contract)
+    MemReader(const unsigned char*& m, const unsigned char* e) : mem(m), end(e) {}
+    bool read(void* dst, size_t n) override {
+        if (end && (mem > end || n > static_cast<size_t>(end - mem))) return false;  // truncated / corrupt model
+        memcpy(dst, mem, n);
+        mem += n;
+        return true;
+    }
 };
 
 static Mat load_blob(Reader& r, int w, int type) {
@@ -190,7 +196,7 @@ Mat ModelBinFromStdio::load(int w, int type) const {
 
 Mat ModelBinFromMemory::load(int w, int type) const {
     if (!mem) return Mat();
-    MemReader r(mem);
+    MemReader r(mem, end);
     return load_blob(r, w, type);
 }
 

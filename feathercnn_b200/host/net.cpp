@@ -19,6 +19,7 @@ namespace feather {
 inline namespace b200 {  // ABI tag: keeps these symbols apart from the reference build when both are loaded
 
 static const char kContainerMagic[8] = {'F', 'T', 'H', 'R', 'B', '2', '0', '0'};
+static const int kMaxLayers = 1 << 20;  // sanity bound on counts read from a .param (a corrupt file must not drive resize())
 
 #define CUDA_OK(expr)                                                                        \
     do {                                                                                     \
@@ -47,6 +48,7 @@ Net::Net(size_t) : Net() {}
 
 Net::~Net() {
     ResetGraph();
+    FreePipeline();
     for (size_t i = 0; i < layers.size(); ++i) {
         delete layers[i];
         layers[i] = NULL;
@@ -103,7 +105,8 @@ int Net::ParseParamText(const char* mem) {
         return -1;
     }
     int layer_count = 0, blob_count = 0;
-    if (sscanf(mem, "%d %d%n", &layer_count, &blob_count, &consumed) != 2 || layer_count <= 0 || blob_count <= 0) {
+    if (sscanf(mem, "%d %d%n", &layer_count, &blob_count, &consumed) != 2 || layer_count <= 0 || blob_count <= 0 ||
+        layer_count > kMaxLayers || blob_count > kMaxLayers) {
         LOGE("issue with param file");
         return -1;
     }
@@ -115,6 +118,10 @@ int Net::ParseParamText(const char* mem) {
         int bottom_count = 0, top_count = 0;
         if (sscanf(mem, "%256s %256s %d %d%n", layer_type, layer_name, &bottom_count, &top_count, &consumed) != 4) {
             LOGE("param file ends after %d of %d layers", i, layer_count);
+            return -1;
+        }
+        if (bottom_count < 0 || top_count < 0 || bottom_count > kMaxLayers || top_count > kMaxLayers) {
+            LOGE("layer %s: bad bottom/top count (%d, %d)", layer_name, bottom_count, top_count);
             return -1;
         }
         mem += consumed;
@@ -265,12 +272,12 @@ int Net::InitFromBuffer(const void* net_buffer, size_t size) {
     }
     uint64_t param_len = 0;
     memcpy(&param_len, p + 8, 8);
-    if (16 + param_len > size) return -1;
+    if (param_len > size - 16) return -1;  // (16 + param_len > size would wrap for a huge param_len)
     std::string text(reinterpret_cast<const char*>(p + 16), static_cast<size_t>(param_len));
     int rc = ParseParamText(text.c_str());
     if (rc) return rc;
     const unsigned char* bin = p + 16 + param_len;
-    ncnn::ModelBinFromMemory mb(bin);
+    ncnn::ModelBinFromMemory mb(bin, p + size);  // bounded: a truncated container fails like a short fread
     rc = LoadWeightsFrom(mb, true);
     if (rc == 0) _weights_loaded = 1;
     return rc;
@@ -497,7 +504,7 @@ int Net::ApplyFusion() {
         for (size_t j = 0; j < layers[i]->tops.size(); ++j) producer[layers[i]->tops[j]] = i;
     for (size_t j = 0; j < layers.size(); ++j) {
         EltwiseLayer* e = dynamic_cast<EltwiseLayer*>(layers[j]);
-        if (!e || e->_fused_away || e->bottoms.size() != 2 || e->tops.size() != 1) continue;
+        if (!e || e->_fused_away || e->bottoms.size() != 2 || e->tops.size() != 1 || !e->plain_sum()) continue;
         for (int k = 1; k >= 0; --k) {
             Blob<float>* mine = e->bottoms[k];
             Blob<float>* other = e->bottoms[1 - k];
@@ -543,6 +550,7 @@ int Net::LayerFusedAway(const std::string& layer_name) const {
 void Net::ResetGraph() {
     for (auto& kv : graph_cache_) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(kv.second));
     graph_cache_.clear();
+    warmed_keys_.clear();
 }
 
 int Net::Forward() {
@@ -556,21 +564,44 @@ int Net::Forward() {
     }
     int rc = this->Reshape();
     if (rc) return rc;
-    if (this->_net_initialized == 0) {
+    // Packed filters are laid out for the precision mode (1 or 2 operand planes) that was current at Init: a later
+    // fcuda_set_precision() must re-pack them before any kernel reads `packed + plane`.
+    const int precision_now = fcuda_get_precision();
+    if (this->_net_initialized == 0 || precision_now != init_precision_) {
+        if (this->_net_initialized) ResetGraph();
         rc = InitLayers();
         if (rc) return rc;
         this->_net_initialized = 1;
+        init_precision_ = precision_now;
     }
     cudaStream_t s = static_cast<cudaStream_t>(rt_param->stream());
 
-    // CUDA-graph replay: one instantiated graph per (blob addresses, shapes) key, so rotating between a few
-    // input buffers / batch sizes replays without re-capturing.
+    // The scratch pool is sized by Reshape (Request) and must exist BEFORE a stream capture begins: cudaMalloc /
+    // cudaFree are illegal inside one.  A pool that moved invalidates every captured graph (they hold its address).
+    {
+        CommonMemPool<float>* pool = rt_param->common_mempool();
+        if (!pool->Alloc()) return FEATHER_ERR_CUDA;
+        float* pool_ptr = nullptr;
+        pool->GetPtr(&pool_ptr);
+        if (pool_ptr != graph_pool_ptr_) {
+            ResetGraph();
+            graph_pool_ptr_ = pool_ptr;
+        }
+    }
+
+    // CUDA-graph replay: one instantiated graph per (blob addresses, blob shapes, scratch pool, precision) key, so
+    // rotating between a few input buffers / batch sizes replays without re-capturing.  Shapes are part of the key:
+    // blobs are grow-only, so two geometries with equal element counts share addresses (224x112 vs 112x224).
     std::vector<size_t> key;
     if (use_graph_ && s != nullptr) {
+        key.push_back(reinterpret_cast<size_t>(graph_pool_ptr_));
+        key.push_back(static_cast<size_t>(precision_now));
         for (size_t i = 0; i < layers.size(); ++i)
             for (size_t j = 0; j < layers[i]->tops.size(); ++j) {
-                key.push_back(reinterpret_cast<size_t>(layers[i]->tops[j]->data()));
-                key.push_back(layers[i]->tops[j]->data_size());
+                const Blob<float>* b = layers[i]->tops[j];
+                key.push_back(reinterpret_cast<size_t>(b->data()));
+                key.push_back((b->num() << 40) ^ (b->channels() << 20) ^ b->height());
+                key.push_back(b->width());
             }
         std::map<std::vector<size_t>, void*>::iterator hit = graph_cache_.find(key);
         if (hit != graph_cache_.end()) {
@@ -580,7 +611,9 @@ int Net::Forward() {
     }
 
     const unsigned long long before = fcuda_launch_count();
-    if (use_graph_ && s != nullptr && warmed_up_) {
+    // The first Forward of every new key runs eagerly (kernel attributes, lazily created tensor maps); the second one
+    // with that key is captured.
+    if (use_graph_ && s != nullptr && warmed_keys_.count(key)) {
         if (graph_cache_.size() >= 16) ResetGraph();
         cudaGraph_t graph = nullptr;
         CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -604,8 +637,84 @@ int Net::Forward() {
     }
     rc = RunLayers();
     launches_per_forward_ = fcuda_launch_count() - before;
-    warmed_up_ = true;  // first eager pass allocated the scratch pool and set kernel attributes
+    if (use_graph_ && s != nullptr && rc == 0) {
+        if (warmed_keys_.size() >= 64) warmed_keys_.clear();
+        warmed_keys_.insert(key);
+    }
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pipelined end-to-end path: host batch -> H2D (copy stream) -> Forward -> D2H of one blob, two batches in flight.
+// The H2D copy of batch i+1 runs behind an event while batch i computes; what FeedInput (net.cpp:232-243) does
+// synchronously per image in the reference.
+// ---------------------------------------------------------------------------------------------------------
+int Net::SubmitBatch(const float* host_nchw, int batch, const char* blob_name, float* host_out) {
+    if (input_name_.empty() || input_c_ <= 0 || !host_nchw || batch < 1) return -1;
+    cudaStream_t s = static_cast<cudaStream_t>(rt_param->stream());
+    if (!copy_stream_) {
+        cudaStream_t cs = nullptr;
+        CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        copy_stream_ = cs;
+    }
+    cudaStream_t cs = static_cast<cudaStream_t>(copy_stream_);
+    PipeSlot& sl = pipe_[submitted_ & 1];
+    if (!sl.ev_h2d) {
+        cudaEvent_t a, b, c;
+        CUDA_OK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
+        sl.ev_h2d = a; sl.ev_free = b; sl.ev_done = c;
+    }
+    const size_t floats = static_cast<size_t>(batch) * input_c_ * input_h_ * input_w_;
+    if (floats > sl.capacity) {
+        if (sl.used) CUDA_OK(cudaEventSynchronize(static_cast<cudaEvent_t>(sl.ev_done)));
+        if (sl.dev) cudaFree(sl.dev);
+        sl.dev = nullptr;
+        sl.capacity = 0;
+        CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&sl.dev), floats * sizeof(float)));
+        sl.capacity = floats;
+    }
+    // the previous Forward that read this slot must have finished before the slot is overwritten
+    if (sl.used) CUDA_OK(cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(sl.ev_free), 0));
+    CUDA_OK(cudaMemcpyAsync(sl.dev, host_nchw, floats * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_h2d), cs));
+    CUDA_OK(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(sl.ev_h2d), 0));
+    int rc = FeedInputDevice(input_name_.c_str(), sl.dev, batch, input_c_, input_h_, input_w_);
+    if (rc) return rc;
+    rc = Forward();
+    if (rc) return rc;
+    CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_free), s));
+    if (blob_name && host_out) {
+        std::map<std::string, Blob<float>*>::iterator it = blob_map.find(blob_name);
+        if (it == blob_map.end() || !it->second->data()) return -1;
+        CUDA_OK(cudaMemcpyAsync(host_out, it->second->data(), it->second->data_size() * sizeof(float),
+                                cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_done), s));
+    sl.used = true;
+    return static_cast<int>(submitted_++ & 0x3fffffff);
+}
+
+int Net::WaitBatch(int ticket) {
+    if (ticket < 0) return -1;
+    PipeSlot& sl = pipe_[ticket & 1];
+    if (!sl.used) return -1;
+    CUDA_OK(cudaEventSynchronize(static_cast<cudaEvent_t>(sl.ev_done)));
+    return 0;
+}
+
+void Net::FreePipeline() {
+    for (int i = 0; i < 2; ++i) {
+        PipeSlot& sl = pipe_[i];
+        if (sl.ev_h2d) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_h2d));
+        if (sl.ev_free) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_free));
+        if (sl.ev_done) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_done));
+        if (sl.dev) cudaFree(sl.dev);
+        sl = PipeSlot();
+    }
+    if (copy_stream_) cudaStreamDestroy(static_cast<cudaStream_t>(copy_stream_));
+    copy_stream_ = nullptr;
 }
 
 }  // inline namespace b200

@@ -104,6 +104,18 @@ class Net:
         """README-style ``Forward(float*)`` over a (pinned) host buffer holding `batch` images."""
         _check("ForwardBatch", self._lib.fnet_forward_batch(self._h, ctypes.c_void_p(host_ptr), batch))
 
+    def SubmitBatch(self, host_ptr: int, batch: int, blob: str | None = None, host_out_ptr: int = 0) -> int:
+        """Pipelined end-to-end step (two in flight): H2D on a copy stream, Forward, D2H of `blob` into `host_out_ptr`.
+        Returns a ticket for WaitBatch.  Host buffers should be pinned and stay valid until the wait."""
+        t = self._lib.fnet_submit_batch(self._h, ctypes.c_void_p(host_ptr), batch, blob.encode() if blob else None,
+                                        ctypes.c_void_p(host_out_ptr))
+        if t < 0:
+            raise FeatherError("SubmitBatch", t)
+        return t
+
+    def WaitBatch(self, ticket: int) -> None:
+        _check("WaitBatch", self._lib.fnet_wait_batch(self._h, ticket))
+
     def Synchronize(self) -> None:
         _check("Synchronize", self._lib.fnet_synchronize(self._h))
 

@@ -77,7 +77,9 @@ int fcuda_conv_assign_output_dim(FcudaConvParam* param);
 int fcuda_conv_select_algo(const FcudaConvParam* param, int* algo);
 
 /* B200 cost-model variant of SelectAlgo: starts from the reference rule and moves bandwidth-bound Winograd layers
- * (<= 128 channels on images >= 28 wide) and the im2col layers to FCUDA_SGECONV.  Same return convention. */
+ * (<= 128 channels on images >= 28 wide) and the im2col layers to FCUDA_SGECONV.  Unlike the reference rule it treats
+ * group == 1 with one input channel as an ordinary convolution, requires group > 1 and OC == IC for FCUDA_DEPTHWISE, and
+ * sends partial groups / channel-multiplier depthwise to the grouped FCUDA_SGECONV instead of returning -1. */
 int fcuda_conv_select_algo_tuned(const FcudaConvParam* param, int* algo);
 
 /* GET_BUFFER_SIZE_FUNC, booster.h:151: scratch and processed-kernel sizes in floats for `batch` images. */
@@ -129,6 +131,10 @@ int fcuda_scale_forward(float* output, const float* input, int channels, size_t 
                         const float* bias, int batch, void* stream);
 /* booster::add_relu<fuse_relu> (avx/generic_kernels.cpp:138-169). */
 int fcuda_eltwise_add_forward(float* output, const float* a, const float* b, size_t n, int relu, void* stream);
+/* Eltwise operations the reference rejects (src/layers/eltwise_layer.h:57-66), with ncnn's semantics:
+ * op 0 PROD a*b, op 1 SUM coeff_a*a + coeff_b*b, op 2 MAX max(a,b); optional ReLU.  In-place (output == a) is allowed. */
+int fcuda_eltwise_forward(float* output, const float* a, const float* b, size_t n, int op, float coeff_a, float coeff_b,
+                          int relu, void* stream);
 /* ReluLayer::Forward (src/layers/relu_layer.h:29-41). */
 int fcuda_relu_forward(float* output, const float* input, size_t n, void* stream);
 /* SoftmaxLayer::Forward (src/layers/softmax_layer.h:32-55): over each image's whole blob. */
@@ -148,6 +154,17 @@ int fcuda_copy_channels(float* dst, int dst_channels, int dst_channel_offset, co
 int fcuda_conv_forward_residual(const FcudaConvParam* param, int algo, float* output, const float* input,
                                 const float* packed_kernel, float* scratch, const float* bias, const float* residual,
                                 int relu_after_add, int batch, void* stream);
+
+/* Extended forward (beyond the reference, which rejects both: dilation at src/layers/conv_layer.h:43-47, partial groups at
+ * avx/booster.cpp:304-308).  Same as fcuda_conv_forward[_residual] (`residual` may be NULL) plus a tap spacing.
+ *   dilation: FCUDA_SGECONV only (-200 otherwise); the caller sets param->output_h/w for the dilated extent
+ *             out = (in + pads - dilation*(k-1) - 1) / stride + 1.
+ *   groups  : with FCUDA_SGECONV and param->group > 1 (also through the plain entry points) input_channels and
+ *             output_channels are the TOTAL channel counts, the raw kernel is (OC, IC/group, KH, KW) and group g
+ *             maps input channels [g*IC/G, (g+1)*IC/G) to output channels [g*OC/G, (g+1)*OC/G). */
+int fcuda_conv_forward_ext(const FcudaConvParam* param, int algo, float* output, const float* input,
+                           const float* packed_kernel, float* scratch, const float* bias, const float* residual,
+                           int relu_after_add, int dilation_h, int dilation_w, int batch, void* stream);
 
 /* Profiling aid for bench.py's roofline leg: while enabled, every TensorGEMM launch is bracketed by CUDA events
  * on its own stream.  fcuda_profile_collect synchronises and reports, since the last enable: summed device time

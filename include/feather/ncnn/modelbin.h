@@ -28,11 +28,14 @@ private:
 
 class ModelBinFromMemory : public ModelBin {
 public:
-    explicit ModelBinFromMemory(const unsigned char*& _mem) : mem(_mem) {}
+    // `end` (one past the last byte) is optional: the reference's reader takes no size (modelbin.cpp:200-293) and a
+    // truncated buffer makes it read past the end; with `end` a short buffer yields an empty Mat like a short fread.
+    explicit ModelBinFromMemory(const unsigned char*& _mem, const unsigned char* _end = nullptr) : mem(_mem), end(_end) {}
     Mat load(int w, int type) const override;
 
 private:
     const unsigned char*& mem;
+    const unsigned char* end;
 };
 
 // Returns zero-filled blobs of the requested size without touching any file: lets every rank of a

@@ -13,6 +13,7 @@
 #pragma once
 
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -59,6 +60,12 @@ public:
     int ForwardBatch(const float* host_nchw, int batch);  // FeedInputBatch(first Input layer) + Forward
     int ExtractDevice(std::string blob_name, const float** device_ptr, int* n, int* c, int* h, int* w);
     int Synchronize();
+    // Pipelined end-to-end path (two batches in flight): the H2D copy of a batch runs on a copy stream behind an
+    // event while the previous batch computes; Forward follows on the Net's stream, then the D2H copy of `blob_name`
+    // (may be NULL) into `host_out`.  `host_nchw` / `host_out` should be pinned and must stay valid until WaitBatch.
+    // Returns a ticket (>= 0) for WaitBatch, or a negative error code.
+    int SubmitBatch(const float* host_nchw, int batch, const char* blob_name, float* host_out);
+    int WaitBatch(int ticket);
 
     // Weight arena: every weight blob of the model, contiguous on the device.  Rank 0 of a multi-GPU job
     // fills it with LoadWeights(); other ranks call PrepareWeightArena(), receive the bytes (e.g.
@@ -90,6 +97,13 @@ private:
     int BindWeightBlobs(bool upload);
     int ApplyFusion();
     void ResetGraph();
+    void FreePipeline();
+    struct PipeSlot {
+        float* dev = nullptr;
+        size_t capacity = 0;
+        void *ev_h2d = nullptr, *ev_free = nullptr, *ev_done = nullptr;  // cudaEvent_t
+        bool used = false;
+    };
 
     RuntimeParameter<float>* rt_param;
     std::vector<Layer*> layers;
@@ -108,7 +122,12 @@ private:
     unsigned long long launches_per_forward_ = 0;
     bool owns_stream_ = false;
     bool fusion_applied_ = false;
-    bool warmed_up_ = false;
+    std::set<std::vector<size_t>> warmed_keys_;  // graph keys that already ran once eagerly
+    float* graph_pool_ptr_ = nullptr;            // scratch pool address the cached graphs were captured with
+    int init_precision_ = -1;                    // fcuda precision mode the packed filters were made for
+    PipeSlot pipe_[2];
+    void* copy_stream_ = nullptr;
+    unsigned submitted_ = 0;
 };
 
 }  // inline namespace b200

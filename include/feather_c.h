@@ -33,6 +33,10 @@ int fnet_feed_input_batch(void* net, const char* input_name, const float* host_n
 int fnet_feed_input_device(void* net, const char* input_name, const float* device_nchw, int n, int c, int h, int w);
 int fnet_forward(void* net);                                     /* Net::Forward, net.cpp:298-334 */
 int fnet_forward_batch(void* net, const float* host_nchw, int batch); /* README.md:65 with a batch */
+/* pipelined end-to-end path: H2D on a copy stream behind an event, Forward, D2H of `blob` into host_out; two batches
+ * in flight; returns a ticket >= 0 for fnet_wait_batch (Net::SubmitBatch / WaitBatch) */
+int fnet_submit_batch(void* net, const float* host_nchw, int batch, const char* blob, float* host_out);
+int fnet_wait_batch(void* net, int ticket);
 int fnet_synchronize(void* net);
 int fnet_blob_shape(void* net, const char* blob, int* n, int* c, int* h, int* w);
 int fnet_extract_blob(void* net, const char* blob, float* host_out);  /* README.md:69 */

@@ -60,13 +60,14 @@ static int run_case(const Case& c, int planes, bool bench) {
     float *dAh, *dAl, *dBh, *dBl, *dD, *dR, *dbias;
     CK(cudaMalloc(&dAh, nA * 4)); CK(cudaMalloc(&dAl, nA * 4));
     CK(cudaMalloc(&dBh, nB * 4)); CK(cudaMalloc(&dBl, nB * 4));
-    CK(cudaMalloc(&dD, nD * 4)); CK(cudaMalloc(&dR, nD * 4)); CK(cudaMalloc(&dbias, c.N * 4));
+    const int splits = c.epi == EPI_COLMAJOR_PARTIAL ? tensor_gemm_effective_split(c.K, c.split_k) : 1;
+    CK(cudaMalloc(&dD, nD * 4 * splits)); CK(cudaMalloc(&dR, nD * 4)); CK(cudaMalloc(&dbias, c.N * 4));
     CK(cudaMemcpy(dAh, Ahi.data(), nA * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dAl, Alo.data(), nA * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dBh, Bhi.data(), nB * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dBl, Blo.data(), nB * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dbias, bias.data(), c.N * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemset(dD, 0, nD * 4));
+    CK(cudaMemset(dD, 0, nD * 4 * splits));
     CK(cudaMemset(dR, 0, nD * 4));
 
     GemmProblem p{};
@@ -75,6 +76,7 @@ static int run_case(const Case& c, int planes, bool bench) {
     p.M = c.M; p.N = c.N; p.K = c.K; p.G = c.G; p.planes = planes; p.epilogue = c.epi; p.ldd = ldd;
     p.P = c.P; p.bias = (c.epi == EPI_NCHW) ? dbias : nullptr; p.relu = (c.epi == EPI_NCHW) ? 1 : 0;
     p.split_k = c.split_k;
+    p.split_stride = (long long)nD;
     int rc = tensor_gemm(p, 0);
     if (rc) { printf("tensor_gemm rc=%d\n", rc); return 1; }
     CK(cudaDeviceSynchronize());
@@ -86,8 +88,13 @@ static int run_case(const Case& c, int planes, bool bench) {
     if (rc) { printf("simt_gemm rc=%d\n", rc); return 1; }
     CK(cudaDeviceSynchronize());
 
-    std::vector<float> D(nD), R(nD);
-    CK(cudaMemcpy(D.data(), dD, nD * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> D(nD), R(nD), parts(nD * splits);
+    CK(cudaMemcpy(parts.data(), dD, nD * 4 * splits, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nD; ++i) {  // fixed-order sum of the k-split planes (what fc_reduce does on the device)
+        float v = 0.f;
+        for (int sp = 0; sp < splits; ++sp) v += parts[(size_t)sp * nD + i];
+        D[i] = v;
+    }
     CK(cudaMemcpy(R.data(), dR, nD * 4, cudaMemcpyDeviceToHost));
 
     double max_ref = 0, max_err = 0, max_err_host = -1;
@@ -153,13 +160,13 @@ int main(int argc, char** argv) {
         {200, 160, 64, 1, EPI_ROWMAJOR, 1, 1, true},    // N > 128
         {392, 64, 28, 1, EPI_NCHW, 196, 1, true},       // conv-like: 2 images of 14x14
         {500, 100, 148, 1, EPI_NCHW, 250, 1, true},
-        {256, 8, 512, 1, EPI_COLMAJOR_ATOMIC, 1, 1, true},   // FC: M=out, N=batch
-        {384, 16, 1024, 1, EPI_COLMAJOR_ATOMIC, 1, 4, true}, // split-K atomics
+        {256, 8, 512, 1, EPI_COLMAJOR_PARTIAL, 1, 1, true},   // FC: M=out, N=batch
+        {384, 16, 1024, 1, EPI_COLMAJOR_PARTIAL, 1, 4, true}, // split-K partial planes
         // larger, SIMT-checked
         {6400, 64, 64, 64, EPI_ROWMAJOR, 1, 1, false},       // Winograd conv 64->64 @56x56, batch 64 rows /64
         {1152, 512, 512, 16, EPI_ROWMAJOR, 1, 1, false},
         {12544, 256, 64, 1, EPI_NCHW, 3136, 1, false},        // 1x1 conv 64->256 @56x56, 4 images
-        {4096, 64, 25088, 1, EPI_COLMAJOR_ATOMIC, 1, 8, false},  // VGG fc6 @ batch 64
+        {4096, 64, 25088, 1, EPI_COLMAJOR_PARTIAL, 1, 8, false},  // VGG fc6 @ batch 64
     };
     int fails = 0;
     for (const auto& c : cases)

@@ -149,14 +149,47 @@ def test_load_param_builds_the_blob_graph(tmp_path):
     ("7767516\n1 1\nInput data 0 1 data 0=4 1=4 2=1\n", -1),                                   # bad magic, utils.cpp:36-40
     ("7767517\n2 2\nInput data 0 1 data 0=4 1=4 2=1\nReLU r 1 1 nope out\n", -300),            # topology, net.cpp:127-131
     ("7767517\n2 2\nInput data 0 1 data 0=4 1=4 2=1\nFancyOp f 1 1 data out\n", -200),        # unregistered, net.cpp:107-111
-    ("7767517\n2 2\nInput data 0 1 data 0=4 1=4 2=1\nConvolution c 1 1 data out 0=4 1=3 2=2 6=36\n", -200),  # dilation
-    ("7767517\n2 2\nInput data 0 1 data 0=4 1=4 2=1\nEltwise e 1 1 data out 0=0\n", -100),     # PROD unsupported
+    ("7767517\n2 2\nInput data 0 1 data 0=4 1=4 2=1\nConvolution c 1 1 data out 0=4 1=3 8=1 6=36\n", -200),  # int8, conv_layer.h:49-54
+    ("7767517\n2 2\nInput data 0 1 data 0=4 1=4 2=1\nEltwise e 1 1 data out 0=7\n", -100),     # unknown Eltwise op
+    ("7767517\n2 2\nInput data 0 1 data 0=4 1=4 2=1\nEltwise e 1 1 data out 0=0 -23301=2,0.5,0.5\n", -100),  # coeffs only with SUM
+    ("7767517\n-3 2\nInput data 0 1 data 0=4 1=4 2=1\n", -1),                                   # corrupt counts
+    ("7767517\n1 1\nInput data 0 -5 data 0=4 1=4 2=1\n", -1),                                   # negative top count
 ])
 def test_load_param_rejects_like_the_reference(text, code):
     from feathercnn_b200.net import FeatherError
     with pytest.raises(FeatherError) as e:
         _net().LoadParamFromText(text)
     assert e.value.code == code
+
+
+@pytest.mark.parametrize("text", [
+    # what the reference rejects (conv_layer.h:43-47, eltwise_layer.h:57-66, avx/booster.cpp:304-308,
+    # concat_layer.h:50-54) loads here
+    "7767517\n2 2\nInput data 0 1 data 0=4 1=4 2=1\nConvolution c 1 1 data out 0=4 1=3 2=2 6=36\n",        # dilation 2
+    "7767517\n2 2\nInput data 0 1 data 0=8 1=8 2=8\nConvolution c 1 1 data out 0=16 1=3 7=4 6=288\n",      # 4 groups of 2 -> 4
+    "7767517\n3 3\nInput a 0 1 a 0=4 1=4 2=1\nInput b 0 1 b 0=4 1=4 2=1\nEltwise e 2 1 a b out 0=0\n",      # PROD
+    "7767517\n3 3\nInput a 0 1 a 0=4 1=4 2=1\nInput b 0 1 b 0=4 1=4 2=1\nEltwise e 2 1 a b out 0=2\n",      # MAX
+    "7767517\n3 3\nInput a 0 1 a 0=4 1=4 2=1\nInput b 0 1 b 0=4 1=4 2=1\nEltwise e 2 1 a b out 0=1 -23301=2,0.5,-2.0\n",
+    "7767517\n3 3\nInput a 0 1 a 0=4 1=4 2=1\nInput b 0 1 b 0=4 1=4 2=1\nConcat c 2 1 a b out 0=2\n",       # concat along w
+])
+def test_load_param_accepts_the_section_8f_extensions(text):
+    _net().LoadParamFromText(text)
+
+
+def test_truncated_or_corrupt_container_is_an_error_not_a_crash(tmp_path):
+    """InitFromBuffer on a short / corrupt .feathermodel must return an error code (the FILE path already did)."""
+    from feathercnn_b200.net import FeatherError
+    from feathercnn_b200.tools import feathermodel, modelgen
+    m = modelgen.mini()
+    param, binf = m.save(tmp_path / "mini")
+    blob = Path(feathermodel.pack(param, binf, tmp_path / "mini.feathermodel")).read_bytes()
+    for cut in (len(blob) - 1, len(blob) // 2, 24, 17):
+        with pytest.raises(FeatherError):
+            _net().InitFromBuffer(blob[:cut])
+    huge = bytearray(blob)
+    huge[8:16] = (2**64 - 8).to_bytes(8, "little")  # param_len that wraps 16 + param_len
+    with pytest.raises(FeatherError):
+        _net().InitFromBuffer(bytes(huge))
 
 
 RESNET_BLOCK = """7767517
