@@ -64,8 +64,12 @@ def fcuda() -> ctypes.CDLL:
             "fcuda_conv_init": (i, [P, i, vp, vp, vp]),
             "fcuda_conv_forward": (i, [P, i, vp, vp, vp, vp, vp, i, vp]),
             "fcuda_conv_forward_residual": (i, [P, i, vp, vp, vp, vp, vp, vp, i, i, vp]),
+            "fcuda_conv_can_pool": (i, [P, i]),
+            "fcuda_conv_forward_pool": (i, [P, i, vp, vp, vp, vp, vp, i, vp]),
             "fcuda_conv_forward_ext": (i, [P, i, vp, vp, vp, vp, vp, vp, i, i, i, i, vp]),
             "fcuda_eltwise_forward": (i, [vp, vp, vp, sz, i, ctypes.c_float, ctypes.c_float, i, vp]),
+            "fcuda_pixel_channels": (i, [i, ctypes.POINTER(i), ctypes.POINTER(i)]),
+            "fcuda_from_pixels": (i, [vp, vp, i, i, i, i, i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), i, vp]),
             "fcuda_tensor_gemm": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
             "fcuda_split_tf32": (i, [vp, vp, vp, sz, vp]),
             "fcuda_inner_product_get_buffer_size": (i, [i, i, i, szp, szp]),
@@ -117,6 +121,7 @@ def feather() -> ctypes.CDLL:
             "fnet_attach_weights": (i, [vp]),
             "fnet_feed_input_batch": (i, [vp, cp, vp, i, i, i, i]),
             "fnet_feed_input_device": (i, [vp, cp, vp, i, i, i, i]),
+            "fnet_feed_input_pixels": (i, [vp, cp, vp, i, i, i, i, i, i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
             "fnet_forward": (i, [vp]),
             "fnet_forward_batch": (i, [vp, vp, i]),
             "fnet_submit_batch": (i, [vp, vp, i, cp, vp]),

@@ -125,7 +125,8 @@ class ConvBooster:
 
 def conv_forward(param: ConvParam, x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None = None,
                  algo: int | None = None, residual: torch.Tensor | None = None,
-                 relu_after_add: bool = False, dilation: int = 1, tuned: bool = False) -> tuple[torch.Tensor, int]:
+                 relu_after_add: bool = False, dilation: int = 1, tuned: bool = False,
+                 pool: bool = False) -> tuple[torch.Tensor, int]:
     """Whole ConvBooster protocol for a batch x (N, IC, H, W) -> (N, OC, OH, OW).  Returns (output, algo).
     With `residual` (shaped like the output) the fused Eltwise-SUM entry point is used instead of Forward.
     `dilation` > 1 goes through fcuda_conv_forward_ext (the caller sets param.output_h/w for the dilated extent)."""
@@ -141,6 +142,13 @@ def conv_forward(param: ConvParam, x: torch.Tensor, w: torch.Tensor, b: torch.Te
     packed = torch.empty(max(packed_n, 1), device=x.device, dtype=torch.float32)
     scratch = torch.empty(max(scratch_n, 1), device=x.device, dtype=torch.float32)
     cb.Init(param, packed, w.contiguous())
+    if pool:  # fused trailing 2x2 / stride-2 max pooling: the output is the pooled blob
+        out = torch.empty((n, param.output_channels, (param.output_h + 1) // 2, (param.output_w + 1) // 2), device=x.device,
+                          dtype=torch.float32)
+        _check("fcuda_conv_forward_pool",
+               fcuda().fcuda_conv_forward_pool(ctypes.byref(param), cb.algo, _ptr(out), _ptr(x.contiguous()), _ptr(packed),
+                                               _ptr(scratch), _ptr(b), n, _stream()))
+        return out, cb.algo
     out = torch.empty((n, param.output_channels, param.output_h, param.output_w), device=x.device, dtype=torch.float32)
     if dilation > 1:
         _check("fcuda_conv_forward_ext",
@@ -179,6 +187,30 @@ def eltwise(a: torch.Tensor, b: torch.Tensor, op: int, ca: float = 1.0, cb: floa
     _check("fcuda_eltwise_forward",
            fcuda().fcuda_eltwise_forward(_ptr(out), _ptr(a.contiguous()), _ptr(b.contiguous()), a.numel(), op, ca, cb,
                                          int(relu), _stream()))
+    return out
+
+
+PIXEL_RGB, PIXEL_BGR, PIXEL_GRAY, PIXEL_RGBA = 1, 2, 4, 8  # ncnn pixel types (mat.h:126-129); conversion = from | (to << 16)
+
+
+def from_pixels(pixels: torch.Tensor, type_: int, target_w: int = 0, target_h: int = 0, mean=None, norm=None) -> torch.Tensor:
+    """(N, h, w[, c]) uint8 CUDA tensor -> (N, C, th, tw) fp32: from_pixels[_resize] + substract_mean_normalize on the GPU."""
+    import numpy as np
+    lib = fcuda()
+    assert pixels.is_cuda and pixels.dtype == torch.uint8 and pixels.is_contiguous()
+    n, h, w = pixels.shape[:3]
+    sc, oc = ctypes.c_int(), ctypes.c_int()
+    _check("fcuda_pixel_channels", lib.fcuda_pixel_channels(type_, ctypes.byref(sc), ctypes.byref(oc)))
+    assert pixels[0].numel() == h * w * sc.value
+    tw, th = target_w or w, target_h or h
+    out = torch.empty((n, oc.value, th, tw), device=pixels.device, dtype=torch.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    m = None if mean is None else np.ascontiguousarray(mean, np.float32)
+    s = None if norm is None else np.ascontiguousarray(norm, np.float32)
+    _check("fcuda_from_pixels",
+           lib.fcuda_from_pixels(_ptr(out), ctypes.c_void_p(pixels.data_ptr()), type_, w, h, tw, th,
+                                 None if m is None else m.ctypes.data_as(fp), None if s is None else s.ctypes.data_as(fp), n,
+                                 _stream()))
     return out
 
 

@@ -5,7 +5,10 @@
 // avx/booster.cpp:105-118) and of im2col + packed SGEMM (avx/booster.cpp:83-102) with a Blackwell formulation that
 // has NO intermediate in HBM and not even an A tile in shared memory:
 //
-//   D[pixel][oc] = sum_k  A[pixel][k] * Wp[oc][k],    k = (u*KW + v)*IC + ic,
+//   D[pixel][oc] = sum_k  A[pixel][k] * Wp[oc][k],    k = (u*KW + v)*IC + ic   (IC % 32 != 0)
+//                                                      k = ((ic/32)*KH*KW + u*KW + v)*32 + ic%32   (IC % 32 == 0: a k-block
+//                                                      is one tap x 32 channels, taps innermost so that the 3x3 slab
+//                                                      producer below serves all nine taps of a channel block from one slab)
 //   A[pixel][k]  = X[n][ic][oy*s+u-pad][ox*s+v-pad]   (0 outside the image: the im2col rule, generic_kernels.cpp:66-67)
 //
 //   M tile     = 128 output pixels = four 32-pixel row segments ("boxes", consecutive in (n, oy, ox/32) order);
@@ -34,6 +37,8 @@
 #include "conv_igemm.cuh"
 
 #include "common.cuh"
+
+#include <stdlib.h>
 #include "tcgen05.cuh"
 
 namespace fcuda {
@@ -104,6 +109,12 @@ struct IgemmArgs {
     int num_n;               // ceil(OC / BN)
     long long pixel_tiles;   // ceil(total_boxes / 4)
     int relu;
+    int issuers;             // MMA issuer threads: 2 when BN <= 64 and the tile has >= 2 k-blocks, else 1
+    int acc_stride;          // TMEM columns per accumulator slot: BN, or 2*BN with two issuers (one accumulator each)
+    int acc_slots;           // accumulator ring depth = accumulator columns / acc_stride (power of two, <= 4)
+    int pool;                // SLAB only: fuse a following 2x2 / stride-2 max pooling; `out` is the pooled blob
+    int taps;                // KH*KW
+    unsigned tap_inv;        // ceil(65536 / KW): tap / KW == (tap * tap_inv) >> 16 for tap < 64
 };
 
 struct BoxCoord { int n, oy, ox0; bool valid; };
@@ -123,6 +134,54 @@ __device__ __forceinline__ BoxCoord decode_box(uint32_t b, const IgemmArgs& a) {
     c.oy = static_cast<int>(oy);
     c.ox0 = static_cast<int>(rem - oy * static_cast<uint32_t>(a.bpr)) * 32;
     return c;
+}
+
+// SLAB mode: a tile is a 4-row x 32-column patch of one image, tiles enumerated as (n, oy/4, ox/32); args.per_img =
+// ceil(OH/4) * bpr tiles per image, args.total_boxes = 4 * number of tiles.  Warp (TMEM quadrant) q covers the 2 x 16
+// sub-patch rows 2*(q>>1) .. +1, columns 16*(q&1) .. +15: lane l = row (l >> 4), column (l & 15).  Both pixels of a 2x2
+// pooling window then sit in ONE warp (lane ^ 16, lane ^ 1) and the epilogue can pool with two shuffles.
+__device__ __forceinline__ BoxCoord decode_patch(uint32_t ptile, const IgemmArgs& a) {  // oy / ox0 = patch origin
+    BoxCoord c;
+    const uint32_t n = fast_div(ptile, a.m_per_img, a.per_img);
+    const uint32_t rem = ptile - n * static_cast<uint32_t>(a.per_img);
+    const uint32_t ty = fast_div(rem, a.m_bpr, a.bpr);
+    c.n = static_cast<int>(n);
+    c.oy = static_cast<int>(ty) * 4;
+    c.ox0 = static_cast<int>(rem - ty * static_cast<uint32_t>(a.bpr)) * 32;
+    c.valid = ptile * 4u < static_cast<uint32_t>(a.total_boxes);
+    return c;
+}
+__device__ __forceinline__ int patch_row(int q, int lane) { return 2 * (q >> 1) + (lane >> 4); }
+__device__ __forceinline__ int patch_col(int q, int lane) { return 16 * (q & 1) + (lane & 15); }
+
+// 3x3 / stride-1 slab: 32 channels x 6 rows x 34 columns of (hi, lo) pairs = the input halo of a 4 x 32 output patch
+constexpr int kSlabRows = 6, kSlabCols = 34;
+constexpr int kSlabChStride = kSlabRows * kSlabCols;          // float2 elements per channel
+constexpr int kSlabBytes = 32 * kSlabChStride * 8;            // 52,224 B
+constexpr int kProducerThreads = 4 * kGroups * 32;            // 384
+
+// Ring-slot release.  A producer group visits only every third k-block and the two MMA issuers retire their k-blocks
+// independently of each other, so with ONE mbarrier per slot "the MMAs of k-block g-4 have retired" cannot be read off the
+// parity: a group whose last visit to the slot was three rounds ago sees the same parity when the lagging issuer is
+// still two rounds behind (observed with the fast slab producers: an unconsumed A tile was overwritten).  Each slot
+// therefore has TWO release barriers used by alternating rounds (round = g / STAGES): the barrier of round r completes a
+// phase every second round, so its parity distinguishes rounds r, r+2 and r-2, and being four rounds ahead is impossible —
+// the group's previous k-blocks g-3, g-6 needed slots released by BOTH issuers (odd and even k-blocks), each of which
+// retires in order.  Waiting too long cannot happen either: the barrier only advances again after g itself is consumed.
+template <int STAGES>
+__device__ __forceinline__ uint64_t* ring_release_bar(uint64_t (*empty_bar)[STAGES], uint32_t g) {
+    return &empty_bar[(g / STAGES) & 1u][g & (STAGES - 1)];
+}
+template <int STAGES>
+__device__ __forceinline__ void wait_ring_slot_free(uint64_t (*empty_bar)[STAGES], uint32_t g) {
+    if (g >= STAGES) {
+        const uint32_t gg = g - STAGES;  // the k-block that used this slot one round earlier
+        ptx::mbar_wait(ring_release_bar<STAGES>(empty_bar, gg), ((gg / STAGES) >> 1) & 1u);
+    }
+}
+
+__device__ __forceinline__ void producer_bar_sync() {  // named barrier 1: the twelve producer warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
 }
 
 // D[tmem] (+)= A[tmem] * B[smem]
@@ -146,7 +205,7 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int BN, int PLANES>
+template <int BN, int PLANES, bool SLAB>
 __global__ void __launch_bounds__(kThreadsIg, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
                   const IgemmArgs args) {
@@ -156,8 +215,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // accumulator ring: as deep as tensor memory allows next to the A ring (4 x 64 columns in 3xTF32 mode).  Tiles with few
     // k-blocks (IC = 3, pointwise layers) are a latency chain gather -> MMA -> epilogue; with 2 slots conv1_1 of VGG
     // spent 3.8k cycles per tile for ~1k cycles of work in any one role.
-    constexpr int ACC = BN <= 64 ? 4 : 2;
-    constexpr uint32_t kAccCols = ACC * BN;
+    constexpr int ACC = 4;                                  // barrier array size; args.acc_slots (<= 4) slots are in use
+    constexpr uint32_t kAccCols = BN <= 64 ? 256 : 2 * BN;  // carved at run time into args.acc_slots slots of args.acc_stride
     constexpr uint32_t kAStageCols = 32 * PLANES;           // [A_hi (32 cols)][A_lo (32 cols)]
     constexpr uint32_t kNeedCols = kAccCols + STAGES * kAStageCols;
     constexpr uint32_t kTmemCols = kNeedCols <= 32 ? 32 : kNeedCols <= 64 ? 64 : kNeedCols <= 128 ? 128 : kNeedCols <= 256 ? 256 : 512;
@@ -170,11 +229,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // one barrier per ring slot covers both operands: 4 arrivals of the owning producer group (A in tensor memory)
     // + 1 arrive.expect_tx of the TMA warp (B bytes landed) -> the MMA thread makes ONE wait per k-block
     __shared__ uint64_t full_bar[STAGES];
-    __shared__ uint64_t empty_bar[STAGES];    // MMAs that read the stage have retired
+    __shared__ uint64_t empty_bar[2][STAGES];  // MMAs that read the stage have retired; [round parity][slot], see wait_ring_slot_free
     __shared__ uint64_t tmem_full_bar[ACC];
     __shared__ uint64_t tmem_empty_bar[ACC];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ volatile uint32_t issued_g;  // k-blocks whose MMAs have been issued (hand-off between the two issuers)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -183,13 +241,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int plane = args.H * args.W;
 
     if (threadIdx.x == 0) {
-        issued_g = 0;
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 5);
-            ptx::mbar_init(&empty_bar[s], 1);
+            ptx::mbar_init(&empty_bar[0][s], 1);
+            ptx::mbar_init(&empty_bar[1][s], 1);
         }
         for (int s = 0; s < ACC; ++s) {
-            ptx::mbar_init(&tmem_full_bar[s], 1);
+            ptx::mbar_init(&tmem_full_bar[s], static_cast<uint32_t>(args.issuers));  // every issuer commits its own MMAs
             ptx::mbar_init(&tmem_empty_bar[s], 4);
         }
         ptx::fence_barrier_init();
@@ -211,6 +269,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
     // bias copy (zeros when the layer has none): the epilogue reads it with broadcast LDS.128
     float* bias_s = reinterpret_cast<float*>(smem + STAGES * kStage + (args.use_table ? kblocks * 32 * 8 : 0));
+    // SLAB: one (BN = 128) or two (BN <= 64) input slabs behind the bias copy, 16-byte aligned
+    constexpr int NSLAB = BN <= 64 ? 2 : 1;
+    float2* slab0 = reinterpret_cast<float2*>(smem + STAGES * kStage + ((args.oc_pad * 4 + 15) & ~15));
     for (int i = threadIdx.x; i < args.oc_pad; i += kThreadsIg)
         bias_s[i] = (args.bias != nullptr && i < args.OC) ? __ldg(args.bias + i) : 0.f;
     if (warp == kWarpMma) {
@@ -233,7 +294,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const uint32_t pt = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
             const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - pt * static_cast<uint32_t>(args.num_n));
             for (int kb = 0; kb < kblocks; ++kb, ++gb) {
-                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                wait_ring_slot_free<STAGES>(empty_bar, gb);
                 IG_TRACE(8, gb);
                 if (leader) {
                     uint8_t* st = smem + stage * kStage;
@@ -251,37 +312,41 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // executes in N/2 cycles; the pipe holds ~6 MMAs and ISSUE BLOCKS beyond that; a pipe that has run dry needs
         // ~390 cycles before the next MMA completes; and the scalar work of one k-block (barrier wait, fence,
         // descriptor arithmetic, commit, loop) is ~300-400 cycles of dependent single-thread issue.  One issuer therefore
-        // leaves the pipe idle about half of the time at N=64.  With two issuers, one thread's scalar work overlaps
-        // the other's (blocking) MMA issue; the hand-off is a shared-memory counter, ~50 cycles against the ~190
-        // cycles of work still queued when an issuer finishes.  k-block g (running over this CTA's tiles) belongs to
-        // issuer g & 1; MMAs into one accumulator execute in issue order, so the overwrite of the tile's first MMA and
-        // the commit of its last MMA cover both threads' work.
+        // leaves the pipe idle about half of the time at N = 64, so two threads alternate k-blocks there.
+        // Round 2: each issuer accumulates into ITS OWN accumulator (even k-blocks -> columns [0, BN), odd -> [BN, 2BN) of
+        // the slot) and the epilogue adds the two.  Round 1 let both threads accumulate into one accumulator, handing
+        // the issue order over through a shared counter; the determinism probe (scripts/determinism_probe.py) showed the
+        // tensor pipe does not keep MMAs of two issuing warps in issue order — results differed run to run in the last
+        // bit (fp32 summation order), and an overtaken accumulate=0 MMA would have been a silent wrong result.  With
+        // disjoint accumulators there is no cross-thread ordering left: each thread's commit covers exactly its own MMAs.
         if (ptx::elect_one()) {
             constexpr uint32_t idesc = make_idesc_tf32(BN);
             const uint64_t dB0 = make_smem_desc_sw128(ptx::smem_u32(smem));
-            uint32_t g = static_cast<uint32_t>(warp - kWarpMma);
+            const uint32_t me = static_cast<uint32_t>(warp - kWarpMma);
+            const uint32_t nissue = static_cast<uint32_t>(args.issuers);
+            uint32_t g = me;
             long long tile = blockIdx.x;
-            int kb = static_cast<int>(g);
+            int kb = static_cast<int>(me);
             uint32_t it = 0;
+            if (me >= nissue) tile = total_tiles;  // single-issuer launch: the second issuer idles
             for (;;) {
                 while (kb >= kblocks && tile < total_tiles) { kb -= kblocks; tile += gridDim.x; ++it; }
                 if (tile >= total_tiles) break;
                 const int stage = static_cast<int>(g & (STAGES - 1));
                 const uint32_t phase = (g / STAGES) & 1u;
-                const uint32_t as = it & (ACC - 1);
-                const uint32_t tmem_d = tmem_base + as * BN;
+                const uint32_t as = it & static_cast<uint32_t>(args.acc_slots - 1);
+                const uint32_t tmem_d = tmem_base + as * static_cast<uint32_t>(args.acc_stride) + me * BN;
                 const uint64_t dB = dB0 + static_cast<uint64_t>(stage * (kStage >> 4));
                 const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
                 const uint32_t ta = tmem_a0 + stage * kAStageCols;
-                if (kb == 0) ptx::mbar_wait(&tmem_empty_bar[as], ((it / ACC) & 1u) ^ 1u);
+                const bool first_visit = kb < static_cast<int>(nissue);  // this thread's first k-block of the tile
+                if (first_visit) ptx::mbar_wait(&tmem_empty_bar[as], ((it / static_cast<uint32_t>(args.acc_slots)) & 1u) ^ 1u);
                 ptx::mbar_wait(&full_bar[stage], phase);
                 IG_TRACE_T(5, g);
-                while (issued_g < g) {}  // the other issuer has put k-block g-1 into the pipe
-                IG_TRACE_T(6, g);
                 ptx::tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {  // 8 k-values (TMEM columns / 32 smem bytes) per MMA
-                    const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+                    const uint32_t first = (first_visit && k == 0) ? 0u : 1u;
                     if (PLANES == 2) {
                         umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);   // A_lo * B_hi
                         umma_tf32_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_hi * B_lo
@@ -290,15 +355,127 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, first);
                     }
                 }
-                issued_g = g + 1;
-                ptx::umma_commit(&empty_bar[stage]);
-                if (kb == kblocks - 1) ptx::umma_commit(&tmem_full_bar[as]);
+                ptx::umma_commit(ring_release_bar<STAGES>(empty_bar, g));
+                if (kb + static_cast<int>(nissue) >= kblocks) ptx::umma_commit(&tmem_full_bar[as]);  // my last k-block here
                 IG_TRACE_T(7, g);
-                g += kIssuers;
-                kb += kIssuers;
+                g += nissue;
+                kb += static_cast<int>(nissue);
             }
         }
-    } else if (warp >= 4) {
+    } else if (SLAB && warp >= 4) {
+        // ===================== A producers, 3x3 stride-1 slab variant =====================
+        // The generic producers below gather every k-block from global memory and split it, i.e. each input element
+        // is loaded and split NINE times (once per tap) at 4.3 instructions per element — the issue-bound part of VGG
+        // conv1_2 (tensor pipe 59 %).  Here the twelve producer warps first stage the halo of the tile's 4 x 32 output
+        // patch for one 32-channel block — 6 rows x 34 columns x 32 channels — into shared memory ONCE, already split
+        // into (hi, lo) pairs (coalesced LDG along x, one STS.64 per element; zero padding and image edges by predicate);
+        // the nine taps are then 32 LDS.64 + 8 tcgen05.st per thread and k-block, addresses = one base + immediates.
+        // Item = (tile, channel block); its 9 k-blocks go round-robin to the 3 groups, so group g always serves the taps
+        // of kernel COLUMN g (v = g, u = 0..2).  Loads of item j+1 are in flight while the taps of item j run.
+        const int pt = static_cast<int>(threadIdx.x) - 128;   // 0..383
+        const int pw = warp - 4;                               // 0..11
+        const int group = pw >> 2;
+        const int q = warp & 3;
+        const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+        const int cblocks = args.IC >> 5;
+        const uint32_t plane_bytes = static_cast<uint32_t>(plane) * 4u;
+        // fill roles: warp pw stages slab row fr of channels fc0 .. fc0+15 (lane = column 0..31); thread pt additionally
+        // stages ONE element of the two tail columns: line (pt >> 1) = channel * 6 + row, column 32 + (pt & 1)
+        const int fr = pw % kSlabRows, fc0 = (pw / kSlabRows) * 16;
+        const int tl_line = pt >> 1, tl_c = 32 + (pt & 1);
+        const int tl_cl = tl_line / kSlabRows, tl_r = tl_line - tl_cl * kSlabRows;
+
+        long long tile = blockIdx.x;
+        int cb = 0;
+        bool have = tile < total_tiles;
+        float v[16], vt = 0.f;
+        auto load_item = [&](long long t, int cbl) {
+            const uint32_t ptile = fast_div(static_cast<uint32_t>(t), args.m_num_n, args.num_n);
+            const BoxCoord bx = decode_patch(ptile, args);
+            const bool tile_ok = bx.valid;
+            const float* img = args.in + (static_cast<long long>(tile_ok ? bx.n : 0) * args.in_img_c + cbl * 32) * plane;
+            const int iy0 = bx.oy - args.pad_top, ix0 = bx.ox0 - args.pad_left;
+            {
+                const int iy = iy0 + fr, ix = ix0 + lane;
+                const bool ok = tile_ok && static_cast<unsigned>(iy) < static_cast<unsigned>(args.H) &&
+                                static_cast<unsigned>(ix) < static_cast<unsigned>(args.W);
+                const char* p = reinterpret_cast<const char*>(img + static_cast<long long>(fc0) * plane +
+                                                              static_cast<long long>(iy) * args.W + ix);
+                asm volatile("" : "+l"(p));  // opaque base: one IMAD.WIDE per load
+                if (__all_sync(0xffffffffu, ok)) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        v[i] = __ldg(reinterpret_cast<const float*>(p + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(i)));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        v[i] = ok ? __ldg(reinterpret_cast<const float*>(p + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(i))) : 0.f;
+                }
+            }
+            {
+                const int iy = iy0 + tl_r, ix = ix0 + tl_c;
+                const bool ok = tile_ok && static_cast<unsigned>(iy) < static_cast<unsigned>(args.H) &&
+                                static_cast<unsigned>(ix) < static_cast<unsigned>(args.W);
+                vt = ok ? __ldg(img + static_cast<long long>(tl_cl) * plane + static_cast<long long>(iy) * args.W + ix) : 0.f;
+            }
+        };
+        auto split_pair = [](float x) {
+            float2 r;
+            r.x = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+            r.y = PLANES == 2 ? x - r.x : 0.f;
+            if (PLANES == 1) r.x = x;
+            return r;
+        };
+
+        if (have) load_item(tile, cb);
+        uint32_t j = 0;  // running item index of this CTA; its k-blocks are 9j .. 9j+8
+        while (have) {
+            float2* slab = slab0 + (NSLAB == 2 ? (j & 1u) : 0u) * (kSlabBytes / 8);
+            if (NSLAB == 1) producer_bar_sync();  // single slab: every group has finished the taps of item j-1
+            {
+                float2* sp = slab + (fc0 * kSlabRows + fr) * kSlabCols + lane;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sp[i * kSlabChStride] = split_pair(v[i]);
+                slab[tl_line * kSlabCols + tl_c] = split_pair(vt);
+            }
+            producer_bar_sync();  // item j is staged (two slabs: this also orders the taps of j-1 before the fill of j+1)
+            // cursor to the next item; its loads fly while this item's taps run
+            int ncb = cb + 1;
+            long long ntile = tile;
+            if (ncb == cblocks) { ncb = 0; ntile += gridDim.x; }
+            const bool nhave = ntile < total_tiles;
+            if (nhave) load_item(ntile, ncb);
+            // taps (u, v = group) for u = 0..2: k-block 9j + 3u + group
+            const char* tb = reinterpret_cast<const char*>(slab + patch_row(q, lane) * kSlabCols + patch_col(q, lane) + group);
+#pragma unroll 1
+            for (int u = 0; u < 3; ++u) {
+                const uint32_t g = j * 9u + static_cast<uint32_t>(3 * u + group);
+                const int my_stage = static_cast<int>(g & (STAGES - 1));
+                const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
+                const char* src = tb + u * (kSlabCols * 8);
+                wait_ring_slot_free<STAGES>(empty_bar, g);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int part = 0; part < 4; ++part) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const float2 e = *reinterpret_cast<const float2*>(src + (part * 8 + r) * (kSlabChStride * 8));
+                        hi[r] = __float_as_uint(e.x);
+                        lo[r] = __float_as_uint(e.y);
+                    }
+                    tmem_st_32x8(ta + part * 8, hi);
+                    if (PLANES == 2) tmem_st_32x8(ta + 32 + part * 8, lo);
+                }
+                tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&full_bar[my_stage]);
+            }
+            tile = ntile; cb = ncb; have = nhave;
+            ++j;
+        }
+    } else if (!SLAB && warp >= 4) {
         // ===================== A producers: gather + 3xTF32 split -> tensor memory =====================
         // k-block number g (running over all tiles of this CTA) belongs to group g % kGroups and ring slot
         // g % STAGES; a group visits only its own k-blocks.  The group is latency-bound, not issue-bound (a gather
@@ -308,7 +485,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int group = (warp - 4) >> 2;
         const int q = warp & 3;  // TMEM lane quadrant this warp may write == box index inside the tile
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-        const int cblocks = args.IC >> 5;                              // fast path only
         const uint32_t plane_bytes = static_cast<uint32_t>(plane) * 4u;  // host guarantees H*W < 2^30
         const int kb_mod = kblocks % kGroups;
 
@@ -317,7 +493,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         uint32_t g0 = 0;   // running index of the current tile's k-block 0
         int g0_mod = 0;    // g0 % kGroups
         int kb = 0;
-        int tap = 0, tu = 0, tv = 0, cb = 0;  // fast path: k-block kb = tap * cblocks + cb, tap = tu*KW + tv
+        int tap = 0, tu = 0, tv = 0, cb = 0;  // fast path: k-block kb = cb * taps + tap, tap = tu*KW + tv
         const float* base = args.in;
         unsigned long long tapmask = 0;  // bit (u*KW+v) set <=> that tap of this lane's pixel lies inside the image
         bool have = false;
@@ -352,11 +528,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             base = args.in + (static_cast<long long>(bx.valid ? bx.n : 0) * args.in_img_c) * plane +
                    static_cast<long long>(iy0) * args.W + ix0;
             asm volatile("" : "+l"(base));  // opaque: see gather()
-            tap = 0; tu = 0; tv = 0; cb = kb;
+            cb = 0; tap = kb;  // kb < kGroups here; gather() normalises
         };
         auto advance = [&]() {
             kb += kGroups;
-            cb += kGroups;
+            tap += kGroups;
             if (kb >= kblocks) {
                 tile += gridDim.x;
                 g0 += static_cast<uint32_t>(kblocks);
@@ -371,11 +547,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 // IC % 32 == 0: the whole k-block is one tap -> one predicate; the 32 channel addresses are
                 // kp + r*plane_bytes, one IMAD.WIDE each off an opaque pointer (otherwise nvcc re-derives every
                 // address from args.in with ~8 integer instructions per load)
-                while (cb >= cblocks) {
-                    cb -= cblocks;
-                    ++tap;
-                    if (++tv == args.KW) { tv = 0; ++tu; }
-                }
+                while (tap >= args.taps) { tap -= args.taps; ++cb; }
+                tu = static_cast<int>((static_cast<unsigned>(tap) * args.tap_inv) >> 16);
+                tv = tap - tu * args.KW;
                 const char* kp = reinterpret_cast<const char*>(base) +
                                  (static_cast<long long>(cb * 32) * plane + tu * args.dil_h * args.W + tv * args.dil_w) * 4;
                 asm volatile("" : "+l"(kp));
@@ -407,10 +581,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         while (have) {
             const uint32_t g = g0 + static_cast<uint32_t>(kb);
             const int my_stage = static_cast<int>(g & (STAGES - 1));
-            const uint32_t my_phase = (g / STAGES) & 1u;
             const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
             if (q == 0) IG_TRACE(0, g);
-            ptx::mbar_wait(&empty_bar[my_stage], my_phase ^ 1);
+            wait_ring_slot_free<STAGES>(empty_bar, g);
             if (q == 0) IG_TRACE(1, g);
             ptx::tc_fence_after();
 #pragma unroll
@@ -448,28 +621,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // ===================== epilogue (warps 0..3) =====================
         const int q = warp & 3;
         const float floor_v = args.relu ? 0.f : -INFINITY;
-        const uint32_t oplane_bytes = static_cast<uint32_t>(args.OH * args.OW) * 4u;  // host: OH*OW < 2^30
+        // geometry of the blob that is stored: the convolution output, or (SLAB, args.pool) its 2x2 / stride-2 max pooling
+        const bool pool = SLAB && args.pool != 0;
+        const int SH = pool ? (args.OH + 1) >> 1 : args.OH, SW = pool ? (args.OW + 1) >> 1 : args.OW;
+        const uint32_t oplane_bytes = static_cast<uint32_t>(SH * SW) * 4u;  // host: OH*OW < 2^30
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
             const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - ptile * static_cast<uint32_t>(args.num_n));
-            const uint32_t as = it & (ACC - 1);
-            const uint32_t aphase = (it / ACC) & 1u;
-            const BoxCoord bx = decode_box(ptile * 4 + q, args);  // this warp's 32 TMEM lanes are box q
-            const int ox = bx.ox0 + lane;
-            const bool ok = bx.valid && ox < args.OW;
-            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-            const size_t oplane = static_cast<size_t>(args.OH) * args.OW;
+            const uint32_t as = it & static_cast<uint32_t>(args.acc_slots - 1);
+            const uint32_t aphase = (it / static_cast<uint32_t>(args.acc_slots)) & 1u;
+            // this warp's 32 TMEM lanes: box q (32 pixels of one row), or in SLAB mode a 2 x 16 sub-patch of the tile
+            const BoxCoord bx = SLAB ? decode_patch(ptile, args) : decode_box(ptile * 4 + q, args);
+            const int oy = SLAB ? bx.oy + patch_row(q, lane) : bx.oy;
+            const int ox = SLAB ? bx.ox0 + patch_col(q, lane) : bx.ox0 + lane;
+            const bool ok = bx.valid && ox < args.OW && oy < args.OH;
+            const int sy = pool ? oy >> 1 : oy, sx = pool ? ox >> 1 : ox;  // where this lane stores
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * static_cast<uint32_t>(args.acc_stride);
+            const bool dual = args.issuers == 2;  // second issuer's accumulator sits BN columns further
+            const size_t oplane = static_cast<size_t>(SH) * SW;
             if (args.residual != nullptr && bx.valid) {
                 // The fused Eltwise addend comes from HBM; a load issued after the accumulator is ready would put its
                 // ~1k-cycle latency on every 32-column chunk (measured: ResNet-50 8.3 -> 12.0 ms per step).  Each lane
                 // prefetches whole 128-byte channel rows of this warp's box while the MMAs of the tile are still running.
+                const int prow = SLAB ? min(bx.oy + 2 * (q >> 1), args.OH - 1) : bx.oy, pcol = SLAB ? bx.ox0 + 16 * (q & 1) : bx.ox0;
                 const char* rbase = reinterpret_cast<const char*>(args.residual + (static_cast<size_t>(bx.n) * args.out_img_c) * oplane +
-                                                                 static_cast<size_t>(bx.oy) * args.OW + bx.ox0);
+                                                                 static_cast<size_t>(prow) * args.OW + pcol);
                 for (int c = lane; c < BN; c += 32) {
                     const int oc = n_blk * BN + c;
-                    if (oc < args.OC)
+                    if (oc < args.OC) {
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(rbase + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(oc)));
+                        if (SLAB && prow + 1 < args.OH)  // the sub-patch's second row
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(rbase + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(oc) + static_cast<unsigned long long>(args.OW) * 4ull));
+                    }
                 }
             }
             ptx::mbar_wait_relaxed<200>(&tmem_full_bar[as], aphase);
@@ -482,7 +666,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(taddr0 + c0, r);
                 char* dst = reinterpret_cast<char*>(args.out + (static_cast<size_t>(ok ? bx.n : 0) * args.out_img_c + oc0) * oplane +
-                                                    static_cast<size_t>(bx.oy) * args.OW + ox);
+                                                    static_cast<size_t>(sy) * SW + sx);
                 asm volatile("" : "+l"(dst));  // one IMAD.WIDE per store off an opaque base
                 // fused Eltwise SUM: the other addend sits at the same NCHW position
                 const long long res_off = args.residual ? reinterpret_cast<const char*>(args.residual) - reinterpret_cast<const char*>(args.out) : 0;
@@ -506,7 +690,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     }
                 }
                 ptx::tmem_ld_wait();
-                if (ok) {
+                if (dual) {
+                    // even-k-block accumulator, then the odd-k-block one, folded in this fixed order (one register set:
+                    // both accumulators live at once would spill next to the residual)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) res[j] += __uint_as_float(r[j]);
+                    ptx::tmem_ld_32x32(taddr0 + BN + c0, r);
+                    ptx::tmem_ld_wait();
+                }
+                if (pool) {
+                    // 2x2 / stride-2 max pooling of the sub-patch (pooling_layer.h:38-91, pad 0): the window of the pixel at
+                    // an even (row, column) is lanes {l, l^1, l^16, l^17}; pixels outside the image hold -inf.  max commutes
+                    // with the per-channel bias and with ReLU, so both are applied to the pooled value.
+                    const bool writer = ok && (lane & 17) == 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float v = ok ? __uint_as_float(r[j]) + res[j] : -INFINITY;
+                        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+                        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+                        if (writer && oc0 + j < args.OC)
+                            *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(j)) =
+                                fmaxf(v + bias_s[oc0 + j], floor_v);
+                    }
+                } else if (ok) {
                     if (oc0 + 32 <= args.OC) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
@@ -516,7 +722,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                             for (int e = 0; e < 4; ++e) {
                                 const int j = j4 * 4 + e;
                                 *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(j)) =
-                                    fmaxf(__uint_as_float(r[j]) + bb[e] + res[j], floor_v);
+                                    fmaxf(__uint_as_float(r[j]) + res[j] + bb[e], floor_v);
                             }
                         }
                     } else {
@@ -524,7 +730,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         for (int j = 0; j < 32; ++j)
                             if (oc0 + j < args.OC)
                                 *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(j)) =
-                                    fmaxf(__uint_as_float(r[j]) + bias_s[oc0 + j] + res[j], floor_v);
+                                    fmaxf(__uint_as_float(r[j]) + res[j] + bias_s[oc0 + j], floor_v);
                     }
                 }
             }
@@ -554,7 +760,16 @@ igemm_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, f
     const int oc = static_cast<int>(idx / Kf);
     float v = 0.f;
     if (k < IC * taps) {
-        const int tap = k / IC, ic = k - tap * IC;
+        int tap, ic;
+        if (IC % 32 == 0) {  // k = (cb * taps + tap) * 32 + ic % 32
+            const int kb = k >> 5;
+            const int cb = kb / taps;
+            tap = kb - cb * taps;
+            ic = cb * 32 + (k & 31);
+        } else {             // k = tap * IC + ic
+            tap = k / IC;
+            ic = k - tap * IC;
+        }
         v = w[(static_cast<size_t>(oc) * IC + ic) * taps + tap];
     }
     if (lo) {
@@ -567,7 +782,7 @@ igemm_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, f
     }
 }
 
-template <int BN, int PLANES>
+template <int BN, int PLANES, bool SLAB>
 int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return FCUDA_ERR_CUDA;
@@ -602,8 +817,11 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     a.kblocks = ceil_div(K, 32);
     a.use_table = (p.IC % 32 == 0) ? 0 : 1;
     a.bpr = ceil_div(p.OW, 32);
-    a.per_img = p.OH * a.bpr;
-    a.total_boxes = static_cast<long long>(p.N) * p.OH * a.bpr;
+    a.per_img = (SLAB ? ceil_div(p.OH, 4) : p.OH) * a.bpr;  // SLAB: tiles (4 x 32 patches) per image, else boxes per image
+    a.total_boxes = static_cast<long long>(p.N) * a.per_img * (SLAB ? 4 : 1);
+    a.pool = SLAB ? p.pool : 0;
+    a.taps = taps;
+    a.tap_inv = (65536u + static_cast<unsigned>(p.KW) - 1u) / static_cast<unsigned>(p.KW);
     auto magic = [](int d) { return d > 1 ? ~0ull / static_cast<unsigned long long>(d) + 1ull : 0ull; };
     a.m_per_img = magic(a.per_img);
     a.m_bpr = magic(a.bpr);
@@ -616,13 +834,22 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
         static_cast<long long>(p.H) * p.W >= (1ll << 30) || static_cast<long long>(p.OH) * p.OW >= (1ll << 30))
         return -1;
     a.relu = p.relu;
+    // two issuers (one accumulator each) where one thread cannot keep the pipe fed: N <= 64 and at least four k-blocks
+    // per tile (short-K tiles are epilogue-bound and would only pay the second accumulator read); BN = 128 has 768 cycles of MMA work per k-block against ~350 of issue work, and only 256 accumulator
+    // columns.  FCUDA_IGEMM_ISSUERS=1 forces one issuer (diagnostic).
+    static const int issuers_env = [] { const char* e = getenv("FCUDA_IGEMM_ISSUERS"); return (e && e[0] == '1') ? 1 : kIssuers; }();
+    a.issuers = (BN <= 64 && a.kblocks >= 4) ? issuers_env : 1;
+    a.acc_stride = a.issuers == 2 ? 2 * BN : BN;
+    a.acc_slots = (BN <= 64 ? 256 : 2 * BN) / a.acc_stride;
+    if (a.acc_slots > 4) a.acc_slots = 4;
     const long long total = a.pixel_tiles * a.num_n;
     const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
     constexpr int kStage = PLANES * BN * 32 * 4;
     const int table_bytes = a.use_table ? a.kblocks * 32 * 8 : 0;
-    const int smem = kStagesIg * kStage + table_bytes + a.oc_pad * 4 + 1024;
+    constexpr int kSlabs = BN <= 64 ? 2 : 1;
+    const int smem = kStagesIg * kStage + table_bytes + ((a.oc_pad * 4 + 15) & ~15) + (SLAB ? kSlabs * kSlabBytes : 0) + 1024;
     if (smem > 227 * 1024 - 2048) return -1;
-    auto kern = conv_igemm_kernel<BN, PLANES>;
+    auto kern = conv_igemm_kernel<BN, PLANES, SLAB>;
     static SmemAttrCache attr_cache;
     if (int rc = ensure_dynamic_smem(kern, smem, attr_cache)) return rc;
     // algorithmic work of the layer: direct-convolution FLOPs; input + filters read once, output written once
@@ -659,12 +886,27 @@ int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, in
     return 0;
 }
 
+// 3x3, stride 1, dense taps, whole 32-channel blocks: the slab producer (FCUDA_IGEMM_SLAB=0 keeps the generic gather)
+static bool slab_eligible(const IgemmProblem& p) {
+    static const bool off = [] { const char* e = getenv("FCUDA_IGEMM_SLAB"); return e && e[0] == '0'; }();
+    return !off && p.KH == 3 && p.KW == 3 && p.stride_h == 1 && p.stride_w == 1 && p.dil_h <= 1 && p.dil_w <= 1 &&
+           p.IC % 32 == 0 && p.pad_top <= 2 && p.pad_left <= 2;
+}
+
+bool conv_igemm_can_pool(const IgemmProblem& p) { return slab_eligible(p) && p.residual == nullptr; }
+
 int conv_igemm_forward(const IgemmProblem& p, cudaStream_t stream) {
     if (!conv_igemm_supported(p.IC, p.KH, p.KW)) return -1;
+    if (p.pool && !conv_igemm_can_pool(p)) return -200;
     const bool x3 = p.planes == 2;
-    if (p.OC <= 32) return x3 ? launch_igemm<32, 2>(p, stream) : launch_igemm<32, 1>(p, stream);
-    if (p.OC <= 64) return x3 ? launch_igemm<64, 2>(p, stream) : launch_igemm<64, 1>(p, stream);
-    return x3 ? launch_igemm<128, 2>(p, stream) : launch_igemm<128, 1>(p, stream);
+    if (slab_eligible(p)) {
+        if (p.OC <= 32) return x3 ? launch_igemm<32, 2, true>(p, stream) : launch_igemm<32, 1, true>(p, stream);
+        if (p.OC <= 64) return x3 ? launch_igemm<64, 2, true>(p, stream) : launch_igemm<64, 1, true>(p, stream);
+        return x3 ? launch_igemm<128, 2, true>(p, stream) : launch_igemm<128, 1, true>(p, stream);
+    }
+    if (p.OC <= 32) return x3 ? launch_igemm<32, 2, false>(p, stream) : launch_igemm<32, 1, false>(p, stream);
+    if (p.OC <= 64) return x3 ? launch_igemm<64, 2, false>(p, stream) : launch_igemm<64, 1, false>(p, stream);
+    return x3 ? launch_igemm<128, 2, false>(p, stream) : launch_igemm<128, 1, false>(p, stream);
 }
 
 }  // namespace fcuda

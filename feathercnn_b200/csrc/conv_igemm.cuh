@@ -19,6 +19,7 @@ struct IgemmProblem {
     int dil_h, dil_w;       // dilation (0 or 1 = dense taps)
     int in_c_total;         // channels per image of the INPUT tensor when `input` addresses a channel slice of it
     int out_c_total;        // same for output / residual (grouped convolution = one launch per group on slices)
+    int pool;               // fuse a following 2x2 / stride-2 max pooling (pad 0): `output` is (N, OC, (OH+1)/2, (OW+1)/2)
 };
 
 // KH*KW <= 63 and, unless IC % 32 == 0, KH*KW*IC <= 8192 (shared-memory k-table).
@@ -27,6 +28,8 @@ bool conv_igemm_supported(int IC, int KH, int KW);
 size_t conv_igemm_packed_floats(int OC, int IC, int taps, int planes);
 // raw (OC, IC, KH, KW) -> [OC][Kf] hi (+ lo) planes.
 int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, int IC, int taps, cudaStream_t s);
+// True when the launch can apply a fused 2x2 / stride-2 max pooling (the 3x3 stride-1 slab kernel without a residual).
+bool conv_igemm_can_pool(const IgemmProblem& p);
 int conv_igemm_forward(const IgemmProblem& p, cudaStream_t stream);
 
 }  // namespace fcuda

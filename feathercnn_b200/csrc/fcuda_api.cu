@@ -9,6 +9,7 @@
 #include "depthwise.cuh"
 #include "layers.cuh"
 #include "pack.cuh"
+#include "preprocess.cuh"
 #include "tensor_gemm.cuh"
 #include "winograd.cuh"
 
@@ -319,7 +320,7 @@ int fcuda_conv_init(const FcudaConvParam* p, int algo, float* packed, const floa
 
 static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
                              float* scratch, const float* bias, const float* residual, int relu_after_add, int batch,
-                             void* stream, int dil_h = 1, int dil_w = 1);
+                             void* stream, int dil_h = 1, int dil_w = 1, int pool = 0);
 
 int fcuda_conv_forward_ext(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
                            float* scratch, const float* bias, const float* residual, int relu_after_add, int dilation_h,
@@ -354,7 +355,7 @@ int fcuda_conv_forward_residual(const FcudaConvParam* p, int algo, float* output
 
 static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
                              float* scratch, const float* bias, const float* residual, int relu_after_add, int batch,
-                             void* stream, int dil_h, int dil_w) {
+                             void* stream, int dil_h, int dil_w, int pool) {
     ConvPlan pl;
     int rc = make_plan(p, algo, batch, &pl);
     if (rc) return rc;
@@ -385,11 +386,12 @@ static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, c
                 g.algo_flops = 2.0 * OC * IC * 9.0 * p->output_h * p->output_w * batch *
                                (static_cast<double>(R1 - R0) / pl.total_tile_rows);
                 if ((rc = tensor_gemm(g, s))) return rc;
-                if ((rc = wino_output_transform(pl.tile, Mbuf, output, b, pl.wg, R0, R1, relu, s))) return rc;
+                if ((rc = wino_output_transform(pl.tile, Mbuf, output, b, pl.wg, R0, R1, relu, pool, s))) return rc;
             }
             return 0;
         }
         case FCUDA_IM2COL: {
+            if (pool) return -200;
             const size_t w_plane = static_cast<size_t>(OC) * pl.pg.Kp;
             float* P = scratch;
             for (long long m0 = 0; m0 < pl.total_pixels; m0 += pl.pixels_per_chunk) {
@@ -436,17 +438,46 @@ static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, c
                     g.H = p->input_h; g.W = p->input_w; g.OH = p->output_h; g.OW = p->output_w;
                 }
                 g.planes = pl.np; g.relu = residual ? relu_after_add : relu;
+                g.pool = pool;
+                if (pool) {  // pooled output planes
+                    g.output = output + static_cast<size_t>(gi) * OCg * (static_cast<size_t>((p->output_h + 1) / 2) * ((p->output_w + 1) / 2));
+                    g.out_c_total = OC;
+                }
                 if ((rc = conv_igemm_forward(g, s))) return rc;
             }
             return 0;
         }
         case FCUDA_NAIVE:
+            if (pool) return -200;
             return conv_direct(input, packed, b, output, pl.pg, OC, relu, batch, s);
         case FCUDA_DEPTHWISE:
+            if (pool) return -200;
             return depthwise_forward(input, packed, b, output, pl.dg, relu, batch, s);
         default:
             return -1;
     }
+}
+
+// Can fcuda_conv_forward_pool fuse the pooling for this layer?  Winograd: always (the output tile starts at an even
+// coordinate); implicit GEMM: the 3x3 / stride-1 slab kernel (group 1).
+int fcuda_conv_can_pool(const FcudaConvParam* p, int algo) {
+    if (!p) return 0;
+    if (algo == FCUDA_WINOGRADF63 || algo == FCUDA_WINOGRADF23) return 1;
+    if (algo == FCUDA_SGECONV) {
+        IgemmProblem g{};
+        g.IC = p->input_channels / (p->group > 0 ? p->group : 1);
+        g.KH = p->kernel_h; g.KW = p->kernel_w; g.stride_h = p->stride_h; g.stride_w = p->stride_w;
+        g.pad_top = p->pad_top; g.pad_left = p->pad_left;
+        return conv_igemm_can_pool(g) ? 1 : 0;
+    }
+    return 0;
+}
+
+int fcuda_conv_forward_pool(const FcudaConvParam* p, int algo, float* output, const float* input, const float* packed,
+                            float* scratch, const float* bias, int batch, void* stream) {
+    if (!p) return -100;
+    if (!fcuda_conv_can_pool(p, algo)) return -200;
+    return conv_forward_impl(p, algo, output, input, packed, scratch, bias, nullptr, 0, batch, stream, 1, 1, 1);
 }
 
 int fcuda_tensor_gemm(float* d, const float* a, const float* b_hi, const float* b_lo, int m, int n, int k, int g,
@@ -613,6 +644,14 @@ int fcuda_copy_channels(float* dst, int dst_channels, int dst_channel_offset, co
         return -100;
     return copy_channels(src, dst, static_cast<size_t>(channels) * stride, static_cast<size_t>(dst_channels) * stride,
                          static_cast<size_t>(dst_channel_offset) * stride, batch, as_stream(stream));
+}
+
+int fcuda_pixel_channels(int type, int* src_channels, int* out_channels) { return pixel_channels(type, src_channels, out_channels); }
+
+int fcuda_from_pixels(float* output, const unsigned char* pixels, int type, int w, int h, int target_w, int target_h,
+                      const float* mean_vals, const float* norm_vals, int batch, void* stream) {
+    if (!output || !pixels) return -100;
+    return from_pixels(output, pixels, type, w, h, target_w, target_h, mean_vals, norm_vals, batch, as_stream(stream));
 }
 
 void fcuda_profile_tensor_gemm(int enable) { gemm_profile_enable(enable != 0); }

@@ -305,7 +305,12 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         : "memory");
 }
 
-template <int BN, int ISSUERS>
+// CL > 1: CL CTAs of a thread-block cluster work on CL consecutive M tiles of the same (g, n-block) and share the B tiles:
+// each CTA fetches 1/CL of the B_hi / B_lo rows and TMA-multicasts them into every CTA's ring slot, so the L2 -> SM traffic of
+// B (the transformed filters, re-read by every M tile: 2.5 GB through L2 per VGG conv3 launch in round 1, the kernel's
+// measured limiter) drops by CL.  A slot may only be overwritten once EVERY CTA of the cluster has retired the MMAs that
+// read it: the producers exchange that through peer_free_bar (remote mbarrier arrives).
+template <int BN, int ISSUERS, int CL>
 __global__ void __launch_bounds__(kThreadsTs + 32 * (ISSUERS - 1), 1)
 tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmBlo, const GemmKernelArgs args) {
@@ -325,6 +330,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __shared__ uint64_t full_bar[STAGES];     // TMA landed A raw + B_hi + B_lo
     __shared__ uint64_t a_ready_bar[STAGES];  // a splitter group parked A_hi/A_lo in TMEM
     __shared__ uint64_t empty_bar[STAGES];    // MMAs reading the stage (smem B, TMEM A) retired
+    __shared__ uint64_t peer_free_bar[STAGES];  // CL > 1: the other CTAs of the cluster have released their copy of the slot
     __shared__ uint64_t tmem_full_bar[2];
     __shared__ uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
@@ -332,9 +338,16 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    static_assert(CL == 1 || ISSUERS == 1, "the cluster variant uses one issuer");
+    static_assert(CL == 1 || (BN / CL) % 8 == 0, "each CTA multicasts whole 8-row swizzle atoms of B");
+    // work items: CL == 1: one M tile per item, strided by the grid; CL > 1: CL consecutive M tiles per item (args.num_m
+    // counts those groups), strided by the number of clusters, this CTA takes M tile  group * CL + rank
     const int tiles_per_g = args.num_m * args.num_n;
     const int total_tiles = tiles_per_g * args.G * args.split_k;
     const int kb_per_split = (args.k_blocks_total + args.split_k - 1) / args.split_k;
+    const int t_first = CL == 1 ? static_cast<int>(blockIdx.x) : static_cast<int>(ptx::cluster_id_x());
+    const int t_step = CL == 1 ? static_cast<int>(gridDim.x) : static_cast<int>(ptx::cluster_count_x());
+    const int cta_rank = CL == 1 ? 0 : static_cast<int>(ptx::cluster_ctarank());
 
     if (threadIdx.x == 0) {
         issued_g = 0;
@@ -342,6 +355,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&a_ready_bar[s], 4);
             ptx::mbar_init(&empty_bar[s], 1);
+            ptx::mbar_init(&peer_free_bar[s], CL > 1 ? CL - 1 : 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full_bar[s], 1);
@@ -360,6 +374,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (CL > 1) ptx::cluster_sync_all();  // every CTA's barriers are initialised before a peer arrives on / multicasts to them
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     const uint32_t tmem_a0 = tmem_base + kAccCols;
@@ -369,23 +384,45 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const bool leader = ptx::elect_one();
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = t_first; tile < total_tiles; tile += t_step) {
             const int ks = tile / (tiles_per_g * args.G);
             const int rem = tile - ks * (tiles_per_g * args.G);
             const int g = rem / tiles_per_g;
             const int mn = rem - g * tiles_per_g;
-            const int m_blk = mn / args.num_n;
-            const int n_blk = mn - m_blk * args.num_n;
+            const int m_grp = mn / args.num_n;
+            const int n_blk = mn - m_grp * args.num_n;
+            const int m_blk = m_grp * CL + cta_rank;
             const int kb0 = ks * kb_per_split;
             const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
             for (int kb = kb0; kb < kb1; ++kb) {
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (CL > 1) {
+                    // my copy of the slot is free: tell the peers, then wait until theirs are (their multicast lands in
+                    // my slot, mine in theirs)
+                    if (leader) {
+#pragma unroll
+                        for (int c = 0; c < CL; ++c)
+                            if (c != cta_rank) ptx::mbar_arrive_remote(&peer_free_bar[stage], static_cast<uint32_t>(c));
+                    }
+                    __syncwarp();
+                    ptx::mbar_wait_cluster(&peer_free_bar[stage], phase);
+                }
                 if (leader) {
                     uint8_t* st = smem + stage * kStage;
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kStage);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kStage);  // own A + all CL pieces of B_hi and B_lo
                     ptx::tma_load_3d(st, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM, g);
-                    ptx::tma_load_3d(st + kATile, &tmB, &full_bar[stage], kb * kBK, n_blk * BN, g);
-                    ptx::tma_load_3d(st + kATile + kBTile, &tmBlo, &full_bar[stage], kb * kBK, n_blk * BN, g);
+                    if (CL == 1) {
+                        ptx::tma_load_3d(st + kATile, &tmB, &full_bar[stage], kb * kBK, n_blk * BN, g);
+                        ptx::tma_load_3d(st + kATile + kBTile, &tmBlo, &full_bar[stage], kb * kBK, n_blk * BN, g);
+                    } else {
+                        constexpr int kRows = BN / CL;          // B rows this CTA fetches for the whole cluster
+                        constexpr int kPiece = kRows * kBK * 4;
+                        constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
+                        ptx::tma_load_3d_multicast(st + kATile + cta_rank * kPiece, &tmB, &full_bar[stage], kb * kBK,
+                                                   n_blk * BN + cta_rank * kRows, g, kMask);
+                        ptx::tma_load_3d_multicast(st + kATile + kBTile + cta_rank * kPiece, &tmBlo, &full_bar[stage],
+                                                   kb * kBK, n_blk * BN + cta_rank * kRows, g, kMask);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -399,7 +436,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const uint64_t dB0 = make_smem_desc_sw128(ptx::smem_u32(smem) + kATile);
             uint32_t g = 0;  // running k-block index over this CTA's tiles
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = t_first; tile < total_tiles; tile += t_step, ++it) {
                 const int ks = tile / (tiles_per_g * args.G);
                 const int kb0 = ks * kb_per_split;
                 const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
@@ -440,7 +477,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         uint32_t phase = 0;
         int it = 0;
         bool ready = false;  // a_ready_bar[stage] already observed complete for `phase`
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = t_first; tile < total_tiles; tile += t_step, ++it) {
             const int ks = tile / (tiles_per_g * args.G);
             const int kb0 = ks * kb_per_split;
             const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
@@ -487,7 +524,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const uint32_t sw = static_cast<uint32_t>(row & 7);  // 128B swizzle: 16-byte chunk c lives at c ^ (row & 7)
         int stage = 0, g_par = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = t_first; tile < total_tiles; tile += t_step) {
             const int ks = tile / (tiles_per_g * args.G);
             const int kb0 = ks * kb_per_split;
             const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
@@ -528,13 +565,14 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = t_first; tile < total_tiles; tile += t_step, ++it) {
             const int ks = tile / (tiles_per_g * args.G);
             const int rem = tile - ks * (tiles_per_g * args.G);
             const int g = rem / tiles_per_g;
             const int mn = rem - g * tiles_per_g;
-            const int m_blk = mn / args.num_n;
-            const int n_blk = mn - m_blk * args.num_n;
+            const int m_grp = mn / args.num_n;
+            const int n_blk = mn - m_grp * args.num_n;
+            const int m_blk = m_grp * CL + cta_rank;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait_relaxed(&tmem_full_bar[as], aphase);
@@ -548,6 +586,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CL > 1) ptx::cluster_sync_all();  // no CTA may exit while a peer can still arrive on / multicast into its smem
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
@@ -756,34 +795,86 @@ static int ts_issuers() {  // FCUDA_TS_ISSUERS=1|2 (experiment switch)
     return v;
 }
 
-template <int BN, int ISSUERS>
+static int gemm_cluster_env() {  // FCUDA_GEMM_CLUSTER=1|2|4 (experiment switch; unset = policy in pick_cluster)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FCUDA_GEMM_CLUSTER");
+        v = e ? atoi(e) : 0;
+        if (v != 1 && v != 2 && v != 4) v = 0;
+    }
+    return v;
+}
+
+template <int BN, int ISSUERS, int CL>
 static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
     CUtensorMap tmA, tmB, tmBlo;
     const long long as = p.a_batch_stride ? p.a_batch_stride : static_cast<long long>(p.M) * p.K;
     const long long bs = p.b_batch_stride ? p.b_batch_stride : static_cast<long long>(p.N) * p.K;
     int rc;
     if ((rc = make_map(&tmA, p.A, p.K, p.M, p.G, as, kBM))) return rc;
-    if ((rc = make_map(&tmB, p.B_hi, p.K, p.N, p.G, bs, BN))) return rc;
-    if ((rc = make_map(&tmBlo, p.B_lo, p.K, p.N, p.G, bs, BN))) return rc;
+    if ((rc = make_map(&tmB, p.B_hi, p.K, p.N, p.G, bs, BN / CL))) return rc;   // CL > 1: each CTA fetches BN / CL rows
+    if ((rc = make_map(&tmBlo, p.B_lo, p.K, p.N, p.G, bs, BN / CL))) return rc;
     GemmKernelArgs a;
     fill_kernel_args(p, BN, &a);
+    if (CL > 1) a.num_m = ceil_div(a.num_m, CL);  // work items = groups of CL consecutive M tiles
     const long long total = static_cast<long long>(a.num_m) * a.num_n * a.G * a.split_k;
     if (total > 0x7fffffffLL) return -1;
-    const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
     constexpr int kStage = kBM * kBK * 4 + 2 * BN * kBK * 4;
     static_assert(kStagesTs * kStage + 1024 <= 227 * 1024, "smem budget");
     const int smem = kStagesTs * kStage + 1024;
-    auto kern = tensor_gemm_ts_kernel<BN, ISSUERS>;
+    auto kern = tensor_gemm_ts_kernel<BN, ISSUERS, CL>;
     static SmemAttrCache attr_cache;
-    if (int rc = ensure_dynamic_smem(kern, smem, attr_cache)) return rc;
+    if (int rc2 = ensure_dynamic_smem(kern, smem, attr_cache)) return rc2;
     const double dense = 2.0 * p.M * static_cast<double>(p.N) * p.K * p.G;
+    const int threads = kThreadsTs + 32 * (ISSUERS - 1);
+    if (CL == 1) {
+        const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+        const int prof = prof_begin(stream, PROF_TENSOR_GEMM, p.algo_flops > 0 ? p.algo_flops : dense, dense * 3.0,
+                                    gemm_algo_bytes(p));
+        kern<<<grid, threads, smem, stream>>>(tmA, tmB, tmBlo, a);
+        FCUDA_CHECK_LAUNCH();
+        count_launch();
+        prof_end(prof, stream);
+        return 0;
+    }
+    // cluster launch: as many clusters as can be co-resident (1 CTA per SM), never more than there are work items
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    static int max_clusters[kMaxDevices] = {};
+    const int dev = current_device();
+    if (max_clusters[dev] == 0) {
+        cfg.gridDim = dim3(static_cast<unsigned>(sm_count() / CL * CL));
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = sm_count() / CL;
+        }
+        max_clusters[dev] = n;
+    }
+    const long long nclusters = total < max_clusters[dev] ? total : max_clusters[dev];
+    cfg.gridDim = dim3(static_cast<unsigned>(nclusters * CL));
     const int prof = prof_begin(stream, PROF_TENSOR_GEMM, p.algo_flops > 0 ? p.algo_flops : dense, dense * 3.0,
                                 gemm_algo_bytes(p));
-    kern<<<grid, kThreadsTs + 32 * (ISSUERS - 1), smem, stream>>>(tmA, tmB, tmBlo, a);
-    FCUDA_CHECK_LAUNCH();
+    FCUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBlo, a));
     count_launch();
     prof_end(prof, stream);
     return 0;
+}
+
+// CTAs per cluster for a 3xTF32 problem: B sharing pays when several M tiles exist per (g, n-block); an odd M-tile count
+// costs one idle-rows tile per group, so small M keeps the plain kernel.
+static int pick_cluster(const GemmProblem& p) {
+    if (p.split_k > 1 || p.epilogue == EPI_COLMAJOR_PARTIAL) return 1;
+    const int e = gemm_cluster_env();
+    const int num_m = ceil_div(p.M, kBM);
+    if (e) return num_m >= e ? e : 1;
+    // Measured on B200 (profiles/r02e_lean.log, VGG-16 b64): 6.77 ms per step without clusters, 7.61 with pairs, 9.38 with
+    // quads — the per-k-block cross-CTA handshake costs more than the halved B traffic saves, because L2 was not the
+    // limiter (the epilogue was).  The multicast variant stays behind FCUDA_GEMM_CLUSTER for experiments.
+    return 1;
 }
 
 int tensor_gemm(const GemmProblem& p, cudaStream_t stream) {
@@ -791,13 +882,16 @@ int tensor_gemm(const GemmProblem& p, cudaStream_t stream) {
     if (p.split_k > 1 && p.epilogue != EPI_COLMAJOR_PARTIAL) return -1;
     if (p.planes == 2) {
         if (ts_issuers() == 2) {
-            if (p.N <= 32) return launch_ts<32, 2>(p, stream);
-            if (p.N <= 64) return launch_ts<64, 2>(p, stream);
-            return launch_ts<128, 2>(p, stream);
+            if (p.N <= 32) return launch_ts<32, 2, 1>(p, stream);
+            if (p.N <= 64) return launch_ts<64, 2, 1>(p, stream);
+            return launch_ts<128, 2, 1>(p, stream);
         }
-        if (p.N <= 32) return launch_ts<32, 1>(p, stream);
-        if (p.N <= 64) return launch_ts<64, 1>(p, stream);
-        return launch_ts<128, 1>(p, stream);
+        const int cl = pick_cluster(p);
+        if (p.N <= 32) return launch_ts<32, 1, 1>(p, stream);
+        if (p.N <= 64) return cl == 4 ? launch_ts<64, 1, 4>(p, stream) : cl == 2 ? launch_ts<64, 1, 2>(p, stream)
+                                                                                  : launch_ts<64, 1, 1>(p, stream);
+        return cl == 4 ? launch_ts<128, 1, 4>(p, stream) : cl == 2 ? launch_ts<128, 1, 2>(p, stream)
+                                                                    : launch_ts<128, 1, 1>(p, stream);
     }
     // N tile: smallest supported tile that covers N (fewer wasted MMA columns), capped at 256.
     if (p.N <= 32) return launch<32, 1, 8>(p, stream);

@@ -230,16 +230,19 @@ wino_input_kernel(const float* __restrict__ in, float* __restrict__ V, WinoGeom 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Output transform  Y = A^T M A  (+bias, ReLU), clipped NCHW store
+// Output transform  Y = A^T M A  (+bias, ReLU), clipped NCHW store; POOL: a following 2x2 / stride-2 max pooling
+// (pooling_layer.h:38-91, pad 0) is applied to the tile in registers — the 6x6 (2x2) output tile starts at an even
+// coordinate, so no window straddles two tiles — and only the pooled (OH+1)/2 x (OW+1)/2 blob is written.
 // ------------------------------------------------------------------------------------------------
-template <int T>
+template <int T, bool POOL>
 __global__ void __launch_bounds__(kXformThreads)
 wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const float* __restrict__ bias, WinoGeom g,
                    int R0, int Tc, int relu) {
     using W = Wino<T>;
     constexpr int OT = W::kOut;
-    constexpr int COLS = OT * kSegTiles;     // 30 for F(6,3)
-    constexpr int CH_STRIDE = OT * COLS + 1;
+    constexpr int ST = POOL ? OT / 2 : OT;     // rows / columns of the tile as stored
+    constexpr int COLS = ST * kSegTiles;       // 30 (15 pooled) for F(6,3)
+    constexpr int CH_STRIDE = ST * COLS + 1;
     __shared__ float slab[kChBlock * CH_STRIDE];
 
     const int segs = (g.tilesX + kSegTiles - 1) / kSegTiles;
@@ -274,38 +277,64 @@ wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const f
             for (int i = 0; i < OT; ++i) tmp[i][b] = s[i];
         }
         const float bv = bias ? __ldg(bias + oc) : 0.f;
-        float* dst = slab + lane * CH_STRIDE + w * OT;
+        float* dst = slab + lane * CH_STRIDE + w * ST;
+        if (!POOL) {
 #pragma unroll
-        for (int i = 0; i < OT; ++i) {
-            float s[OT];
-            W::at(tmp[i], s);
+            for (int i = 0; i < OT; ++i) {
+                float s[OT];
+                W::at(tmp[i], s);
 #pragma unroll
-            for (int j = 0; j < OT; ++j) {
-                float v = s[j] + bv;
-                if (relu) v = fmaxf(v, 0.f);
-                dst[i * COLS + j] = v;
+                for (int j = 0; j < OT; ++j) {
+                    float v = s[j] + bv;
+                    if (relu) v = fmaxf(v, 0.f);
+                    dst[i * COLS + j] = v;
+                }
+            }
+        } else {
+            // outputs outside the image (partial tiles, odd OH / OW) must not win a window: -inf
+            const int oy0 = ty * OT, ox0 = tx * OT;
+#pragma unroll
+            for (int i = 0; i < OT; i += 2) {
+                float s0[OT], s1[OT];
+                W::at(tmp[i], s0);
+                W::at(tmp[i + 1], s1);
+                const bool r1 = oy0 + i + 1 < g.OH;
+#pragma unroll
+                for (int j = 0; j < OT; j += 2) {
+                    const bool c1 = ox0 + j + 1 < g.OW;
+                    float v = s0[j];
+                    if (c1) v = fmaxf(v, s0[j + 1]);
+                    if (r1) {
+                        v = fmaxf(v, s1[j]);
+                        if (c1) v = fmaxf(v, s1[j + 1]);
+                    }
+                    v += bv;  // max commutes with the per-channel bias and with ReLU
+                    if (relu) v = fmaxf(v, 0.f);
+                    dst[(i >> 1) * COLS + (j >> 1)] = v;
+                }
             }
         }
     }
     __syncthreads();
 
-    // store: warp w takes channels w, w+5, ...; the OT rows of a channel are unrolled; lane = column (30 of 32 lanes)
-    const int oy0 = ty * OT, ox = tx0 * OT + lane;
-    const size_t oplane = static_cast<size_t>(g.OH) * g.OW;
+    // store: warp w takes channels w, w+5, ...; the ST rows of a channel are unrolled; lane = column
+    const int SH = POOL ? (g.OH + 1) / 2 : g.OH, SW = POOL ? (g.OW + 1) / 2 : g.OW;  // stored blob geometry
+    const int oy0 = ty * ST, ox = tx0 * ST + lane;
+    const size_t oplane = static_cast<size_t>(SH) * SW;
     float* img = out + static_cast<size_t>(n) * g.C_out * oplane;
-    const bool x_ok = lane < COLS && ox < g.OW;
+    const bool x_ok = lane < COLS && ox < SW;
     unsigned row_ok = 0;
 #pragma unroll
-    for (int r = 0; r < OT; ++r)
-        if (oy0 + r < g.OH) row_ok |= 1u << r;
+    for (int r = 0; r < ST; ++r)
+        if (oy0 + r < SH) row_ok |= 1u << r;
     for (int c = w; c < kChBlock; c += kSegTiles) {
         const int o = c0 + c;
         if (!(x_ok && o < g.C_out)) continue;
-        float* p = img + static_cast<size_t>(o) * oplane + static_cast<size_t>(oy0) * g.OW + ox;
+        float* p = img + static_cast<size_t>(o) * oplane + static_cast<size_t>(oy0) * SW + ox;
         const float* sp = slab + c * CH_STRIDE + lane;
 #pragma unroll
-        for (int r = 0; r < OT; ++r)
-            if ((row_ok >> r) & 1u) p[r * g.OW] = sp[r * COLS];
+        for (int r = 0; r < ST; ++r)
+            if ((row_ok >> r) & 1u) p[r * SW] = sp[r * COLS];
     }
 }
 
@@ -339,15 +368,21 @@ int wino_input_transform(int tile, const float* in, float* V, const WinoGeom& g,
 }
 
 int wino_output_transform(int tile, const float* M, float* out, const float* bias, const WinoGeom& g, int R0, int R1,
-                          int relu, cudaStream_t s) {
+                          int relu, int pool, cudaStream_t s) {
     const int segs = ceil_div(g.tilesX, kSegTiles);
     const int Tc = (R1 - R0) * g.tilesX;
     dim3 grid(static_cast<unsigned>(segs) * (R1 - R0), ceil_div(g.C_out, kChBlock));
     const double imgs = static_cast<double>(R1 - R0) / g.tilesY;  // tile-rows of the chunk, in images
+    const double out_px = pool ? static_cast<double>((g.OH + 1) / 2) * ((g.OW + 1) / 2) : static_cast<double>(g.OH) * g.OW;
     const int prof = prof_begin(s, PROF_WINO_OUTPUT, 0, 0,
-                                4.0 * (imgs * g.C_out * g.OH * g.OW + static_cast<double>(tile) * tile * Tc * g.C_out));
-    if (tile == 8) wino_output_kernel<8><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
-    else wino_output_kernel<4><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+                                4.0 * (imgs * g.C_out * out_px + static_cast<double>(tile) * tile * Tc * g.C_out));
+    if (tile == 8) {
+        if (pool) wino_output_kernel<8, true><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+        else wino_output_kernel<8, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+    } else {
+        if (pool) wino_output_kernel<4, true><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+        else wino_output_kernel<4, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+    }
     prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();
     count_launch();

@@ -57,6 +57,10 @@ int fnet_attach_weights(void* h) { return static_cast<Net*>(h)->AttachWeights();
 int fnet_feed_input_batch(void* h, const char* name, const float* host, int n, int c, int hh, int w) {
     return static_cast<Net*>(h)->FeedInputBatch(name, host, n, c, hh, w);
 }
+int fnet_feed_input_pixels(void* h, const char* name, const unsigned char* host_pixels, int type, int w, int hh, int target_w,
+                           int target_h, int batch, const float* mean_vals, const float* norm_vals) {
+    FNET_GUARD(static_cast<Net*>(h)->FeedInputPixels(name, host_pixels, type, w, hh, target_w, target_h, batch, mean_vals, norm_vals))
+}
 int fnet_feed_input_device(void* h, const char* name, const float* dev, int n, int c, int hh, int w) {
     return static_cast<Net*>(h)->FeedInputDevice(name, dev, n, c, hh, w);
 }

@@ -9,6 +9,8 @@
 
 #include <vector>
 
+#include "pooling_layer.h"
+
 namespace feather {
 inline namespace b200 {  // ABI tag: keeps these symbols apart from the reference build when both are loaded
 
@@ -21,6 +23,7 @@ public:
     ~ConvLayer() {
         delete processed_weights;
         delete folded_bias;
+        delete pre_pool;
     }
 
     int LoadParam(const ncnn::ParamDict& pd) {
@@ -110,7 +113,10 @@ public:
             if (conv_param.output_h <= 0 || conv_param.output_w <= 0) return FEATHER_ERR_WEIGHTS;
         }
         const int batch = bottom_blob->num();
-        tops[0]->ReshapeWithRealloc(batch, conv_param.output_channels, conv_param.output_h, conv_param.output_w);
+        if (fused_pool)  // the top is the pooled blob (ceil mode, pooling_layer.h:129-130 with k = s = 2, pad 0)
+            tops[0]->ReshapeWithRealloc(batch, conv_param.output_channels, (conv_param.output_h + 1) / 2, (conv_param.output_w + 1) / 2);
+        else
+            tops[0]->ReshapeWithRealloc(batch, conv_param.output_channels, conv_param.output_h, conv_param.output_w);
         // FEATHER_ALGO_POLICY=reference keeps avx/booster.cpp:283-310 verbatim; default is the B200 cost model
         static const bool reference_policy = [] {
             const char* e = getenv("FEATHER_ALGO_POLICY");
@@ -136,6 +142,15 @@ public:
         rc = conv_booster.GetBufferSize(&conv_param, &buffer_size, &dull, batch);
         if (rc) return rc;
         MEMPOOL_CHECK_RETURN(this->common_mempool->Request(sizeof(float) * buffer_size));
+        if (fused_pool) {
+            // algorithms that cannot pool in their epilogue run the convolution into a private blob, then the pooling kernel
+            pool_in_epilogue = dilation_h == 1 && dilation_w == 1 && fcuda_conv_can_pool(&conv_param, conv_booster.GetAlgo()) != 0;
+            if (!pool_in_epilogue) {
+                if (!pre_pool) pre_pool = new Blob<float>(this->name + "_pre_pool");
+                pre_pool->ReshapeWithRealloc(batch, conv_param.output_channels, conv_param.output_h, conv_param.output_w);
+                if (!pre_pool->data()) return FEATHER_ERR_CUDA;
+            }
+        }
         if (init_algo >= 0 && init_algo != conv_booster.GetAlgo()) return Init();  // shape change switched algorithms
         return 0;
     }
@@ -188,6 +203,17 @@ public:
     int Forward() {
         float* buffer = NULL;
         MEMPOOL_CHECK_RETURN(this->common_mempool->GetPtr(&buffer));
+        if (fused_pool) {
+            const int batch = static_cast<int>(bottoms[0]->num());
+            if (pool_in_epilogue)
+                return fcuda_conv_forward_pool(&conv_param, conv_booster.GetAlgo(), tops[0]->data(), bottoms[0]->data(),
+                                               processed_kernel, buffer, bias_data, batch, stream());
+            int rc = fcuda_conv_forward_ext(&conv_param, conv_booster.GetAlgo(), pre_pool->data(), bottoms[0]->data(),
+                                            processed_kernel, buffer, bias_data, NULL, 0, dilation_h, dilation_w, batch, stream());
+            if (rc) return rc;
+            return fcuda_pooling_forward(tops[0]->data(), pre_pool->data(), conv_param.output_channels, conv_param.output_h,
+                                         conv_param.output_w, 0, 2, 2, 2, 2, 0, 0, 0, 0, 0, batch, stream());
+        }
         if (dilation_h > 1 || dilation_w > 1)
             return fcuda_conv_forward_ext(&conv_param, conv_booster.GetAlgo(), tops[0]->data(), bottoms[0]->data(),
                                           processed_kernel, buffer, bias_data, residual ? residual->data() : NULL,
@@ -201,14 +227,21 @@ public:
 
     // Net::ApplyFusion: absorb `Eltwise SUM(this->top, other) [+ReLU]` (a ResNet shortcut) into this layer's epilogue.
     int FuseResidual(Blob<float>* other, int relu) {
-        if (residual != NULL) return 0;
+        if (residual != NULL || fused_pool) return 0;
         residual = other;
         relu_after_add = relu;
         return 1;
     }
 
-    int Fuse(Layer* next_layer) {  // conv_layer.h:174-185, extended to BatchNorm and Scale
-        if (conv_param.activation == booster::ReLU) return 0;  // the activation is always last
+    int Fuse(Layer* next_layer) {  // conv_layer.h:174-185, extended to BatchNorm, Scale and a trailing 2x2 max pooling
+        if (fused_pool) return 0;  // the pooling is always last
+        if (next_layer->type.compare("Pooling") == 0) {
+            PoolingLayer* pl = dynamic_cast<PoolingLayer*>(next_layer);
+            if (!pl || !pl->IsMax2x2Stride2() || residual != NULL) return 0;
+            fused_pool = true;
+            return 1;
+        }
+        if (conv_param.activation == booster::ReLU) return 0;  // the activation precedes only the pooling
         if (next_layer->type.compare("ReLU") == 0) {
             conv_param.activation = booster::ReLU;
             return 1;
@@ -261,6 +294,10 @@ protected:
     // fused Eltwise SUM (Net::ApplyFusion)
     Blob<float>* residual = NULL;
     int relu_after_add = 0;
+    // fused trailing 2x2 / stride-2 max pooling (Net::ApplyFusion)
+    bool fused_pool = false;
+    bool pool_in_epilogue = false;
+    Blob<float>* pre_pool = NULL;
 
 };
 

@@ -53,6 +53,12 @@ public:
                                      global_pooling ? 1 : 0, bottoms[0]->num(), stream());
     }
 
+    // 2x2 / stride 2 / no padding / max: the pooling a convolution can absorb into its epilogue (Net::ApplyFusion)
+    bool IsMax2x2Stride2() const {
+        return !global_pooling && pooling_type == 0 && kernel_h == 2 && kernel_w == 2 && stride_h == 2 && stride_w == 2 &&
+               pad_left == 0 && pad_right == 0 && pad_top == 0 && pad_bottom == 0;
+    }
+
 private:
     int input_h, input_w, input_channels, output_h, output_w, output_channels;
     int pad_left, pad_bottom, pad_right, pad_top;

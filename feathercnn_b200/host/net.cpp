@@ -54,6 +54,7 @@ Net::~Net() {
         layers[i] = NULL;
     }
     if (weight_arena_) cudaFree(weight_arena_);
+    if (pixel_stage_) cudaFree(pixel_stage_);
     if (owns_stream_ && rt_param->stream()) cudaStreamDestroy(static_cast<cudaStream_t>(rt_param->stream()));
     delete rt_param->common_mempool();
     delete rt_param;
@@ -328,6 +329,35 @@ int Net::FeedInputBatch(const char* input_name, const float* host_nchw, int n, i
     if (it == blob_map.end() || !host_nchw || n < 1) return -1;
     it->second->ReshapeWithRealloc(n, c, h, w);
     return it->second->CopyFromHost(host_nchw, rt_param->stream());
+}
+
+// ncnn::Mat::from_pixels[_resize] + substract_mean_normalize + FeedInput (README.md:64-66 usage), for a whole batch and on
+// the device: the u8 images cross PCIe (4x fewer bytes than fp32) and one fused kernel writes the input blob.
+int Net::FeedInputPixels(const char* input_name, const unsigned char* host_pixels, int type, int w, int h, int target_w,
+                         int target_h, int batch, const float* mean_vals, const float* norm_vals) {
+    std::map<std::string, Blob<float>*>::iterator it = this->blob_map.find(std::string(input_name));
+    if (it == blob_map.end() || !host_pixels || batch < 1) return -1;
+    int src_c = 0, out_c = 0;
+    int rc = fcuda_pixel_channels(type, &src_c, &out_c);
+    if (rc) return rc;
+    if (target_w <= 0) target_w = w;
+    if (target_h <= 0) target_h = h;
+    const size_t bytes = static_cast<size_t>(batch) * w * h * src_c;
+    cudaStream_t s = static_cast<cudaStream_t>(rt_param->stream());
+    if (bytes > pixel_stage_bytes_) {
+        if (pixel_stage_) {
+            CUDA_OK(cudaStreamSynchronize(s));
+            cudaFree(pixel_stage_);
+        }
+        pixel_stage_ = nullptr;
+        pixel_stage_bytes_ = 0;
+        CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&pixel_stage_), bytes));
+        pixel_stage_bytes_ = bytes;
+    }
+    CUDA_OK(cudaMemcpyAsync(pixel_stage_, host_pixels, bytes, cudaMemcpyHostToDevice, s));
+    it->second->ReshapeWithRealloc(batch, out_c, target_h, target_w);
+    if (!it->second->data()) return FEATHER_ERR_CUDA;
+    return fcuda_from_pixels(it->second->data(), pixel_stage_, type, w, h, target_w, target_h, mean_vals, norm_vals, batch, s);
 }
 
 int Net::FeedInputDevice(const char* input_name, const float* device_nchw, int n, int c, int h, int w) {

@@ -90,6 +90,20 @@ class Net:
                                                                  x.ctypes.data_as(ctypes.c_void_p), n, c, h, w))
         self._keepalive = x
 
+    def FeedInputPixels(self, pixels: np.ndarray, type_: int, target_w: int = 0, target_h: int = 0, mean=None, norm=None,
+                        name: str | None = None) -> None:
+        """(N, h, w[, c]) uint8 interleaved images -> resize -> planar fp32 -> (x - mean) * norm, on the device
+        (ncnn::Mat::from_pixels_resize + substract_mean_normalize + FeedInput, /root/reference/src/ncnn/mat.h:149-160)."""
+        pixels = np.ascontiguousarray(pixels, np.uint8)
+        n, h, w = pixels.shape[:3]
+        fp = ctypes.POINTER(ctypes.c_float)
+        m = None if mean is None else np.ascontiguousarray(mean, np.float32)
+        s = None if norm is None else np.ascontiguousarray(norm, np.float32)
+        _check("FeedInputPixels", self._lib.fnet_feed_input_pixels(
+            self._h, (name or self.input_name).encode(), pixels.ctypes.data_as(ctypes.c_void_p), type_, w, h, target_w,
+            target_h, n, None if m is None else m.ctypes.data_as(fp), None if s is None else s.ctypes.data_as(fp)))
+        self.Synchronize()  # the pageable host array may be released by the caller
+
     def FeedInputDevice(self, data_ptr: int, shape, name: str | None = None) -> None:
         n, c, h, w = shape
         _check("FeedInputDevice", self._lib.fnet_feed_input_device(self._h, (name or self.input_name).encode(),

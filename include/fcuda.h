@@ -155,6 +155,28 @@ int fcuda_conv_forward_residual(const FcudaConvParam* param, int algo, float* ou
                                 const float* packed_kernel, float* scratch, const float* bias, const float* residual,
                                 int relu_after_add, int batch, void* stream);
 
+/* Convolution (+bias, +ReLU per param->activation) with a FOLLOWING 2x2 / stride-2 / pad-0 max pooling fused into its
+ * epilogue (ConvLayer::Forward then PoolingLayer::Forward, src/layers/pooling_layer.h:38-91): `output` is the pooled blob
+ * (batch, OC, (OH+1)/2, (OW+1)/2) — ceil mode, windows clipped at the border like the reference.  fcuda_conv_can_pool
+ * says whether the algorithm can do it (Winograd F(6,3)/F(2,3): the output tile is pooled in registers; FCUDA_SGECONV:
+ * 3x3 / stride-1 layers with IC % 32 == 0, pooled by two shuffles per value); otherwise the call returns -200. */
+int fcuda_conv_can_pool(const FcudaConvParam* param, int algo);
+int fcuda_conv_forward_pool(const FcudaConvParam* param, int algo, float* output, const float* input,
+                            const float* packed_kernel, float* scratch, const float* bias, int batch, void* stream);
+
+/* Input staging on the GPU, the step before the hot path.  One fused pass over a batch of u8 images:
+ * ncnn::Mat::from_pixels / from_pixels_resize (src/ncnn/mat.h:149-152; mat_pixel.cpp:1329-1410; the 11-bit fixed-point
+ * bilinear of mat_pixel_resize.cpp:26-278, bit-exact) and Mat::substract_mean_normalize (mat.h:159-160, mat.cpp:30-107).
+ *   type       ncnn pixel type, mat.h:126-146: PIXEL_RGB 1, BGR 2, GRAY 4, RGBA 8, conversions = from | (to << 16)
+ *   pixels     DEVICE pointer, `batch` interleaved u8 images of w*h*src_channels bytes each
+ *   target_*   output size (<= 0: keep w / h; equal to w / h: no resize, like mat_pixel.cpp:1371)
+ *   mean/norm  HOST arrays of out_channels floats or NULL (mean only: x - mean; norm only: x * norm; both: x*norm - mean*norm)
+ *   output     (batch, out_channels, target_h, target_w) fp32, dense planes
+ * Returns -200 for a type from_pixels does not know (it returns an empty Mat). */
+int fcuda_pixel_channels(int type, int* src_channels, int* out_channels);
+int fcuda_from_pixels(float* output, const unsigned char* pixels, int type, int w, int h, int target_w, int target_h,
+                      const float* mean_vals, const float* norm_vals, int batch, void* stream);
+
 /* Extended forward (beyond the reference, which rejects both: dilation at src/layers/conv_layer.h:43-47, partial groups at
  * avx/booster.cpp:304-308).  Same as fcuda_conv_forward[_residual] (`residual` may be NULL) plus a tap spacing.
  *   dilation: FCUDA_SGECONV only (-200 otherwise); the caller sets param->output_h/w for the dilated extent

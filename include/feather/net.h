@@ -57,6 +57,11 @@ public:
     // ---- batched / device API (new) ----------------------------------------------------------------
     int FeedInputBatch(const char* input_name, const float* host_nchw, int n, int c, int h, int w);
     int FeedInputDevice(const char* input_name, const float* device_nchw, int n, int c, int h, int w);
+    // u8 images (interleaved, ncnn pixel `type`, mat.h:126-146) -> resize -> planar fp32 -> (x - mean) * norm, on the
+    // device, straight into the input blob: ncnn::Mat::from_pixels_resize + substract_mean_normalize + FeedInput for a
+    // batch (mat.h:149-160).  mean_vals / norm_vals: host arrays or NULL; target <= 0 keeps w / h.
+    int FeedInputPixels(const char* input_name, const unsigned char* host_pixels, int type, int w, int h, int target_w,
+                        int target_h, int batch, const float* mean_vals, const float* norm_vals);
     int ForwardBatch(const float* host_nchw, int batch);  // FeedInputBatch(first Input layer) + Forward
     int ExtractDevice(std::string blob_name, const float** device_ptr, int* n, int* c, int* h, int* w);
     int Synchronize();
@@ -125,6 +130,8 @@ private:
     std::set<std::vector<size_t>> warmed_keys_;  // graph keys that already ran once eagerly
     float* graph_pool_ptr_ = nullptr;            // scratch pool address the cached graphs were captured with
     int init_precision_ = -1;                    // fcuda precision mode the packed filters were made for
+    unsigned char* pixel_stage_ = nullptr;  // device staging of the u8 images of FeedInputPixels
+    size_t pixel_stage_bytes_ = 0;
     PipeSlot pipe_[2];
     void* copy_stream_ = nullptr;
     unsigned submitted_ = 0;

@@ -30,6 +30,10 @@ int fnet_prepare_weight_arena(void* net);                        /* non-root ran
 int fnet_weight_arena(void* net, float** device_ptr, size_t* floats);
 int fnet_attach_weights(void* net);                              /* after the arena was filled (NCCL broadcast) */
 int fnet_feed_input_batch(void* net, const char* input_name, const float* host_nchw, int n, int c, int h, int w);
+/* u8 images -> (resize) -> planar fp32 -> mean / norm on the device into the input blob (ncnn::Mat::from_pixels_resize +
+ * substract_mean_normalize + FeedInput, src/ncnn/mat.h:149-160); mean_vals / norm_vals may be NULL */
+int fnet_feed_input_pixels(void* net, const char* input_name, const unsigned char* host_pixels, int type, int w, int h,
+                           int target_w, int target_h, int batch, const float* mean_vals, const float* norm_vals);
 int fnet_feed_input_device(void* net, const char* input_name, const float* device_nchw, int n, int c, int h, int w);
 int fnet_forward(void* net);                                     /* Net::Forward, net.cpp:298-334 */
 int fnet_forward_batch(void* net, const float* host_nchw, int batch); /* README.md:65 with a batch */

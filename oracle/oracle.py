@@ -24,6 +24,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 _ORACLE_SO = _HERE / "_build" / "liboracle.so"
 _REF_SO = _HERE / "_ref" / "libfeather_ref.so"
+_REF_CUDA_SO = _HERE / "_ref" / "libfeather_ref_cuda.so"  # the reference host on libfcuda.so (tests/integration/cuda_booster.cpp)
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 
@@ -185,13 +186,24 @@ def reference_available() -> bool:
     return _REF_SO.exists()
 
 
+def reference_cuda_available() -> bool:
+    return _REF_CUDA_SO.exists()
+
+
+def reference_on_cuda() -> "Reference":
+    """The unmodified reference host (feather::Net, ConvLayer, ...) with tests/integration/cuda_booster.cpp in place of
+    src/booster/avx/booster.cpp: its ConvBooster function table points into libfcuda.so (compiled)."""
+    return Reference(_REF_CUDA_SO)
+
+
 class Reference:
     """The unmodified reference build (oracle/_ref)."""
 
-    def __init__(self):
-        if not _REF_SO.exists():
-            raise FileNotFoundError(f"{_REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
-        self.lib = ctypes.CDLL(str(_REF_SO))
+    def __init__(self, so_path: Path | None = None):
+        so_path = so_path or _REF_SO
+        if not so_path.exists():
+            raise FileNotFoundError(f"{so_path} missing: run `make -C oracle ref ref_cuda` where /root/reference exists")
+        self.lib = ctypes.CDLL(str(so_path), mode=ctypes.RTLD_LOCAL)
         self.lib.ref_net_create.restype = ctypes.c_void_p
         self.lib.ref_net_time_forward.restype = ctypes.c_double
         if hasattr(self.lib, "ref_modelbin_load_mem"):
@@ -203,6 +215,15 @@ class Reference:
         buf = ctypes.create_string_buffer(blob + b"\0" * 64, len(blob) + 64)
         n = self.lib.ref_modelbin_load_mem(ctypes.cast(buf, ctypes.POINTER(ctypes.c_ubyte)), w, type_, _fp(out))
         return (None, -1) if n < 0 else (out[:w].copy(), int(n))
+
+    def from_pixels(self, pixels: np.ndarray, type_: int, target_w: int = 0, target_h: int = 0):
+        """ncnn::Mat::from_pixels / from_pixels_resize of the reference on one (h, w[, c]) uint8 image -> (C, th, tw) or None."""
+        pixels = np.ascontiguousarray(pixels, np.uint8)
+        h, w = pixels.shape[:2]
+        tw, th = target_w or w, target_h or h
+        out = np.zeros((4, th, tw), np.float32)
+        c = self.lib.ref_from_pixels(pixels.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)), type_, w, h, tw, th, _fp(out))
+        return None if c < 0 else out[:c].copy()
 
     def conv(self, p: ConvParam, x, w, b=None, algo: int = -1, repeat: int = 1):
         x = np.ascontiguousarray(x, np.float32)
@@ -222,8 +243,8 @@ class Reference:
 class ReferenceNet:
     """feather::Net of the unmodified reference (LoadParam/LoadWeights/FeedInput/Forward/Extract)."""
 
-    def __init__(self, param_path: str, bin_path: str):
-        self.ref = Reference()
+    def __init__(self, param_path: str, bin_path: str, ref: "Reference | None" = None):
+        self.ref = ref or Reference()
         self.h = ctypes.c_void_p(self.ref.lib.ref_net_create())
         rc = self.ref.lib.ref_net_load(self.h, str(param_path).encode(), str(bin_path).encode())
         if rc != 0:
@@ -256,6 +277,89 @@ class ReferenceNet:
             self.ref.lib.ref_net_destroy(self.h)
         except Exception:
             pass
+
+
+# --------------------------------------------------------------------------------------------------
+# Input staging restatement (ncnn::Mat::from_pixels[_resize] + substract_mean_normalize), NumPy
+# --------------------------------------------------------------------------------------------------
+PIXEL_RGB, PIXEL_BGR, PIXEL_GRAY, PIXEL_RGBA = 1, 2, 4, 8  # mat.h:126-129; conversions = from | (to << 16)
+
+
+def _pixel_plan(type_: int):
+    """(source channels, gray?, channel map) following Mat::from_pixels, mat_pixel.cpp:1329-1367."""
+    frm, to = type_ & 0xffff, type_ >> 16
+    src_c = {PIXEL_RGB: 3, PIXEL_BGR: 3, PIXEL_GRAY: 1, PIXEL_RGBA: 4}.get(frm)
+    if src_c is None:
+        return None
+    if to == 0:
+        return src_c, False, list(range(src_c))
+    if (frm, to) in ((PIXEL_RGB, PIXEL_BGR), (PIXEL_BGR, PIXEL_RGB), (PIXEL_RGBA, PIXEL_BGR)):
+        return src_c, False, [2, 1, 0]
+    if (frm, to) == (PIXEL_RGBA, PIXEL_RGB):
+        return src_c, False, [0, 1, 2]
+    if frm == PIXEL_GRAY and to in (PIXEL_RGB, PIXEL_BGR):
+        return src_c, False, [0, 0, 0]
+    if to == PIXEL_GRAY and frm in (PIXEL_RGB, PIXEL_RGBA):
+        return src_c, True, [0, 1, 2]
+    if to == PIXEL_GRAY and frm == PIXEL_BGR:
+        return src_c, True, [2, 1, 0]
+    return None
+
+
+def _resize_coef(n_dst: int, n_src: int):
+    """xofs / ialpha of resize_bilinear_c* (mat_pixel_resize.cpp:52-74): float coefficients -> 11-bit shorts."""
+    scale = np.float64(n_src) / np.float64(n_dst)
+    d = np.arange(n_dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    lo = s < 0
+    s[lo], f[lo] = 0, 0.0
+    hi = s >= n_src - 1
+    s[hi], f[hi] = n_src - 2, 1.0
+    a0 = ((np.float32(1.0) - f) * np.float32(2048.0)).astype(np.float32)
+    a1 = (f * np.float32(2048.0)).astype(np.float32)
+    sat = lambda x: np.clip((x + np.where(x >= 0, np.float32(0.5), np.float32(-0.5))).astype(np.int64), -32768, 32767)
+    return s, sat(a0), sat(a1)
+
+
+def resize_bilinear_u8(img: np.ndarray, tw: int, th: int) -> np.ndarray:
+    """resize_bilinear_c1/c3/c4 (mat_pixel_resize.cpp:26-278): (h, w, c) uint8 -> (th, tw, c) uint8, bit-exact."""
+    h, w, c = img.shape
+    sx, a0, a1 = _resize_coef(tw, w)
+    sy, b0, b1 = _resize_coef(th, h)
+    src = img.astype(np.int64)
+    to_short = lambda v: ((v + 32768) % 65536) - 32768
+    rows = to_short((src[:, sx, :] * a0[None, :, None] + src[:, sx + 1, :] * a1[None, :, None]) >> 4)  # (h, tw, c)
+    r0, r1 = rows[sy], rows[sy + 1]
+    v = (to_short((b0[:, None, None] * r0) >> 16) + to_short((b1[:, None, None] * r1) >> 16) + 2) >> 2
+    return (v % 256).astype(np.uint8)
+
+
+def from_pixels(img: np.ndarray, type_: int, target_w: int = 0, target_h: int = 0, mean=None, norm=None):
+    """Mat::from_pixels[_resize] then Mat::substract_mean_normalize (mat.cpp:30-107) -> (C, H, W) float32, or None."""
+    plan = _pixel_plan(type_)
+    if plan is None:
+        return None
+    src_c, gray, cmap = plan
+    img = np.ascontiguousarray(img, np.uint8).reshape(img.shape[0], img.shape[1], src_c)
+    h, w = img.shape[:2]
+    tw, th = target_w or w, target_h or h
+    if (tw, th) != (w, h):
+        img = resize_bilinear_u8(img, tw, th)
+    p = img.astype(np.int64)
+    if gray:  # mat_pixel.cpp:545-548,627
+        out = ((p[..., cmap[0]] * 77 + p[..., cmap[1]] * 150 + p[..., cmap[2]] * 29) >> 8)[None].astype(np.float32)
+    else:
+        out = np.stack([p[..., i] for i in cmap]).astype(np.float32)
+    if mean is not None and norm is None:
+        out = out + (-np.asarray(mean, np.float32))[:, None, None]
+    elif mean is None and norm is not None:
+        out = out * np.asarray(norm, np.float32)[:, None, None]
+    elif mean is not None:
+        n32, m32 = np.asarray(norm, np.float32), np.asarray(mean, np.float32)
+        out = out * n32[:, None, None] + (-m32 * n32)[:, None, None]
+    return out.astype(np.float32)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -4,8 +4,10 @@
 //   booster::ConvBooster            /root/reference/src/booster/include/booster/booster.h:151-170
 //   feather::Net                    /root/reference/src/net.h:30-70
 //   ncnn::ModelBinFromMemory        /root/reference/src/ncnn/modelbin.h:55-65 (weight-blob decoder: fp32 / fp16 / LUT)
+//   ncnn::Mat::from_pixels[_resize] /root/reference/src/ncnn/mat.h:149-152 (input staging)
 // Used by tests/ (parity oracle), __graft_entry__.smoke() and bench.py's CPU baseline.
 #include <booster/booster.h>
+#include <ncnn/mat.h>
 #include <ncnn/modelbin.h>
 #include <net.h>
 
@@ -194,6 +196,18 @@ long ref_modelbin_load_mem(const unsigned char* buf, int w, int type, float* out
     if (m.empty()) return -1;
     memcpy(out, m.data, sizeof(float) * static_cast<size_t>(w));
     return static_cast<long>(mem - buf);
+}
+
+// ncnn::Mat::from_pixels / from_pixels_resize of the reference (mat_pixel.cpp:1329-1410, mat_pixel_resize.cpp) -> dense
+// planar floats.  Returns the number of output channels, or -1 when the reference returned an empty Mat.
+int ref_from_pixels(const unsigned char* pixels, int type, int w, int h, int target_w, int target_h, float* out) {
+    Quiet q;
+    ncnn::Mat m = (target_w == w && target_h == h) ? ncnn::Mat::from_pixels(pixels, type, w, h)
+                                                   : ncnn::Mat::from_pixels_resize(pixels, type, w, h, target_w, target_h);
+    if (m.empty()) return -1;
+    const size_t plane = static_cast<size_t>(m.w) * m.h;
+    for (int c = 0; c < m.c; ++c) memcpy(out + plane * c, m.channel(c), sizeof(float) * plane);
+    return m.c;
 }
 
 }  // extern "C"

@@ -112,9 +112,11 @@ def test_unsupported_algorithms_return_minus_one(cuda, oracle):
     s, k = ctypes.c_size_t(), ctypes.c_size_t()
     # unselected and crashing upstream, avx/booster.cpp:258,291-292
     assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), booster.WINOGRADF63FUSED, 1, ctypes.byref(s), ctypes.byref(k)) == -1
-    # grouped (non-depthwise) convolution is unsupported by every algorithm, like upstream
+    # grouped (non-depthwise) convolution: -1 like upstream (avx/booster.cpp:304-308) for every algorithm but the grouped
+    # implicit GEMM, this engine's extension (tests/test_gpu_ext.py)
     bad = booster.ConvParam.make(64, 64, 16, 16, 3, pad=1, group=4)
-    for algo in (booster.SGECONV, booster.IM2COL, booster.WINOGRADF63, booster.DEPTHWISE):
+    assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(bad), booster.SGECONV, 1, ctypes.byref(s), ctypes.byref(k)) == 0
+    for algo in (booster.IM2COL, booster.WINOGRADF63, booster.DEPTHWISE):
         assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(bad), algo, 1, ctypes.byref(s), ctypes.byref(k)) == -1
     pg = booster.ConvParam.make(64, 64, 16, 16, 3, pad=1, group=4)  # partial groups: avx/booster.cpp:304-308
     a = ctypes.c_int()
@@ -244,3 +246,40 @@ def test_full_size_linearity_vgg_conv(cuda):
     want = (2.0 * y1 + y2)
     err = (y3 - want).abs().max().item() / want.abs().max().item()
     assert err < 2e-4
+
+
+@pytest.mark.parametrize("algo_name,geom", [
+    ("WINOGRADF63", (32, 16, 24, 24, 1)),      # whole tiles
+    ("WINOGRADF63", (64, 32, 15, 13, 1)),      # odd output: clipped windows, partial tiles
+    ("WINOGRADF63", (256, 128, 56, 56, 1)),    # VGG conv3-class, several tile rows
+    ("WINOGRADF23", (16, 16, 10, 14, 1)),
+    ("SGECONV", (64, 64, 64, 96, 1)),          # slab kernel, two issuers, several tiles per image
+    ("SGECONV", (64, 32, 15, 13, 1)),          # odd output, partial 4 x 32 patches
+    ("SGECONV", (128, 64, 112, 112, 1)),       # BN = 128 (one issuer), VGG conv2_1 shape
+    ("SGECONV", (32, 32, 30, 70, 0)),          # no padding
+])
+def test_conv_with_fused_max_pool(cuda, algo_name, geom):
+    """fcuda_conv_forward_pool == the convolution followed by PoolingLayer (2x2 / s2 / pad 0 / max, ceil mode,
+    pooling_layer.h:38-91,129-130): max commutes exactly with the per-channel bias and with ReLU, so the fused result is
+    bit-identical to pooling the unfused output."""
+    from feathercnn_b200 import booster
+    booster.set_precision(booster.PRECISION_TF32X3)
+    oc, ic, h, w, pad = geom
+    rng = np.random.default_rng(oc * 7 + h)
+    x = cuda.from_numpy(rng.uniform(-0.5, 0.5, (3, ic, h, w)).astype(np.float32)).cuda()
+    wt = cuda.from_numpy((rng.standard_normal((oc, ic, 3, 3)) * np.sqrt(2.0 / (ic * 9))).astype(np.float32)).cuda()
+    b = cuda.from_numpy(rng.uniform(-0.1, 0.1, oc).astype(np.float32)).cuda()
+    algo = getattr(booster, algo_name)
+    for relu in (True, False):
+        p = booster.ConvParam.make(oc, ic, h, w, 3, pad=pad, relu=relu)
+        plain, _ = booster.conv_forward(p, x, wt, b, algo=algo)
+        want = booster.pooling(plain, 0, 2, 2, 2, 2, 0, 0, 0, 0)
+        got, _ = booster.conv_forward(p, x, wt, b, algo=algo, pool=True)
+        cuda.cuda.synchronize()
+        assert got.shape == want.shape
+        np.testing.assert_array_equal(got.cpu().numpy(), want.cpu().numpy())
+    # algorithms that cannot pool in their epilogue say so
+    p = booster.ConvParam.make(oc, ic, h, w, 3, pad=pad)
+    with pytest.raises(booster.FcudaError) as e:
+        booster.conv_forward(p, x, wt, b, algo=booster.IM2COL, pool=True)
+    assert e.value.code == -200

@@ -117,3 +117,59 @@ def test_softmax_large_and_relu_unaligned(cuda, restatement):
     yd = _t(cuda, y)
     np.testing.assert_array_equal(booster.relu(yd).cpu().numpy(), np.maximum(y, 0))
     np.testing.assert_array_equal(booster.relu(yd[1:].clone()).cpu().numpy(), np.maximum(y[1:], 0))
+
+
+def test_from_pixels_resize_mean_normalize(cuda, oracle):
+    """fcuda_from_pixels: every ncnn pixel type, with and without the fixed-point bilinear resize, bit-exact against the
+    reference's from_pixels[_resize] (or its pinned NumPy restatement when oracle/_ref is absent); mean / norm variants of
+    Mat::substract_mean_normalize (mat.cpp:30-107) to fp32 rounding."""
+    from feathercnn_b200 import booster
+    from test_oracle import PIXEL_TYPES
+    ref = oracle.Reference() if oracle.reference_available() else None
+    rng = np.random.default_rng(1)
+    for (h, w, tw, th) in [(32, 48, 0, 0), (37, 53, 224, 224), (240, 320, 224, 224), (17, 9, 40, 31), (2, 2, 5, 7)]:
+        for t, c in PIXEL_TYPES:
+            imgs = rng.integers(0, 256, (3, h, w, c), dtype=np.uint8)
+            got = booster.from_pixels(cuda.from_numpy(imgs).cuda(), t, tw, th).cpu().numpy()
+            for n in range(3):
+                want = ref.from_pixels(imgs[n], t, tw, th) if ref else oracle.from_pixels(imgs[n], t, tw, th)
+                np.testing.assert_array_equal(got[n], want, err_msg=f"type {t:#x} {w}x{h}->{tw}x{th} image {n}")
+    imgs = rng.integers(0, 256, (2, 60, 80, 3), dtype=np.uint8)
+    mean, norm = [104.0, 117.0, 123.0], [0.017, 0.0175, 0.0171]
+    for m, s in ((mean, None), (None, norm), (mean, norm)):
+        got = booster.from_pixels(cuda.from_numpy(imgs).cuda(), 1 | (2 << 16), 32, 24, mean=m, norm=s).cpu().numpy()
+        for n in range(2):
+            want = oracle.from_pixels(imgs[n], 1 | (2 << 16), 32, 24, mean=m, norm=s)
+            np.testing.assert_allclose(got[n], want, rtol=2e-6, atol=1e-6)
+    with pytest.raises(booster.FcudaError) as e:
+        booster.from_pixels(cuda.from_numpy(imgs).cuda(), 3)
+    assert e.value.code == -200
+
+
+def test_net_feed_input_pixels(cuda, oracle, model_dir):
+    """Net::FeedInputPixels == from_pixels_resize + substract_mean_normalize + FeedInput, then Forward, against the
+    reference chain on the CPU."""
+    from feathercnn_b200.net import Net
+    from feathercnn_b200.tools import modelgen
+    m = modelgen.mini()
+    param, binf = m.save(model_dir / "mini_px")
+    c, h, w = m.shape["data"]
+    rng = np.random.default_rng(2)
+    n_src_c = 4 if c == 3 else c
+    if c not in (1, 3, 4):
+        pytest.skip("mini net input is not an image")
+    t = {1: 4, 3: 8 | (2 << 16), 4: 8}[c]   # GRAY, RGBA->BGR, RGBA
+    imgs = rng.integers(0, 256, (2, 50, 70, {1: 1, 3: 4, 4: 4}[c]), dtype=np.uint8)
+    mean, norm = [120.0] * c, [1.0 / 128] * c
+    net = Net()
+    net.LoadParam(param)
+    net.LoadWeights(binf)
+    net.FeedInputPixels(imgs, t, w, h, mean, norm)
+    net.Forward()
+    got = net.Extract("prob")
+    cpu = oracle.ReferenceNet(param, binf) if oracle.reference_available() else oracle.OracleNet(param, binf)
+    for n in range(2):
+        x = oracle.from_pixels(imgs[n], t, w, h, mean=mean, norm=norm)
+        cpu.forward(x)
+        want = cpu.extract("prob")
+        assert np.abs(got[n].reshape(want.shape) - want).max() / np.abs(want).max() < 2e-4

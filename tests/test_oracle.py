@@ -117,3 +117,23 @@ def test_pooling_quirks(restatement):
     out = restatement.pooling(x, 0, 3, 3, 2, 2, 1, 1, 1, 1, False)
     assert out.shape == (1, 3, 3) or out.shape == (1, 2, 2)
     assert out[0, 0, 0] == x[0, 0, 0]
+
+
+PIXEL_TYPES = [(1, 3), (2, 3), (4, 1), (8, 4), (1 | (2 << 16), 3), (2 | (1 << 16), 3), (1 | (4 << 16), 3), (2 | (4 << 16), 3),
+               (4 | (1 << 16), 1), (4 | (2 << 16), 1), (8 | (1 << 16), 4), (8 | (2 << 16), 4), (8 | (4 << 16), 4)]
+
+
+def test_pixel_staging_restatement_is_bit_exact_with_the_reference(oracle, reference):
+    """Input staging (SURVEY.md §8f rank 3): the NumPy restatement of ncnn::Mat::from_pixels / from_pixels_resize
+    (mat_pixel.cpp:1329-1410, mat_pixel_resize.cpp:26-278 — u8 fixed-point bilinear, byte work: bit-exact bar) against the
+    unmodified reference, every pixel type, up- and down-scaling, degenerate 2x2 sources."""
+    rng = np.random.default_rng(0)
+    for (h, w, tw, th) in [(32, 48, 24, 24), (37, 53, 224, 224), (64, 64, 64, 64), (240, 320, 224, 224), (17, 9, 40, 31), (2, 2, 5, 7)]:
+        for t, c in PIXEL_TYPES:
+            img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+            want = reference.from_pixels(img, t, tw, th)
+            got = oracle.from_pixels(img, t, tw, th)
+            assert want is not None and got is not None and got.shape == want.shape
+            np.testing.assert_array_equal(got, want, err_msg=f"type {t:#x} {w}x{h}->{tw}x{th}")
+    assert oracle.from_pixels(np.zeros((4, 4, 3), np.uint8), 3) is None          # unknown type: empty Mat upstream
+    assert reference.from_pixels(np.zeros((4, 4, 3), np.uint8), 3) is None
