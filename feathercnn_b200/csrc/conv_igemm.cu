@@ -69,7 +69,8 @@ constexpr int kGroups = 3;                                // producer groups, 4 
 constexpr int kWarpTma = 4 + 4 * kGroups;                  // warps 0-3 epilogue, 4.. producers (quadrant = warp % 4),
 constexpr int kWarpMma = kWarpTma + 1;                    // then one TMA(B) warp and TWO MMA-issuer warps (see the kernel)
 constexpr int kIssuers = 2;
-constexpr int kThreadsIg = (kWarpMma + kIssuers) * 32;
+constexpr int kWarpSlab = kWarpMma + kIssuers;             // SLAB kernels: TMA producer of the input slabs (idle otherwise)
+constexpr int kThreadsIg = (kWarpSlab + 1) * 32;
 constexpr int kStagesIg = 4;                              // ring depth shared by the smem B tiles and the TMEM A tiles
 constexpr int kMaxTableK = 8192;                          // k-table entries that fit beside the B ring
 
@@ -113,6 +114,7 @@ struct IgemmArgs {
     int acc_stride;          // TMEM columns per accumulator slot: BN, or 2*BN with two issuers (one accumulator each)
     int acc_slots;           // accumulator ring depth = accumulator columns / acc_stride (power of two, <= 4)
     int pool;                // SLAB only: fuse a following 2x2 / stride-2 max pooling; `out` is the pooled blob
+    int2 ktab1[32];          // use_table == 2 (K <= 32, e.g. IC = 3 first layers): the k-table in the kernel parameters
     int taps;                // KH*KW
     unsigned tap_inv;        // ceil(65536 / KW): tap / KW == (tap * tap_inv) >> 16 for tap < 64
 };
@@ -154,11 +156,24 @@ __device__ __forceinline__ BoxCoord decode_patch(uint32_t ptile, const IgemmArgs
 __device__ __forceinline__ int patch_row(int q, int lane) { return 2 * (q >> 1) + (lane >> 4); }
 __device__ __forceinline__ int patch_col(int q, int lane) { return 16 * (q & 1) + (lane & 15); }
 
-// 3x3 / stride-1 slab: 32 channels x 6 rows x 34 columns of (hi, lo) pairs = the input halo of a 4 x 32 output patch
-constexpr int kSlabRows = 6, kSlabCols = 34;
-constexpr int kSlabChStride = kSlabRows * kSlabCols;          // float2 elements per channel
-constexpr int kSlabBytes = 32 * kSlabChStride * 8;            // 52,224 B
-constexpr int kProducerThreads = 4 * kGroups * 32;            // 384
+// 3x3 / stride-1 slab: the raw fp32 halo of a 4 x 32 output patch for one 32-channel block, landed by TMA: a
+// {48 columns, 6 rows, 32 channels} box of the NCHW input whose first column is the patch's first column minus 4 (the TMA's
+// innermost start coordinate must be a multiple of 16 bytes — measured, tests/cuda/tma_shift.cu; negative / past-the-end
+// coordinates are zero-filled, which IS the convolution's padding).  48 columns make the row stride 16 banks, so the two
+// half-warps of the 2 x 16 lane mapping read disjoint banks.
+constexpr int kSlabRows = 6, kSlabCols = 48, kSlabShift = 4;
+constexpr int kSlabChBytes = kSlabRows * kSlabCols * 4;       // 1,152 B per channel
+constexpr int kSlabStageBytes = 32 * kSlabChBytes;            // 36,864 B per (tile, channel block)
+__host__ __device__ constexpr int slab_stages(int bn) { return bn <= 64 ? 3 : 2; }
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+        : "memory");
+}
 
 // Ring-slot release.  A producer group visits only every third k-block and the two MMA issuers retire their k-blocks
 // independently of each other, so with ONE mbarrier per slot "the MMAs of k-block g-4 have retired" cannot be read off the
@@ -178,10 +193,6 @@ __device__ __forceinline__ void wait_ring_slot_free(uint64_t (*empty_bar)[STAGES
         const uint32_t gg = g - STAGES;  // the k-block that used this slot one round earlier
         ptx::mbar_wait(ring_release_bar<STAGES>(empty_bar, gg), ((gg / STAGES) >> 1) & 1u);
     }
-}
-
-__device__ __forceinline__ void producer_bar_sync() {  // named barrier 1: the twelve producer warps only
-    asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
 }
 
 // D[tmem] (+)= A[tmem] * B[smem]
@@ -208,7 +219,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 template <int BN, int PLANES, bool SLAB>
 __global__ void __launch_bounds__(kThreadsIg, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
-                  const IgemmArgs args) {
+                  const __grid_constant__ CUtensorMap tmIn, const IgemmArgs args) {
     constexpr int STAGES = kStagesIg;
     constexpr int kBTile = BN * 32 * 4;
     constexpr int kStage = PLANES * kBTile;                 // smem per stage: [B_hi][B_lo]
@@ -230,6 +241,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // + 1 arrive.expect_tx of the TMA warp (B bytes landed) -> the MMA thread makes ONE wait per k-block
     __shared__ uint64_t full_bar[STAGES];
     __shared__ uint64_t empty_bar[2][STAGES];  // MMAs that read the stage have retired; [round parity][slot], see wait_ring_slot_free
+    __shared__ uint64_t slab_full[3];    // SLAB: TMA landed the slab of an item (tile, channel block)
+    __shared__ uint64_t slab_empty[3];   // SLAB: all twelve producer warps have served the item's nine taps
     __shared__ uint64_t tmem_full_bar[ACC];
     __shared__ uint64_t tmem_empty_bar[ACC];
     __shared__ uint32_t tmem_base_smem;
@@ -250,13 +263,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             ptx::mbar_init(&tmem_full_bar[s], static_cast<uint32_t>(args.issuers));  // every issuer commits its own MMAs
             ptx::mbar_init(&tmem_empty_bar[s], 4);
         }
+        for (int s = 0; s < 3; ++s) {
+            ptx::mbar_init(&slab_full[s], 1);
+            ptx::mbar_init(&slab_empty[s], 4 * kGroups);
+        }
         ptx::fence_barrier_init();
     }
     if (warp == kWarpTma && lane == 0) {
         ptx::prefetch_tensormap(&tmW);
         if (PLANES == 2) ptx::prefetch_tensormap(&tmWlo);
+        if (SLAB) ptx::prefetch_tensormap(&tmIn);
     }
-    if (args.use_table) {
+    if (args.use_table == 1) {
         for (int k = threadIdx.x; k < kblocks * 32; k += kThreadsIg) {
             int2 e = make_int2(0, 63);  // padding rows: tap 63 is never valid
             if (k < args.K) {
@@ -268,10 +286,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         }
     }
     // bias copy (zeros when the layer has none): the epilogue reads it with broadcast LDS.128
-    float* bias_s = reinterpret_cast<float*>(smem + STAGES * kStage + (args.use_table ? kblocks * 32 * 8 : 0));
-    // SLAB: one (BN = 128) or two (BN <= 64) input slabs behind the bias copy, 16-byte aligned
-    constexpr int NSLAB = BN <= 64 ? 2 : 1;
-    float2* slab0 = reinterpret_cast<float2*>(smem + STAGES * kStage + ((args.oc_pad * 4 + 15) & ~15));
+    // SLAB: the input-slab ring sits right behind the filter ring (both multiples of 1 KB), then the bias copy
+    constexpr int SST = slab_stages(BN);
+    uint8_t* slab0 = smem + STAGES * kStage;
+    float* bias_s = reinterpret_cast<float*>(smem + STAGES * kStage + (SLAB ? SST * kSlabStageBytes : 0) +
+                                             (args.use_table == 1 ? kblocks * 32 * 8 : 0));
+
     for (int i = threadIdx.x; i < args.oc_pad; i += kThreadsIg)
         bias_s[i] = (args.bias != nullptr && i < args.OC) ? __ldg(args.bias + i) : 0.f;
     if (warp == kWarpMma) {
@@ -306,7 +326,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= kWarpMma) {
+    } else if (warp >= kWarpMma && warp < kWarpSlab) {
         // ===================== MMA issuers: two elected threads alternate k-blocks =====================
         // Measured on B200 (tests/cuda/mma_rate.cu, tests/cuda/igemm_trace.cu): a TS-form kind::tf32 MMA of N columns
         // executes in N/2 cycles; the pipe holds ~6 MMAs and ISSUE BLOCKS beyond that; a pipe that has run dry needs
@@ -362,118 +382,78 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 kb += static_cast<int>(nissue);
             }
         }
+    } else if (warp == kWarpSlab) {
+        // ===================== SLAB: TMA producer of the input slabs =====================
+        // one {48 x 6 x 32} box per item (tile, channel block), SST items ahead of the producers
+        if (SLAB) {
+            const bool leader = ptx::elect_one();
+            const int cblocks = args.IC >> 5;
+            uint32_t j = 0;
+            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+                const BoxCoord bx = decode_patch(ptile, args);
+                for (int cb = 0; cb < cblocks; ++cb, ++j) {
+                    const uint32_t st = j % SST;
+                    ptx::mbar_wait(&slab_empty[st], ((j / SST) & 1u) ^ 1u);
+                    if (leader) {
+                        ptx::mbar_arrive_expect_tx(&slab_full[st], kSlabStageBytes);
+                        tma_load_4d(slab0 + st * kSlabStageBytes, &tmIn, &slab_full[st], bx.ox0 - kSlabShift,
+                                    bx.oy - args.pad_top, cb * 32, bx.n);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
     } else if (SLAB && warp >= 4) {
         // ===================== A producers, 3x3 stride-1 slab variant =====================
-        // The generic producers below gather every k-block from global memory and split it, i.e. each input element
-        // is loaded and split NINE times (once per tap) at 4.3 instructions per element — the issue-bound part of VGG
-        // conv1_2 (tensor pipe 59 %).  Here the twelve producer warps first stage the halo of the tile's 4 x 32 output
-        // patch for one 32-channel block — 6 rows x 34 columns x 32 channels — into shared memory ONCE, already split
-        // into (hi, lo) pairs (coalesced LDG along x, one STS.64 per element; zero padding and image edges by predicate);
-        // the nine taps are then 32 LDS.64 + 8 tcgen05.st per thread and k-block, addresses = one base + immediates.
-        // Item = (tile, channel block); its 9 k-blocks go round-robin to the 3 groups, so group g always serves the taps
-        // of kernel COLUMN g (v = g, u = 0..2).  Loads of item j+1 are in flight while the taps of item j run.
-        const int pt = static_cast<int>(threadIdx.x) - 128;   // 0..383
+        // The generic producers below gather every k-block from global memory: each input element is loaded NINE times
+        // (once per tap) with an IMAD.WIDE + LDG + LOP + FADD each, issue-bound at N = 64 (VGG conv1_2).  Here the halo of
+        // the tile's 4 x 32 output patch for one 32-channel block arrives ONCE by TMA (see above: no load instructions,
+        // no register staging, padding by the OOB fill, SST items of prefetch), and a k-block = one tap is 32 LDS.32
+        // with immediate offsets + the 2-instruction TF32 split + 8 tcgen05.st per thread.  The item's 9 k-blocks go
+        // round-robin to the 3 groups, so group g always serves kernel COLUMN g (v = g, u = 0..2).
+        (void)plane;
         const int pw = warp - 4;                               // 0..11
         const int group = pw >> 2;
         const int q = warp & 3;
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
         const int cblocks = args.IC >> 5;
-        const uint32_t plane_bytes = static_cast<uint32_t>(plane) * 4u;
-        // fill roles: warp pw stages slab row fr of channels fc0 .. fc0+15 (lane = column 0..31); thread pt additionally
-        // stages ONE element of the two tail columns: line (pt >> 1) = channel * 6 + row, column 32 + (pt & 1)
-        const int fr = pw % kSlabRows, fc0 = (pw / kSlabRows) * 16;
-        const int tl_line = pt >> 1, tl_c = 32 + (pt & 1);
-        const int tl_cl = tl_line / kSlabRows, tl_r = tl_line - tl_cl * kSlabRows;
-
-        long long tile = blockIdx.x;
-        int cb = 0;
-        bool have = tile < total_tiles;
-        float v[16], vt = 0.f;
-        auto load_item = [&](long long t, int cbl) {
-            const uint32_t ptile = fast_div(static_cast<uint32_t>(t), args.m_num_n, args.num_n);
-            const BoxCoord bx = decode_patch(ptile, args);
-            const bool tile_ok = bx.valid;
-            const float* img = args.in + (static_cast<long long>(tile_ok ? bx.n : 0) * args.in_img_c + cbl * 32) * plane;
-            const int iy0 = bx.oy - args.pad_top, ix0 = bx.ox0 - args.pad_left;
-            {
-                const int iy = iy0 + fr, ix = ix0 + lane;
-                const bool ok = tile_ok && static_cast<unsigned>(iy) < static_cast<unsigned>(args.H) &&
-                                static_cast<unsigned>(ix) < static_cast<unsigned>(args.W);
-                const char* p = reinterpret_cast<const char*>(img + static_cast<long long>(fc0) * plane +
-                                                              static_cast<long long>(iy) * args.W + ix);
-                asm volatile("" : "+l"(p));  // opaque base: one IMAD.WIDE per load
-                if (__all_sync(0xffffffffu, ok)) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        v[i] = __ldg(reinterpret_cast<const float*>(p + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(i)));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        v[i] = ok ? __ldg(reinterpret_cast<const float*>(p + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(i))) : 0.f;
-                }
-            }
-            {
-                const int iy = iy0 + tl_r, ix = ix0 + tl_c;
-                const bool ok = tile_ok && static_cast<unsigned>(iy) < static_cast<unsigned>(args.H) &&
-                                static_cast<unsigned>(ix) < static_cast<unsigned>(args.W);
-                vt = ok ? __ldg(img + static_cast<long long>(tl_cl) * plane + static_cast<long long>(iy) * args.W + ix) : 0.f;
-            }
-        };
-        auto split_pair = [](float x) {
-            float2 r;
-            r.x = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-            r.y = PLANES == 2 ? x - r.x : 0.f;
-            if (PLANES == 1) r.x = x;
-            return r;
-        };
-
-        if (have) load_item(tile, cb);
+        // this lane's pixel inside the patch (2 x 16 sub-patch per warp) and its first slab element for tap row 0
+        const int lane_off = (patch_row(q, lane) * kSlabCols + patch_col(q, lane) + group - args.pad_left + kSlabShift) * 4;
         uint32_t j = 0;  // running item index of this CTA; its k-blocks are 9j .. 9j+8
-        while (have) {
-            float2* slab = slab0 + (NSLAB == 2 ? (j & 1u) : 0u) * (kSlabBytes / 8);
-            if (NSLAB == 1) producer_bar_sync();  // single slab: every group has finished the taps of item j-1
-            {
-                float2* sp = slab + (fc0 * kSlabRows + fr) * kSlabCols + lane;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) sp[i * kSlabChStride] = split_pair(v[i]);
-                slab[tl_line * kSlabCols + tl_c] = split_pair(vt);
-            }
-            producer_bar_sync();  // item j is staged (two slabs: this also orders the taps of j-1 before the fill of j+1)
-            // cursor to the next item; its loads fly while this item's taps run
-            int ncb = cb + 1;
-            long long ntile = tile;
-            if (ncb == cblocks) { ncb = 0; ntile += gridDim.x; }
-            const bool nhave = ntile < total_tiles;
-            if (nhave) load_item(ntile, ncb);
-            // taps (u, v = group) for u = 0..2: k-block 9j + 3u + group
-            const char* tb = reinterpret_cast<const char*>(slab + patch_row(q, lane) * kSlabCols + patch_col(q, lane) + group);
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int cb = 0; cb < cblocks; ++cb, ++j) {
+                const uint32_t st = j % SST;
+                ptx::mbar_wait(&slab_full[st], (j / SST) & 1u);
+                const char* tb = reinterpret_cast<const char*>(slab0 + st * kSlabStageBytes) + lane_off;
 #pragma unroll 1
-            for (int u = 0; u < 3; ++u) {
-                const uint32_t g = j * 9u + static_cast<uint32_t>(3 * u + group);
-                const int my_stage = static_cast<int>(g & (STAGES - 1));
-                const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
-                const char* src = tb + u * (kSlabCols * 8);
-                wait_ring_slot_free<STAGES>(empty_bar, g);
-                ptx::tc_fence_after();
+                for (int u = 0; u < 3; ++u) {
+                    const uint32_t g = j * 9u + static_cast<uint32_t>(3 * u + group);
+                    const int my_stage = static_cast<int>(g & (STAGES - 1));
+                    const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
+                    const char* src = tb + u * (kSlabCols * 4);
+                    wait_ring_slot_free<STAGES>(empty_bar, g);
+                    ptx::tc_fence_after();
 #pragma unroll
-                for (int part = 0; part < 4; ++part) {
-                    uint32_t hi[8], lo[8];
+                    for (int part = 0; part < 4; ++part) {
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const float2 e = *reinterpret_cast<const float2*>(src + (part * 8 + r) * (kSlabChStride * 8));
-                        hi[r] = __float_as_uint(e.x);
-                        lo[r] = __float_as_uint(e.y);
+                        for (int r = 0; r < 8; ++r) {
+                            const float x = *reinterpret_cast<const float*>(src + (part * 8 + r) * kSlabChBytes);
+                            hi[r] = PLANES == 2 ? (__float_as_uint(x) & 0xFFFFE000u) : __float_as_uint(x);
+                            lo[r] = __float_as_uint(x - __uint_as_float(hi[r]));
+                        }
+                        tmem_st_32x8(ta + part * 8, hi);
+                        if (PLANES == 2) tmem_st_32x8(ta + 32 + part * 8, lo);
                     }
-                    tmem_st_32x8(ta + part * 8, hi);
-                    if (PLANES == 2) tmem_st_32x8(ta + 32 + part * 8, lo);
+                    tmem_st_wait();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&full_bar[my_stage]);
                 }
-                tmem_st_wait();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&full_bar[my_stage]);
+                // (the __syncwarp above orders every lane's slab reads before the release)
+                if (lane == 0) ptx::mbar_arrive(&slab_empty[st]);
             }
-            tile = ntile; cb = ncb; have = nhave;
-            ++j;
         }
     } else if (!SLAB && warp >= 4) {
         // ===================== A producers: gather + 3xTF32 split -> tensor memory =====================
@@ -565,6 +545,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         x[r] = kb_ok ? __ldg(reinterpret_cast<const float*>(
                                            kp + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(r)))
                                      : 0.f;
+                }
+            } else if (args.use_table == 2) {
+                // single k-block (K <= 32): offsets and taps come from the kernel parameters (constant bank, compile-time
+                // index) — the shared-memory table put an LDS + dependent LDG chain on every element (55 % of the
+                // producers' stall cycles on VGG conv1_1, ncu r02f)
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const int2 e = args.ktab1[r];
+                    x[r] = ((tapmask >> e.y) & 1ull) ? __ldg(base + e.x) : 0.f;
                 }
             } else {
 #pragma unroll
@@ -845,9 +834,19 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     const long long total = a.pixel_tiles * a.num_n;
     const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
     constexpr int kStage = PLANES * BN * 32 * 4;
-    const int table_bytes = a.use_table ? a.kblocks * 32 * 8 : 0;
-    constexpr int kSlabs = BN <= 64 ? 2 : 1;
-    const int smem = kStagesIg * kStage + table_bytes + ((a.oc_pad * 4 + 15) & ~15) + (SLAB ? kSlabs * kSlabBytes : 0) + 1024;
+    if (a.use_table && a.kblocks == 1) {
+        a.use_table = 2;
+        for (int k = 0; k < 32; ++k) {
+            a.ktab1[k] = make_int2(0, 63);  // padding rows: tap 63 is never valid
+            if (k < K) {
+                const int tap = k / p.IC, ic = k - tap * p.IC;
+                const int u = tap / p.KW, v = tap - u * p.KW;
+                a.ktab1[k] = make_int2(ic * p.H * p.W + u * a.dil_h * p.W + v * a.dil_w, tap);
+            }
+        }
+    }
+    const int table_bytes = a.use_table == 1 ? a.kblocks * 32 * 8 : 0;
+    const int smem = kStagesIg * kStage + (SLAB ? slab_stages(BN) * kSlabStageBytes : 0) + table_bytes + a.oc_pad * 4 + 1024;
     if (smem > 227 * 1024 - 2048) return -1;
     auto kern = conv_igemm_kernel<BN, PLANES, SLAB>;
     static SmemAttrCache attr_cache;
@@ -858,7 +857,21 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     const int prof = prof_begin(stream, PROF_IGEMM, 2.0 * macs, mma,
                                 4.0 * (static_cast<double>(p.N) * p.IC * p.H * p.W + static_cast<double>(p.OC) * K +
                                        static_cast<double>(p.N) * p.OC * p.OH * p.OW * (p.residual ? 2 : 1)));
-    kern<<<grid, kThreadsIg, smem, stream>>>(tmW, tmWlo, a);
+    CUtensorMap tmIn = tmW;
+    if (SLAB) {  // 4-D map over the NCHW input (or a channel slice of it): {W, H, IC, N}, box {48, 6, 32, 1}, zero OOB fill
+        cuuint64_t dims[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.IC, (cuuint64_t)p.N};
+        cuuint64_t strides[3] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.W * p.H * 4, (cuuint64_t)a.in_img_c * p.W * p.H * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kSlabCols, (cuuint32_t)kSlabRows, 32, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmIn, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.input), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            fprintf(stderr, "fcuda: igemm input tensor map failed (%d)\n", (int)r);
+            return FCUDA_ERR_CUDA;
+        }
+    }
+    kern<<<grid, kThreadsIg, smem, stream>>>(tmW, tmWlo, tmIn, a);
     prof_end(prof, stream);
     FCUDA_CHECK_LAUNCH();
     count_launch();
@@ -889,8 +902,10 @@ int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, in
 // 3x3, stride 1, dense taps, whole 32-channel blocks: the slab producer (FCUDA_IGEMM_SLAB=0 keeps the generic gather)
 static bool slab_eligible(const IgemmProblem& p) {
     static const bool off = [] { const char* e = getenv("FCUDA_IGEMM_SLAB"); return e && e[0] == '0'; }();
+    // + what the TMA needs: 16-byte rows and base (W % 4 == 0 keeps every channel / image / group slice aligned)
     return !off && p.KH == 3 && p.KW == 3 && p.stride_h == 1 && p.stride_w == 1 && p.dil_h <= 1 && p.dil_w <= 1 &&
-           p.IC % 32 == 0 && p.pad_top <= 2 && p.pad_left <= 2;
+           p.IC % 32 == 0 && p.pad_top <= 2 && p.pad_left <= 2 && p.W % 4 == 0 &&
+           (p.input == nullptr || (reinterpret_cast<uintptr_t>(p.input) & 15) == 0);
 }
 
 bool conv_igemm_can_pool(const IgemmProblem& p) { return slab_eligible(p) && p.residual == nullptr; }

@@ -468,6 +468,7 @@ int fcuda_conv_can_pool(const FcudaConvParam* p, int algo) {
         g.IC = p->input_channels / (p->group > 0 ? p->group : 1);
         g.KH = p->kernel_h; g.KW = p->kernel_w; g.stride_h = p->stride_h; g.stride_w = p->stride_w;
         g.pad_top = p->pad_top; g.pad_left = p->pad_left;
+        g.H = p->input_h; g.W = p->input_w;
         return conv_igemm_can_pool(g) ? 1 : 0;
     }
     return 0;

@@ -44,6 +44,7 @@ struct GemmKernelArgs {
     int num_m, num_n, k_blocks_total;
     long long m_offset;
     long long split_stride;
+    int tma_store;   // EPI_ROWMAJOR through shared memory + cp.async.bulk.tensor stores (tmD is valid)
 };
 
 template <int BN, int PLANES>
@@ -313,7 +314,8 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 template <int BN, int ISSUERS, int CL>
 __global__ void __launch_bounds__(kThreadsTs + 32 * (ISSUERS - 1), 1)
 tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmBlo, const GemmKernelArgs args) {
+                      const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmD,
+                      const GemmKernelArgs args) {
     constexpr int STAGES = kStagesTs;
     constexpr int kATile = kBM * kBK * 4;  // 16 KB raw A
     constexpr int kBTile = BN * kBK * 4;
@@ -565,6 +567,8 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;
         int it = 0;
+        uint32_t ebuf = 0;                                     // staging tile toggle of the TMA-store epilogue
+        uint8_t* stage_out = smem + STAGES * kStage;           // 4 warps x 2 tiles x 4 KB, 1024-byte aligned
         for (int tile = t_first; tile < total_tiles; tile += t_step, ++it) {
             const int ks = tile / (tiles_per_g * args.G);
             const int rem = tile - ks * (tiles_per_g * args.G);
@@ -577,11 +581,44 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait_relaxed(&tmem_full_bar[as], aphase);
             ptx::tc_fence_after();
-            epilogue_store<BN>(args, tmem_base, as, q, lane, g, m_blk, n_blk, ks);
+            if (args.tma_store) {
+                // Row-major D[g][m][n] (the Winograd product buffer): a thread holds ONE row of the accumulator, so direct
+                // float4 stores put every lane in a different 128-byte line — 32 sectors per instruction, ~7.4k cycles per
+                // 128 x 128 tile, more than the tile's MMAs at K <= 256 (ncu round 1: tensor pipe 41 % at K = 128, 60 % at
+                // K = 256 = MMA time / this epilogue).  Instead: 32 x 32 chunks go through a 128B-swizzled shared-memory
+                // tile (STS.128, conflict-free per quarter warp) and leave by TMA, which writes whole rows and clips the
+                // M / N tails.  Two staging tiles per warp: the store of chunk i reads while chunk i+1 is being staged.
+                const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int n0 = n_blk * BN + c0;
+                    if (n0 >= args.N) break;  // warp-uniform
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(taddr0 + c0, r);
+                    uint8_t* stg = stage_out + (q * 2 + (ebuf & 1)) * 4096;
+                    if (lane == 0) ptx::tma_store_wait_read<1>();  // the store issued two chunks ago has read this tile
+                    __syncwarp();
+                    ptx::tmem_ld_wait();
+                    uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_3d(&tmD, stg, n0, m_blk * kBM + q * 32, g);
+                        ptx::tma_store_commit();
+                    }
+                    ++ebuf;
+                }
+            } else {
+                epilogue_store<BN>(args, tmem_base, as, q, lane, g, m_blk, n_blk, ks);
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
         }
+        if (args.tma_store && lane == 0) ptx::tma_store_wait_all<0>();  // global writes done before the CTA retires
     }
 
     ptx::tc_fence_before();
@@ -711,6 +748,25 @@ static int make_map(CUtensorMap* map, const float* base, int K, int rows, int G,
     return 0;
 }
 
+// 3D map over [G][rows][cols] fp32 with explicit row / batch strides (floats) and a (box_cols x box_rows x 1) box, 128B swizzle.
+static int make_map_2(CUtensorMap* map, const float* base, int cols, int rows, int G, long long row_stride,
+                      long long batch_stride, int box_cols, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return FCUDA_ERR_CUDA;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(G)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_stride) * 4, static_cast<cuuint64_t>(batch_stride) * 4};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "fcuda: cuTensorMapEncodeTiled (D) failed (%d) cols=%d rows=%d G=%d\n", static_cast<int>(r), cols, rows, G);
+        return FCUDA_ERR_CUDA;
+    }
+    return 0;
+}
+
 bool tensor_gemm_supported(const GemmProblem& p) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.G <= 0) return false;
     if (p.K % 4 != 0) return false;
@@ -817,11 +873,21 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
     GemmKernelArgs a;
     fill_kernel_args(p, BN, &a);
     if (CL > 1) a.num_m = ceil_div(a.num_m, CL);  // work items = groups of CL consecutive M tiles
+    // row-major D leaves through shared memory + TMA (see the epilogue); needs 16-byte rows
+    static const bool tma_store_off = [] { const char* e = getenv("FCUDA_GEMM_TMA_STORE"); return e && e[0] == '0'; }();
+    CUtensorMap tmD = tmA;
+    a.tma_store = 0;
+    if (p.epilogue == EPI_ROWMAJOR && !tma_store_off && p.ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0) {
+        if ((rc = make_map_2(&tmD, p.D, p.N, p.M, p.G, p.ldd, static_cast<long long>(p.M) * p.ldd, 32, 32))) return rc;
+        a.tma_store = 1;
+    }
     const long long total = static_cast<long long>(a.num_m) * a.num_n * a.G * a.split_k;
     if (total > 0x7fffffffLL) return -1;
     constexpr int kStage = kBM * kBK * 4 + 2 * BN * kBK * 4;
     static_assert(kStagesTs * kStage + 1024 <= 227 * 1024, "smem budget");
-    const int smem = kStagesTs * kStage + 1024;
+    constexpr int kStageOut = 4 * 2 * 4096;  // epilogue staging tiles
+    static_assert(kStagesTs * kStage + kStageOut + 1024 <= 227 * 1024, "smem budget");
+    const int smem = kStagesTs * kStage + kStageOut + 1024;
     auto kern = tensor_gemm_ts_kernel<BN, ISSUERS, CL>;
     static SmemAttrCache attr_cache;
     if (int rc2 = ensure_dynamic_smem(kern, smem, attr_cache)) return rc2;
@@ -831,7 +897,7 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
         const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
         const int prof = prof_begin(stream, PROF_TENSOR_GEMM, p.algo_flops > 0 ? p.algo_flops : dense, dense * 3.0,
                                     gemm_algo_bytes(p));
-        kern<<<grid, threads, smem, stream>>>(tmA, tmB, tmBlo, a);
+        kern<<<grid, threads, smem, stream>>>(tmA, tmB, tmBlo, tmD, a);
         FCUDA_CHECK_LAUNCH();
         count_launch();
         prof_end(prof, stream);
@@ -858,7 +924,7 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
     cfg.gridDim = dim3(static_cast<unsigned>(nclusters * CL));
     const int prof = prof_begin(stream, PROF_TENSOR_GEMM, p.algo_flops > 0 ? p.algo_flops : dense, dense * 3.0,
                                 gemm_algo_bytes(p));
-    FCUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBlo, a));
+    FCUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBlo, tmD, a));
     count_launch();
     prof_end(prof, stream);
     return 0;

@@ -254,9 +254,9 @@ def test_full_size_linearity_vgg_conv(cuda):
     ("WINOGRADF63", (256, 128, 56, 56, 1)),    # VGG conv3-class, several tile rows
     ("WINOGRADF23", (16, 16, 10, 14, 1)),
     ("SGECONV", (64, 64, 64, 96, 1)),          # slab kernel, two issuers, several tiles per image
-    ("SGECONV", (64, 32, 15, 13, 1)),          # odd output, partial 4 x 32 patches
+    ("SGECONV", (64, 32, 15, 12, 1)),          # odd output height, partial 4 x 32 patches (the slab TMA needs W % 4 == 0)
     ("SGECONV", (128, 64, 112, 112, 1)),       # BN = 128 (one issuer), VGG conv2_1 shape
-    ("SGECONV", (32, 32, 30, 70, 0)),          # no padding
+    ("SGECONV", (32, 32, 30, 72, 0)),          # no padding
 ])
 def test_conv_with_fused_max_pool(cuda, algo_name, geom):
     """fcuda_conv_forward_pool == the convolution followed by PoolingLayer (2x2 / s2 / pad 0 / max, ceil mode,
@@ -283,3 +283,18 @@ def test_conv_with_fused_max_pool(cuda, algo_name, geom):
     with pytest.raises(booster.FcudaError) as e:
         booster.conv_forward(p, x, wt, b, algo=booster.IM2COL, pool=True)
     assert e.value.code == -200
+
+
+def test_fused_pool_is_refused_where_the_slab_kernel_does_not_apply(cuda):
+    """SGECONV pools only in its 3x3 / stride-1 slab kernel (IC % 32 == 0, rows of whole 16-byte units for the TMA)."""
+    from feathercnn_b200 import booster
+    from feathercnn_b200._lib import fcuda
+    ok = booster.ConvParam.make(64, 64, 16, 16, 3, pad=1)
+    assert fcuda().fcuda_conv_can_pool(ctypes.byref(ok), booster.SGECONV) == 1
+    assert fcuda().fcuda_conv_can_pool(ctypes.byref(ok), booster.WINOGRADF63) == 1
+    assert fcuda().fcuda_conv_can_pool(ctypes.byref(ok), booster.IM2COL) == 0
+    for bad in (booster.ConvParam.make(64, 64, 16, 13, 3, pad=1),   # W % 4 != 0
+                booster.ConvParam.make(64, 48, 16, 16, 3, pad=1),   # IC % 32 != 0
+                booster.ConvParam.make(64, 64, 16, 16, 3, pad=1, stride=2),
+                booster.ConvParam.make(64, 64, 16, 16, 1)):
+        assert fcuda().fcuda_conv_can_pool(ctypes.byref(bad), booster.SGECONV) == 0
