@@ -68,6 +68,8 @@ def fcuda() -> ctypes.CDLL:
             "fcuda_conv_forward_pool": (i, [P, i, vp, vp, vp, vp, vp, i, vp]),
             "fcuda_conv_forward_ext": (i, [P, i, vp, vp, vp, vp, vp, vp, i, i, i, i, vp]),
             "fcuda_eltwise_forward": (i, [vp, vp, vp, sz, i, ctypes.c_float, ctypes.c_float, i, vp]),
+            "fcuda_set_tuning": (i, [ctypes.c_char_p, i]),
+            "fcuda_get_tuning": (i, [ctypes.c_char_p]),
             "fcuda_pixel_channels": (i, [i, ctypes.POINTER(i), ctypes.POINTER(i)]),
             "fcuda_from_pixels": (i, [vp, vp, i, i, i, i, i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), i, vp]),
             "fcuda_tensor_gemm": (i, [vp, vp, vp, vp, i, i, i, i, vp]),

@@ -72,7 +72,7 @@ constexpr int kIssuers = 2;
 constexpr int kWarpSlab = kWarpMma + kIssuers;             // SLAB kernels: TMA producer of the input slabs (idle otherwise)
 constexpr int kThreadsIg = (kWarpSlab + 1) * 32;
 constexpr int kStagesIg = 4;                              // ring depth shared by the smem B tiles and the TMEM A tiles
-constexpr int kMaxTableK = 8192;                          // k-table entries that fit beside the B ring
+constexpr int kMaxTableK = 6144;                          // k-table entries that fit beside the B ring and the staging tiles
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -113,6 +113,7 @@ struct IgemmArgs {
     int issuers;             // MMA issuer threads: 2 when BN <= 64 and the tile has >= 2 k-blocks, else 1
     int acc_stride;          // TMEM columns per accumulator slot: BN, or 2*BN with two issuers (one accumulator each)
     int acc_slots;           // accumulator ring depth = accumulator columns / acc_stride (power of two, <= 4)
+    int tma_out;             // epilogue stores through shared memory + TMA (tmOut is valid); pooled tiles keep direct stores
     int pool;                // SLAB only: fuse a following 2x2 / stride-2 max pooling; `out` is the pooled blob
     int2 ktab1[32];          // use_table == 2 (K <= 32, e.g. IC = 3 first layers): the k-table in the kernel parameters
     int taps;                // KH*KW
@@ -175,6 +176,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // Ring-slot release.  A producer group visits only every third k-block and the two MMA issuers retire their k-blocks
 // independently of each other, so with ONE mbarrier per slot "the MMAs of k-block g-4 have retired" cannot be read off the
 // parity: a group whose last visit to the slot was three rounds ago sees the same parity when the lagging issuer is
@@ -208,6 +215,19 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
+// cta_group::2: one thread of the pair's leader CTA issues for both SMs (M = 256: lanes 0-127 of each CTA's tensor memory)
+__device__ __forceinline__ void umma_tf32_ts_cg2(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -216,13 +236,24 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int BN, int PLANES, bool SLAB>
+// CG = 2: a CTA PAIR (thread-block cluster of 2, cta_group::2) works on 256 output pixels x BN channels: each CTA gathers /
+// stages the A rows of ITS 128 pixels into its own tensor memory and holds HALF of the filter tile (BN/2 rows) in its own
+// shared memory; one thread of the leader CTA issues M = 256 MMAs that read A from both tensor memories and B from both
+// shared memories.  Why: every tcgen05 kernel of this engine sat at ~105 B/clk of shared-memory traffic per SM (ncu
+// r02h: MMA filter reads 64 B/clk + filter TMA writes 43 + slab LDS 43 at N = 64; tensor pipe 65 % on VGG conv1_2, 82 % on
+// conv2_x) — the pair halves the first two terms per SM.  Cross-CTA hand-offs: the peer's producers and a relay warp (which
+// watches the peer's filter TMA) arrive REMOTELY on the leader's full barrier; the leader's tcgen05.commit multicasts the
+// slot-release and accumulator-ready arrivals to both CTAs; the peer's epilogue warps release the accumulator remotely.
+template <int BN, int PLANES, bool SLAB, int CG>
 __global__ void __launch_bounds__(kThreadsIg, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
-                  const __grid_constant__ CUtensorMap tmIn, const IgemmArgs args) {
+                  const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
+                  const IgemmArgs args) {
     constexpr int STAGES = kStagesIg;
-    constexpr int kBTile = BN * 32 * 4;
+    constexpr int kBRows = BN / CG;                         // filter rows this CTA holds (CG = 2: half of the N tile)
+    constexpr int kBTile = kBRows * 32 * 4;
     constexpr int kStage = PLANES * kBTile;                 // smem per stage: [B_hi][B_lo]
+    static_assert(CG == 1 || kBRows % 8 == 0, "whole swizzle atoms per CTA");
     // accumulator ring: as deep as tensor memory allows next to the A ring (4 x 64 columns in 3xTF32 mode).  Tiles with few
     // k-blocks (IC = 3, pointwise layers) are a latency chain gather -> MMA -> epilogue; with 2 slots conv1_1 of VGG
     // spent 3.8k cycles per tile for ~1k cycles of work in any one role.
@@ -235,11 +266,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    int2* ktab = reinterpret_cast<int2*>(smem + STAGES * kStage);  // {element offset, tap index} per k
+    int2* ktab = reinterpret_cast<int2*>(smem + STAGES * kStage + 4 * ((SLAB && BN == 128 && CG == 1) ? 1 : 2) * 4096);  // {element offset, tap index} per k (non-SLAB)
 
     // one barrier per ring slot covers both operands: 4 arrivals of the owning producer group (A in tensor memory)
     // + 1 arrive.expect_tx of the TMA warp (B bytes landed) -> the MMA thread makes ONE wait per k-block
     __shared__ uint64_t full_bar[STAGES];
+    __shared__ uint64_t bfull_bar[STAGES];     // CG = 2, peer CTA: its half of the filter tile has landed (relayed to the leader)
     __shared__ uint64_t empty_bar[2][STAGES];  // MMAs that read the stage have retired; [round parity][slot], see wait_ring_slot_free
     __shared__ uint64_t slab_full[3];    // SLAB: TMA landed the slab of an item (tile, channel block)
     __shared__ uint64_t slab_empty[3];   // SLAB: all twelve producer warps have served the item's nine taps
@@ -249,19 +281,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const long long total_tiles = args.pixel_tiles * args.num_n;
+    // work items: (pixel tile or pair of pixel tiles, n-block); this CTA's pixel tile = item * CG + rank
+    const long long total_tiles = args.pixel_tiles * args.num_n;   // host: pixel_tiles already counts pairs when CG = 2
     const int kblocks = args.kblocks;
     const int plane = args.H * args.W;
+    const uint32_t cta_rank = CG == 1 ? 0u : ptx::cluster_ctarank();
+    const long long tile_first = CG == 1 ? static_cast<long long>(blockIdx.x) : static_cast<long long>(ptx::cluster_id_x());
+    const long long tile_step = CG == 1 ? static_cast<long long>(gridDim.x) : static_cast<long long>(ptx::cluster_count_x());
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            ptx::mbar_init(&full_bar[s], 5);
+            // leader: own filter TMA (1) + own 4 producer warps, + with CG = 2 the peer's 4 producer warps and its relay
+            ptx::mbar_init(&full_bar[s], CG == 1 ? 5 : 10);
+            ptx::mbar_init(&bfull_bar[s], 1);
             ptx::mbar_init(&empty_bar[0][s], 1);
             ptx::mbar_init(&empty_bar[1][s], 1);
         }
         for (int s = 0; s < ACC; ++s) {
             ptx::mbar_init(&tmem_full_bar[s], static_cast<uint32_t>(args.issuers));  // every issuer commits its own MMAs
-            ptx::mbar_init(&tmem_empty_bar[s], 4);
+            ptx::mbar_init(&tmem_empty_bar[s], 4 * CG);  // CG = 2: the peer's epilogue warps arrive remotely on the leader's
         }
         for (int s = 0; s < 3; ++s) {
             ptx::mbar_init(&slab_full[s], 1);
@@ -289,17 +327,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // SLAB: the input-slab ring sits right behind the filter ring (both multiples of 1 KB), then the bias copy
     constexpr int SST = slab_stages(BN);
     uint8_t* slab0 = smem + STAGES * kStage;
-    float* bias_s = reinterpret_cast<float*>(smem + STAGES * kStage + (SLAB ? SST * kSlabStageBytes : 0) +
-                                             (args.use_table == 1 ? kblocks * 32 * 8 : 0));
+    // epilogue staging tiles of the TMA-store path: kOutBufs x 4 KB per epilogue warp, right behind the slab ring
+    constexpr int kOutBufs = (SLAB && BN == 128 && CG == 1) ? 1 : 2;
+    uint8_t* stage_out = smem + STAGES * kStage + (SLAB ? SST * kSlabStageBytes : 0);
+    float* bias_s = reinterpret_cast<float*>(stage_out + 4 * kOutBufs * 4096 + (args.use_table == 1 ? kblocks * 32 * 8 : 0));
 
     for (int i = threadIdx.x; i < args.oc_pad; i += kThreadsIg)
         bias_s[i] = (args.bias != nullptr && i < args.OC) ? __ldg(args.bias + i) : 0.f;
     if (warp == kWarpMma) {
-        ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
-        ptx::tmem_relinquish();
+        if (CG == 1) {
+            ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
+            ptx::tmem_relinquish();
+        } else {
+            ptx::tmem_alloc_cg2(&tmem_base_smem, kTmemCols);
+            ptx::tmem_relinquish_cg2();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (CG == 2) ptx::cluster_sync_all();  // the peer's barriers exist before anyone arrives on them remotely
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     const uint32_t tmem_a0 = tmem_base + kAccCols;
@@ -310,7 +356,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         int stage = 0;
         uint32_t phase = 0;
         uint32_t gb = 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (long long tile = tile_first; tile < total_tiles; tile += tile_step) {
             const uint32_t pt = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
             const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - pt * static_cast<uint32_t>(args.num_n));
             for (int kb = 0; kb < kblocks; ++kb, ++gb) {
@@ -318,9 +364,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 IG_TRACE(8, gb);
                 if (leader) {
                     uint8_t* st = smem + stage * kStage;
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], PLANES * kBTile);
-                    ptx::tma_load_3d(st, &tmW, &full_bar[stage], kb * 32, n_blk * BN, 0);
-                    if (PLANES == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, &full_bar[stage], kb * 32, n_blk * BN, 0);
+                    // CG = 2: rows [rank * BN/2, (rank+1) * BN/2) of the N tile; the peer CTA's copy completes on ITS bfull
+                    // barrier, which its relay warp forwards to the leader CTA's full barrier
+                    uint64_t* bar = (CG == 2 && cta_rank != 0) ? &bfull_bar[stage] : &full_bar[stage];
+                    const int row0 = n_blk * BN + static_cast<int>(cta_rank) * kBRows;
+                    ptx::mbar_arrive_expect_tx(bar, PLANES * kBTile);
+                    ptx::tma_load_3d(st, &tmW, bar, kb * 32, row0, 0);
+                    if (PLANES == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, bar, kb * 32, row0, 0);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -339,18 +389,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // tensor pipe does not keep MMAs of two issuing warps in issue order — results differed run to run in the last
         // bit (fp32 summation order), and an overtaken accumulate=0 MMA would have been a silent wrong result.  With
         // disjoint accumulators there is no cross-thread ordering left: each thread's commit covers exactly its own MMAs.
-        if (ptx::elect_one()) {
-            constexpr uint32_t idesc = make_idesc_tf32(BN);
+        if (CG == 2 && cta_rank != 0) {
+            // peer CTA of a pair: no MMAs are issued here.  Its first "issuer" warp relays "my half of the filter tile has
+            // landed" (a local TMA completion) to the leader's full barrier, k-block by k-block, in order.
+            if (warp == kWarpMma && ptx::elect_one()) {
+                uint32_t g = 0;
+                for (long long tile = tile_first; tile < total_tiles; tile += tile_step)
+                    for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                        ptx::mbar_wait(&bfull_bar[g & (STAGES - 1)], (g / STAGES) & 1u);
+                        ptx::mbar_arrive_remote(&full_bar[g & (STAGES - 1)], 0u);
+                    }
+            }
+        } else if (ptx::elect_one()) {
+            constexpr uint32_t idesc = make_idesc_tf32(BN, 128 * CG);
             const uint64_t dB0 = make_smem_desc_sw128(ptx::smem_u32(smem));
             const uint32_t me = static_cast<uint32_t>(warp - kWarpMma);
             const uint32_t nissue = static_cast<uint32_t>(args.issuers);
             uint32_t g = me;
-            long long tile = blockIdx.x;
+            long long tile = tile_first;
             int kb = static_cast<int>(me);
             uint32_t it = 0;
             if (me >= nissue) tile = total_tiles;  // single-issuer launch: the second issuer idles
             for (;;) {
-                while (kb >= kblocks && tile < total_tiles) { kb -= kblocks; tile += gridDim.x; ++it; }
+                while (kb >= kblocks && tile < total_tiles) { kb -= kblocks; tile += tile_step; ++it; }
                 if (tile >= total_tiles) break;
                 const int stage = static_cast<int>(g & (STAGES - 1));
                 const uint32_t phase = (g / STAGES) & 1u;
@@ -360,23 +421,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
                 const uint32_t ta = tmem_a0 + stage * kAStageCols;
                 const bool first_visit = kb < static_cast<int>(nissue);  // this thread's first k-block of the tile
-                if (first_visit) ptx::mbar_wait(&tmem_empty_bar[as], ((it / static_cast<uint32_t>(args.acc_slots)) & 1u) ^ 1u);
-                ptx::mbar_wait(&full_bar[stage], phase);
+                if (CG == 1) {
+                    if (first_visit) ptx::mbar_wait(&tmem_empty_bar[as], ((it / static_cast<uint32_t>(args.acc_slots)) & 1u) ^ 1u);
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                } else {  // arrivals from the peer CTA: acquire at cluster scope
+                    if (first_visit) ptx::mbar_wait_cluster(&tmem_empty_bar[as], ((it / static_cast<uint32_t>(args.acc_slots)) & 1u) ^ 1u);
+                    ptx::mbar_wait_cluster(&full_bar[stage], phase);
+                }
                 IG_TRACE_T(5, g);
                 ptx::tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {  // 8 k-values (TMEM columns / 32 smem bytes) per MMA
                     const uint32_t first = (first_visit && k == 0) ? 0u : 1u;
-                    if (PLANES == 2) {
-                        umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);   // A_lo * B_hi
-                        umma_tf32_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_hi * B_lo
-                        umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);           // A_hi * B_hi
+                    if (CG == 1) {
+                        if (PLANES == 2) {
+                            umma_tf32_ts(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);   // A_lo * B_hi
+                            umma_tf32_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_hi * B_lo
+                            umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);           // A_hi * B_hi
+                        } else {
+                            umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, first);
+                        }
                     } else {
-                        umma_tf32_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, first);
+                        if (PLANES == 2) {
+                            umma_tf32_ts_cg2(tmem_d, ta + 32 + k * 8, dB + 2 * k, idesc, first);
+                            umma_tf32_ts_cg2(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);
+                            umma_tf32_ts_cg2(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);
+                        } else {
+                            umma_tf32_ts_cg2(tmem_d, ta + k * 8, dB + 2 * k, idesc, first);
+                        }
                     }
                 }
-                ptx::umma_commit(ring_release_bar<STAGES>(empty_bar, g));
-                if (kb + static_cast<int>(nissue) >= kblocks) ptx::umma_commit(&tmem_full_bar[as]);  // my last k-block here
+                if (CG == 1) {
+                    ptx::umma_commit(ring_release_bar<STAGES>(empty_bar, g));
+                    if (kb + static_cast<int>(nissue) >= kblocks) ptx::umma_commit(&tmem_full_bar[as]);  // my last k-block here
+                } else {  // both CTAs of the pair: slot release for their producers / TMA, accumulator-ready for their epilogues
+                    ptx::umma_commit_cg2(ring_release_bar<STAGES>(empty_bar, g), 3);
+                    if (kb + static_cast<int>(nissue) >= kblocks) ptx::umma_commit_cg2(&tmem_full_bar[as], 3);
+                }
                 IG_TRACE_T(7, g);
                 g += nissue;
                 kb += static_cast<int>(nissue);
@@ -389,8 +470,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const bool leader = ptx::elect_one();
             const int cblocks = args.IC >> 5;
             uint32_t j = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+            for (long long tile = tile_first; tile < total_tiles; tile += tile_step) {
+                const uint32_t pitem = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+            const uint32_t ptile = pitem * CG + cta_rank;
                 const BoxCoord bx = decode_patch(ptile, args);
                 for (int cb = 0; cb < cblocks; ++cb, ++j) {
                     const uint32_t st = j % SST;
@@ -421,7 +503,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // this lane's pixel inside the patch (2 x 16 sub-patch per warp) and its first slab element for tap row 0
         const int lane_off = (patch_row(q, lane) * kSlabCols + patch_col(q, lane) + group - args.pad_left + kSlabShift) * 4;
         uint32_t j = 0;  // running item index of this CTA; its k-blocks are 9j .. 9j+8
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (long long tile = tile_first; tile < total_tiles; tile += tile_step) {
             for (int cb = 0; cb < cblocks; ++cb, ++j) {
                 const uint32_t st = j % SST;
                 ptx::mbar_wait(&slab_full[st], (j / SST) & 1u);
@@ -449,7 +531,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     tmem_st_wait();
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&full_bar[my_stage]);
+                    if (lane == 0) {
+                        if (CG == 2 && cta_rank != 0) ptx::mbar_arrive_remote(&full_bar[my_stage], 0u);
+                        else ptx::mbar_arrive(&full_bar[my_stage]);
+                    }
                 }
                 // (the __syncwarp above orders every lane's slab reads before the release)
                 if (lane == 0) ptx::mbar_arrive(&slab_empty[st]);
@@ -469,7 +554,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int kb_mod = kblocks % kGroups;
 
         // cursor over this group's k-blocks
-        long long tile = blockIdx.x;
+        long long tile = tile_first;
         uint32_t g0 = 0;   // running index of the current tile's k-block 0
         int g0_mod = 0;    // g0 % kGroups
         int kb = 0;
@@ -485,13 +570,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 kb = group - g0_mod;
                 if (kb < 0) kb += kGroups;
                 if (kb < kblocks) { have = true; break; }
-                tile += gridDim.x;
+                tile += tile_step;
                 g0 += static_cast<uint32_t>(kblocks);
                 g0_mod += kb_mod;
                 if (g0_mod >= kGroups) g0_mod -= kGroups;
             }
             if (!have) return;
-            const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+            const uint32_t pitem = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+            const uint32_t ptile = pitem * CG + cta_rank;
             const BoxCoord bx = decode_box(ptile * 4 + q, args);
             const int ox = bx.ox0 + lane;
             const bool pix_ok = bx.valid && ox < args.OW;
@@ -514,7 +600,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             kb += kGroups;
             tap += kGroups;
             if (kb >= kblocks) {
-                tile += gridDim.x;
+                tile += tile_step;
                 g0 += static_cast<uint32_t>(kblocks);
                 g0_mod += kb_mod;
                 if (g0_mod >= kGroups) g0_mod -= kGroups;
@@ -604,7 +690,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             if (q == 0) IG_TRACE(4, g);
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&full_bar[my_stage]);
+            if (lane == 0) {
+                if (CG == 2 && cta_rank != 0) ptx::mbar_arrive_remote(&full_bar[my_stage], 0u);
+                else ptx::mbar_arrive(&full_bar[my_stage]);
+            }
         }
     } else {
         // ===================== epilogue (warps 0..3) =====================
@@ -615,9 +704,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int SH = pool ? (args.OH + 1) >> 1 : args.OH, SW = pool ? (args.OW + 1) >> 1 : args.OW;
         const uint32_t oplane_bytes = static_cast<uint32_t>(SH * SW) * 4u;  // host: OH*OW < 2^30
         uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
-            const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - ptile * static_cast<uint32_t>(args.num_n));
+        uint32_t ebuf = 0;  // staging tile toggle of the TMA-store path
+        const bool tma_out = args.tma_out != 0 && !pool;
+        for (long long tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
+            const uint32_t pitem = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+            const uint32_t ptile = pitem * CG + cta_rank;
+            const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - pitem * static_cast<uint32_t>(args.num_n));
             const uint32_t as = it & static_cast<uint32_t>(args.acc_slots - 1);
             const uint32_t aphase = (it / static_cast<uint32_t>(args.acc_slots)) & 1u;
             // this warp's 32 TMEM lanes: box q (32 pixels of one row), or in SLAB mode a 2 x 16 sub-patch of the tile
@@ -701,6 +793,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                             *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(j)) =
                                 fmaxf(v + bias_s[oc0 + j], floor_v);
                     }
+                } else if (tma_out) {
+                    // Per-thread STG moved ~15 B/clk per SM here (igemm trace of VGG conv1_1: 2,250 cycles of epilogue per
+                    // 128 x 64 tile, the whole kernel paced by it).  Instead the 32-channel x 32-pixel chunk is laid out
+                    // [channel][pixel] in shared memory (lane = pixel: conflict-free STS) and leaves as ONE TMA store —
+                    // whole 128-byte rows per channel plane, image borders and the channel tail clipped by the tensor map.
+                    uint8_t* stg = stage_out + (q * kOutBufs + (kOutBufs == 2 ? (ebuf & 1u) : 0u)) * 4096;
+                    if (lane == 0) ptx::tma_store_wait_read<kOutBufs - 1>();  // the store that last read this tile is done with it
+                    __syncwarp();
+                    float* sp = reinterpret_cast<float*>(stg) + lane;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 bv = b4[j4];  // bias_s is padded with zeros up to oc_pad
+                        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = j4 * 4 + e;
+                            sp[j * 32] = fmaxf(__uint_as_float(r[j]) + res[j] + bb[e], floor_v);
+                        }
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && bx.valid) {
+                        if (SLAB) tma_store_4d(&tmOut, stg, bx.ox0 + 16 * (q & 1), bx.oy + 2 * (q >> 1), oc0, bx.n);
+                        else tma_store_4d(&tmOut, stg, bx.ox0, bx.oy, oc0, bx.n);
+                        ptx::tma_store_commit();
+                    }
+                    ++ebuf;
                 } else if (ok) {
                     if (oc0 + 32 <= args.OC) {
 #pragma unroll
@@ -726,15 +845,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             ptx::tc_fence_before();
             __syncwarp();
             if (q == 0) IG_TRACE(10, it);
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+            if (lane == 0) {
+                if (CG == 2 && cta_rank != 0) ptx::mbar_arrive_remote(&tmem_empty_bar[as], 0u);
+                else ptx::mbar_arrive(&tmem_empty_bar[as]);
+            }
         }
+        if (tma_out && lane == 0) ptx::tma_store_wait_all<0>();  // global writes complete before the CTA retires
     }
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CG == 2) ptx::cluster_sync_all();  // the pair's MMAs, remote arrivals and tensor-memory reads are all done
     if (warp == kWarpMma) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+        else ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
     }
 }
 
@@ -771,7 +896,7 @@ igemm_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, f
     }
 }
 
-template <int BN, int PLANES, bool SLAB>
+template <int BN, int PLANES, bool SLAB, int CG>
 int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return FCUDA_ERR_CUDA;
@@ -782,7 +907,7 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     for (int pl = 0; pl < PLANES; ++pl) {
         cuuint64_t dims[3] = {(cuuint64_t)Kf, (cuuint64_t)p.OC, 1};
         cuuint64_t strides[2] = {(cuuint64_t)Kf * 4, (cuuint64_t)Kf * p.OC * 4};
-        cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
+        cuuint32_t box[3] = {32, (cuuint32_t)(BN / CG), 1};  // CG = 2: each CTA of the pair fetches half of the N tile
         cuuint32_t estr[3] = {1, 1, 1};
         const float* base = pl == 0 ? p.w_hi : p.w_lo;
         CUresult r = enc(pl == 0 ? &tmW : &tmWlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims,
@@ -817,7 +942,7 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     a.num_n = ceil_div(p.OC, BN);
     a.m_num_n = magic(a.num_n);
     a.oc_pad = a.num_n * BN;
-    a.pixel_tiles = (a.total_boxes + 3) / 4;
+    a.pixel_tiles = ((a.total_boxes + 3) / 4 + CG - 1) / CG;  // work items: pixel tiles, or pairs of them (CG = 2)
     // 32-bit box / tile arithmetic and 32-bit plane strides inside the kernel
     if (a.total_boxes + 4 >= (1ll << 31) || a.pixel_tiles * a.num_n >= (1ll << 31) ||
         static_cast<long long>(p.H) * p.W >= (1ll << 30) || static_cast<long long>(p.OH) * p.OW >= (1ll << 30))
@@ -826,14 +951,14 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     // two issuers (one accumulator each) where one thread cannot keep the pipe fed: N <= 64 and at least four k-blocks
     // per tile (short-K tiles are epilogue-bound and would only pay the second accumulator read); BN = 128 has 768 cycles of MMA work per k-block against ~350 of issue work, and only 256 accumulator
     // columns.  FCUDA_IGEMM_ISSUERS=1 forces one issuer (diagnostic).
-    static const int issuers_env = [] { const char* e = getenv("FCUDA_IGEMM_ISSUERS"); return (e && e[0] == '1') ? 1 : kIssuers; }();
+    const int issuers_env = tune_get(TUNE_IGEMM_ISSUERS);
     a.issuers = (BN <= 64 && a.kblocks >= 4) ? issuers_env : 1;
     a.acc_stride = a.issuers == 2 ? 2 * BN : BN;
     a.acc_slots = (BN <= 64 ? 256 : 2 * BN) / a.acc_stride;
     if (a.acc_slots > 4) a.acc_slots = 4;
     const long long total = a.pixel_tiles * a.num_n;
-    const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
-    constexpr int kStage = PLANES * BN * 32 * 4;
+    int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+    constexpr int kStage = PLANES * (BN / CG) * 32 * 4;
     if (a.use_table && a.kblocks == 1) {
         a.use_table = 2;
         for (int k = 0; k < 32; ++k) {
@@ -846,14 +971,15 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
         }
     }
     const int table_bytes = a.use_table == 1 ? a.kblocks * 32 * 8 : 0;
-    const int smem = kStagesIg * kStage + (SLAB ? slab_stages(BN) * kSlabStageBytes : 0) + table_bytes + a.oc_pad * 4 + 1024;
+    constexpr int kOutStage = 4 * ((SLAB && BN == 128 && CG == 1) ? 1 : 2) * 4096;
+    const int smem = kStagesIg * kStage + (SLAB ? slab_stages(BN) * kSlabStageBytes : 0) + kOutStage + table_bytes + a.oc_pad * 4 + 1024;
     if (smem > 227 * 1024 - 2048) return -1;
-    auto kern = conv_igemm_kernel<BN, PLANES, SLAB>;
+    auto kern = conv_igemm_kernel<BN, PLANES, SLAB, CG>;
     static SmemAttrCache attr_cache;
     if (int rc = ensure_dynamic_smem(kern, smem, attr_cache)) return rc;
     // algorithmic work of the layer: direct-convolution FLOPs; input + filters read once, output written once
     const double macs = static_cast<double>(p.N) * p.OC * p.OH * p.OW * p.IC * taps;
-    const double mma = 2.0 * static_cast<double>(a.pixel_tiles) * 128 * (a.num_n * BN) * (a.kblocks * 32) * (PLANES == 2 ? 3 : 1);
+    const double mma = 2.0 * static_cast<double>(a.pixel_tiles) * 128 * CG * (a.num_n * BN) * (a.kblocks * 32) * (PLANES == 2 ? 3 : 1);
     const int prof = prof_begin(stream, PROF_IGEMM, 2.0 * macs, mma,
                                 4.0 * (static_cast<double>(p.N) * p.IC * p.H * p.W + static_cast<double>(p.OC) * K +
                                        static_cast<double>(p.N) * p.OC * p.OH * p.OW * (p.residual ? 2 : 1)));
@@ -871,7 +997,47 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
             return FCUDA_ERR_CUDA;
         }
     }
-    kern<<<grid, kThreadsIg, smem, stream>>>(tmW, tmWlo, tmIn, a);
+    // 4-D map over the NCHW output (or a channel slice of it): {OW, OH, OC, N}; box = one epilogue chunk: 32 channels x
+    // (32 pixels of a row | a 2 x 16 sub-patch in SLAB mode).  Needs 16-byte rows; pooled launches keep direct stores.
+    CUtensorMap tmOut = tmW;
+    a.tma_out = 0;
+    if (tune_get(TUNE_IGEMM_TMA_OUT) && !a.pool && p.OW % 4 == 0 && (reinterpret_cast<uintptr_t>(p.output) & 15) == 0) {
+        cuuint64_t dims[4] = {(cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.OC, (cuuint64_t)p.N};
+        cuuint64_t strides[3] = {(cuuint64_t)p.OW * 4, (cuuint64_t)p.OW * p.OH * 4, (cuuint64_t)a.out_img_c * p.OW * p.OH * 4};
+        cuuint32_t box[4] = {SLAB ? 16u : 32u, SLAB ? 2u : 1u, 32, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.output, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            fprintf(stderr, "fcuda: igemm output tensor map failed (%d)\n", (int)r);
+            return FCUDA_ERR_CUDA;
+        }
+        a.tma_out = 1;
+    }
+    if (CG == 1) {
+        kern<<<grid, kThreadsIg, smem, stream>>>(tmW, tmWlo, tmIn, tmOut, a);
+    } else {  // CTA pairs: as many clusters as can be co-resident, never more than there are work items
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(kThreadsIg); cfg.dynamicSmemBytes = smem; cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+        static int max_clusters[kMaxDevices] = {};
+        const int dev = current_device();
+        if (max_clusters[dev] == 0) {
+            cfg.gridDim = dim3(static_cast<unsigned>(sm_count() / CG * CG));
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+                cudaGetLastError();
+                n = sm_count() / CG;
+            }
+            max_clusters[dev] = n;
+        }
+        const long long nclusters = total < max_clusters[dev] ? total : max_clusters[dev];
+        grid = static_cast<int>(nclusters * CG);
+        cfg.gridDim = dim3(static_cast<unsigned>(grid));
+        FCUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmW, tmWlo, tmIn, tmOut, a));
+    }
     prof_end(prof, stream);
     FCUDA_CHECK_LAUNCH();
     count_launch();
@@ -901,7 +1067,7 @@ int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, in
 
 // 3x3, stride 1, dense taps, whole 32-channel blocks: the slab producer (FCUDA_IGEMM_SLAB=0 keeps the generic gather)
 static bool slab_eligible(const IgemmProblem& p) {
-    static const bool off = [] { const char* e = getenv("FCUDA_IGEMM_SLAB"); return e && e[0] == '0'; }();
+    const bool off = tune_get(TUNE_IGEMM_SLAB) == 0;
     // + what the TMA needs: 16-byte rows and base (W % 4 == 0 keeps every channel / image / group slice aligned)
     return !off && p.KH == 3 && p.KW == 3 && p.stride_h == 1 && p.stride_w == 1 && p.dil_h <= 1 && p.dil_w <= 1 &&
            p.IC % 32 == 0 && p.pad_top <= 2 && p.pad_left <= 2 && p.W % 4 == 0 &&
@@ -910,18 +1076,31 @@ static bool slab_eligible(const IgemmProblem& p) {
 
 bool conv_igemm_can_pool(const IgemmProblem& p) { return slab_eligible(p) && p.residual == nullptr; }
 
+// CTA pairs (cta_group::2) when the layer has enough pixel tiles to keep every pair busy (FCUDA_IGEMM_CG=1|2 overrides)
+static int pick_cg(const IgemmProblem& p) {
+    // Measured on B200 (profiles/r02j_lean_cta_group2.log): pairs are bit-identical to single CTAs but slower (VGG-16 7.35 vs
+    // 5.82 ms, ResNet-50 10.2 vs 8.0) — with a 4-deep operand ring the two extra cross-CTA hops per k-block (multicast slot
+    // release, remote full arrival) are not hidden.  Default stays 1; FCUDA_IGEMM_CG=2 / fcuda_set_tuning select pairs.
+    if (p.planes != 2 || p.OC <= 32) return 1;
+    return tune_get(TUNE_IGEMM_CG);
+}
+
+template <bool SLAB>
+static int dispatch_igemm(const IgemmProblem& p, cudaStream_t stream) {
+    const bool x3 = p.planes == 2;
+    if (x3 && pick_cg(p) == 2) {
+        if (p.OC <= 64) return launch_igemm<64, 2, SLAB, 2>(p, stream);
+        return launch_igemm<128, 2, SLAB, 2>(p, stream);
+    }
+    if (p.OC <= 32) return x3 ? launch_igemm<32, 2, SLAB, 1>(p, stream) : launch_igemm<32, 1, SLAB, 1>(p, stream);
+    if (p.OC <= 64) return x3 ? launch_igemm<64, 2, SLAB, 1>(p, stream) : launch_igemm<64, 1, SLAB, 1>(p, stream);
+    return x3 ? launch_igemm<128, 2, SLAB, 1>(p, stream) : launch_igemm<128, 1, SLAB, 1>(p, stream);
+}
+
 int conv_igemm_forward(const IgemmProblem& p, cudaStream_t stream) {
     if (!conv_igemm_supported(p.IC, p.KH, p.KW)) return -1;
     if (p.pool && !conv_igemm_can_pool(p)) return -200;
-    const bool x3 = p.planes == 2;
-    if (slab_eligible(p)) {
-        if (p.OC <= 32) return x3 ? launch_igemm<32, 2, true>(p, stream) : launch_igemm<32, 1, true>(p, stream);
-        if (p.OC <= 64) return x3 ? launch_igemm<64, 2, true>(p, stream) : launch_igemm<64, 1, true>(p, stream);
-        return x3 ? launch_igemm<128, 2, true>(p, stream) : launch_igemm<128, 1, true>(p, stream);
-    }
-    if (p.OC <= 32) return x3 ? launch_igemm<32, 2, false>(p, stream) : launch_igemm<32, 1, false>(p, stream);
-    if (p.OC <= 64) return x3 ? launch_igemm<64, 2, false>(p, stream) : launch_igemm<64, 1, false>(p, stream);
-    return x3 ? launch_igemm<128, 2, false>(p, stream) : launch_igemm<128, 1, false>(p, stream);
+    return slab_eligible(p) ? dispatch_igemm<true>(p, stream) : dispatch_igemm<false>(p, stream);
 }
 
 }  // namespace fcuda

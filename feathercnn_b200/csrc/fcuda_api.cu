@@ -655,6 +655,14 @@ int fcuda_from_pixels(float* output, const unsigned char* pixels, int type, int 
     return from_pixels(output, pixels, type, w, h, target_w, target_h, mean_vals, norm_vals, batch, as_stream(stream));
 }
 
+int fcuda_set_tuning(const char* name, int value) { return tune_set(name, value); }
+int fcuda_get_tuning(const char* name) {
+    static const char* names[TUNE_COUNT] = {"igemm_issuers", "igemm_slab", "igemm_cta_group", "dw_vec", "gemm_cluster", "gemm_tma_store", "igemm_tma_out"};
+    for (int k = 0; k < TUNE_COUNT; ++k)
+        if (name && !strcmp(name, names[k])) return tune_get(k);
+    return -200;
+}
+
 void fcuda_profile_tensor_gemm(int enable) { gemm_profile_enable(enable != 0); }
 int fcuda_profile_collect_kind(int kind, double* total_ms, double* algo_flops, double* mma_flops, double* algo_bytes,
                                long long* launches) {

@@ -47,6 +47,52 @@ pooling_kernel(const float* __restrict__ in, float* __restrict__ out, PoolGeom g
     }
 }
 
+// 3x3 / stride 2 / no padding (ResNet-50's pool1, ceil mode: the last window may be clipped): a warp marches down 16 output
+// rows of a 32-column strip; per input row a lane loads one float2 (columns 2*ox, 2*ox+1) and takes column 2*ox+2 from the
+// next lane by shuffle; every input row is loaded once per strip (the generic kernel above issues 9 scalar loads and ~100
+// instructions of 64-bit index math per output: 0.31 of HBM bandwidth on ResNet-50, profiles/r02k_resnet50_launches_summary.txt).
+__global__ void __launch_bounds__(128)
+pool3x3s2_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int OH, int OW, int type, long long items,
+                 int xstrips, int ystrips) {
+    const long long item = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+    if (item >= items) return;
+    const int lane = threadIdx.x & 31;
+    const int xs = static_cast<int>(item % xstrips);
+    const long long t = item / xstrips;
+    const int ys = static_cast<int>(t % ystrips);
+    const long long plane = t / ystrips;
+    const float* ip = in + plane * H * W;
+    float* op = out + plane * OH * OW;
+    const int ox = xs * 32 + lane, ix = 2 * ox;
+    const int oy0 = ys * 16, oy1 = min(oy0 + 16, OH);
+    const bool c0 = ix < W, c1 = ix + 1 < W, c2 = ix + 2 < W;          // which of the window's three columns exist
+    const float pad = type == 0 ? -FLT_MAX : 0.f;
+    const int ncol = (c0 ? 1 : 0) + (c1 ? 1 : 0) + (c2 ? 1 : 0);
+    // horizontal reduction of one input row over this lane's window (max or sum of the in-bounds columns)
+    auto hrow = [&](int iy, float& r) {
+        float a = pad, b = pad;
+        if (iy < H && c0) {
+            if (c1) { const float2 v = __ldg(reinterpret_cast<const float2*>(ip + static_cast<long long>(iy) * W + ix)); a = v.x; b = v.y; }
+            else a = __ldg(ip + static_cast<long long>(iy) * W + ix);
+        }
+        float c = __shfl_down_sync(0xffffffffu, a, 1);                  // next lane's first column = my third
+        if (lane == 31) c = (iy < H && c2) ? __ldg(ip + static_cast<long long>(iy) * W + ix + 2) : pad;
+        if (!c2) c = pad;
+        r = type == 0 ? fmaxf(fmaxf(a, b), c) : a + b + c;
+    };
+    float carry;  // horizontal result of the row shared by two consecutive windows (row 2*oy)
+    hrow(2 * oy0, carry);
+    for (int oy = oy0; oy < oy1; ++oy) {
+        float r1, r2;
+        hrow(2 * oy + 1, r1);
+        hrow(2 * oy + 2, r2);
+        const int nrow = min(2 * oy + 3, H) - 2 * oy;
+        float v = type == 0 ? fmaxf(fmaxf(carry, r1), r2) : (carry + r1 + r2) / static_cast<float>(nrow * ncol);
+        if (ox < OW) op[static_cast<long long>(oy) * OW + ox] = v;
+        carry = r2;
+    }
+}
+
 // 2x2 / stride 2 / no padding on planes whose width is a multiple of 4 (every VGG pool): a thread reads one float4 of
 // two consecutive rows and writes two outputs, 32-bit index math only; the generic kernel above spends ~100
 // instructions per output on 64-bit div/mod and runs at 40% of HBM.
@@ -256,6 +302,12 @@ int pooling_forward(const float* in, float* out, const PoolGeom& g, int channels
         const unsigned total = static_cast<unsigned>(planes * g.OH * pairs);
         const unsigned long long m = pairs > 1 ? ~0ull / static_cast<unsigned long long>(pairs) + 1ull : 0ull;
         pool2x2_kernel<<<(total + 255) / 256, 256, 0, s>>>(in, out, g.W, g.OW, pairs, m, g.type, total);
+    } else if (g.KH == 3 && g.KW == 3 && g.stride_h == 2 && g.stride_w == 2 && g.pad_top + g.pad_bottom == 0 &&
+               g.pad_left + g.pad_right == 0 && g.W % 2 == 0 && g.OW >= 24 && 2 * (g.OW - 1) < g.W && 2 * (g.OH - 1) < g.H) {
+        const int xstrips = (g.OW + 31) / 32, ystrips = (g.OH + 15) / 16;
+        const long long items = static_cast<long long>(planes) * xstrips * ystrips;
+        pool3x3s2_kernel<<<static_cast<unsigned>((items + 3) / 4), 128, 0, s>>>(in, out, g.H, g.W, g.OH, g.OW, g.type, items,
+                                                                              xstrips, ystrips);
     } else {
         const size_t total = planes * g.OH * g.OW;
         pooling_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, g, total);

@@ -219,6 +219,25 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// ---- cta_group::2 (a CTA pair shares one MMA: M = 256, each CTA holds 128 rows of A / D in its own TMEM and N/2 rows of B in
+// its own shared memory).  alloc / relinquish / dealloc are executed by one warp of EACH CTA of the pair.
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrives on the mbarrier at this CTA-relative offset in every CTA of `cta_mask` once the issuing thread's MMAs have retired
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -273,13 +292,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=BN.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int bn) {
+// Instruction descriptor: D=f32, A=B=tf32, both K-major, M = 128 (256 with cta_group::2), N=BN.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int bn, int m = 128) {
     return (1u << 4)                               // c_format = F32
            | (2u << 7)                             // a_format = TF32
            | (2u << 10)                            // b_format = TF32
            | (static_cast<uint32_t>(bn >> 3) << 17)  // N / 8
-           | (static_cast<uint32_t>(128 >> 4) << 24);  // M / 16
+           | (static_cast<uint32_t>(m >> 4) << 24);  // M / 16
 }
 
 }  // namespace fcuda

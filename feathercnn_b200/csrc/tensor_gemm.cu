@@ -24,6 +24,8 @@
 #include "tcgen05.cuh"
 
 #include <atomic>
+#include <string.h>
+#include <stdlib.h>
 #include <mutex>
 #include <vector>
 
@@ -656,6 +658,44 @@ void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 void reset_launch_count() { g_launches.store(0, std::memory_order_relaxed); }
 
+// ---- kernel-variant switches ---------------------------------------------------------------------------------------
+namespace {
+struct TuneEntry { const char* name; const char* env; int def, lo, hi; int value; bool init; };
+TuneEntry g_tune[TUNE_COUNT] = {
+    {"igemm_issuers", "FCUDA_IGEMM_ISSUERS", 2, 1, 2, 0, false},     // MMA issuer threads of the implicit GEMM (BN <= 64)
+    {"igemm_slab", "FCUDA_IGEMM_SLAB", 1, 0, 1, 0, false},           // TMA-fed slab producer for 3x3 / stride-1 layers
+    {"igemm_cta_group", "FCUDA_IGEMM_CG", 1, 1, 2, 0, false},        // 2 = CTA pairs (cta_group::2, M = 256): correct, measured slower
+    {"dw_vec", "FCUDA_DW_VEC", 1, 0, 1, 0, false},                   // vectorised depthwise kernel on wide planes
+    {"gemm_cluster", "FCUDA_GEMM_CLUSTER", 1, 1, 4, 0, false},       // TMA-multicast of B across a cluster: measured slower
+    {"gemm_tma_store", "FCUDA_GEMM_TMA_STORE", 1, 0, 1, 0, false},   // row-major epilogue through smem + TMA stores
+    {"igemm_tma_out", "FCUDA_IGEMM_TMA_OUT", 1, 0, 1, 0, false},     // implicit-GEMM epilogue through smem + TMA stores
+};
+}  // namespace
+int tune_get(int key) {
+    if (key < 0 || key >= TUNE_COUNT) return 0;
+    TuneEntry& e = g_tune[key];
+    if (!e.init) {
+        e.value = e.def;
+        if (const char* v = getenv(e.env)) {
+            const int x = atoi(v);
+            if (x >= e.lo && x <= e.hi) e.value = x;
+        }
+        e.init = true;
+    }
+    return e.value;
+}
+int tune_set(const char* name, int value) {
+    if (!name) return -200;
+    for (int k = 0; k < TUNE_COUNT; ++k)
+        if (!strcmp(name, g_tune[k].name)) {
+            if (value < g_tune[k].lo || value > g_tune[k].hi || (k == TUNE_GEMM_CLUSTER && value == 3)) return -200;
+            g_tune[k].value = value;
+            g_tune[k].init = true;
+            return 0;
+        }
+    return -200;
+}
+
 // ---- per-launch profiling ------------------------------------------------------------------------
 // Off by default.  When enabled every instrumented launch is bracketed by two CUDA events on its own stream and tagged
 // with its kernel class and ALGORITHMIC work (the FLOPs / bytes the operation needs, not what the kernel happens to
@@ -851,15 +891,7 @@ static int ts_issuers() {  // FCUDA_TS_ISSUERS=1|2 (experiment switch)
     return v;
 }
 
-static int gemm_cluster_env() {  // FCUDA_GEMM_CLUSTER=1|2|4 (experiment switch; unset = policy in pick_cluster)
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("FCUDA_GEMM_CLUSTER");
-        v = e ? atoi(e) : 0;
-        if (v != 1 && v != 2 && v != 4) v = 0;
-    }
-    return v;
-}
+static int gemm_cluster_env() { return tune_get(TUNE_GEMM_CLUSTER); }  // 1 | 2 | 4
 
 template <int BN, int ISSUERS, int CL>
 static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
@@ -874,7 +906,7 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
     fill_kernel_args(p, BN, &a);
     if (CL > 1) a.num_m = ceil_div(a.num_m, CL);  // work items = groups of CL consecutive M tiles
     // row-major D leaves through shared memory + TMA (see the epilogue); needs 16-byte rows
-    static const bool tma_store_off = [] { const char* e = getenv("FCUDA_GEMM_TMA_STORE"); return e && e[0] == '0'; }();
+    const bool tma_store_off = tune_get(TUNE_GEMM_TMA_STORE) == 0;
     CUtensorMap tmD = tmA;
     a.tma_store = 0;
     if (p.epilogue == EPI_ROWMAJOR && !tma_store_off && p.ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0) {

@@ -188,6 +188,19 @@ int fcuda_conv_forward_ext(const FcudaConvParam* param, int algo, float* output,
                            const float* packed_kernel, float* scratch, const float* bias, const float* residual,
                            int relu_after_add, int dilation_h, int dilation_w, int batch, void* stream);
 
+/* Kernel-variant switches for A/B measurements and tests.  Defaults are the measured-best configuration; the environment
+ * variable FCUDA_<NAME> sets the initial value.  Names (value range, default):
+ *   igemm_issuers (1-2, 2)    MMA issuer threads of the implicit GEMM at BN <= 64 (each with its own accumulator)
+ *   igemm_slab (0-1, 1)       TMA-fed input-slab producer for 3x3 / stride-1 layers (0: generic gather)
+ *   igemm_cta_group (1-2, 1)  2: CTA pairs with tcgen05 cta_group::2 (M = 256, half of the filter tile per SM)
+ *   dw_vec (0-1, 1)           vectorised depthwise kernel on wide planes
+ *   gemm_cluster (1|2|4, 1)   TMA multicast of the B operand across a thread-block cluster in the TensorGEMM
+ *   gemm_tma_store (0-1, 1)   row-major TensorGEMM epilogue through shared memory + TMA stores
+ *   igemm_tma_out (0-1, 1)    implicit-GEMM epilogue through shared memory + TMA stores (0: per-thread stores)
+ * Every variant computes the same result (tests/test_gpu_variants.py).  Returns 0 / the value, -200 for an unknown name or value. */
+int fcuda_set_tuning(const char* name, int value);
+int fcuda_get_tuning(const char* name);
+
 /* Profiling aid for bench.py's roofline leg: while enabled, every TensorGEMM launch is bracketed by CUDA events
  * on its own stream.  fcuda_profile_collect synchronises and reports, since the last enable: summed device time
  * (ms), the algorithmic FLOPs those launches stand for (direct-conv count, booster.h:145-148; 2*in*out*batch for

@@ -35,6 +35,7 @@ CASES = [
     ("dw_14_bias_relu", 40, 40, 14, 14, 3, 1, 1, 40, True, True),        # plane kernel (MobileNet 14x14 stage)
     ("dw_14_s2", 40, 40, 14, 14, 3, 2, 1, 40, True, False),              # plane kernel, stride 2 -> 7x7
     ("dw_9_nopad", 12, 12, 9, 11, 3, 1, 0, 12, False, True),             # plane kernel without padding
+    ("dw_cols_ragged", 20, 20, 11, 13, 3, 1, 1, 20, True, False),       # column-per-lane kernel, H != W, planes not a multiple of 2
     ("dw_5x5", 8, 8, 12, 12, 5, 1, 2, 8, False, False),
     ("dw_global", 32, 32, 7, 7, 7, 1, 0, 32, False, False),              # kernel == input: globalDwConv
 ]

@@ -55,6 +55,9 @@ POOL_CASES = [
     (0, 2, 2, (0, 0, 0, 0), False, (3, 10, 4)),       # fast path, one output pair per row
     (0, 2, 2, (0, 0, 0, 0), False, (3, 10, 14)),      # W % 4 != 0 -> generic kernel
     (0, 2, 2, (0, 0, 0, 0), False, (4, 9, 12)),       # odd H (ceil mode) -> generic kernel
+    (1, 3, 2, (0, 0, 0, 0), False, (8, 57, 64)),      # 3x3 s2 strip kernel, average, several strips
+    (0, 3, 2, (0, 0, 0, 0), False, (4, 50, 50)),      # 3x3 s2 strip kernel, last window clipped in x and y (ceil mode)
+    (1, 3, 2, (0, 0, 0, 0), False, (4, 50, 50)),      # same, average divides by the in-bounds count (pooling_layer.h:84)
 ]
 
 

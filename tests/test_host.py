@@ -463,3 +463,18 @@ def test_modelgen_flop_counts_match_survey():
     # parse-only instantiation of the big models is slow (random weights); count FLOPs from a shape-only walk
     m = modelgen.resnet50.__wrapped__() if hasattr(modelgen.resnet50, "__wrapped__") else None
     assert m is None or abs(m.flops / 1e9 - 7.716) < 0.05
+
+
+def test_tuning_switches_are_validated_on_the_host():
+    """fcuda_set_tuning / fcuda_get_tuning (kernel-variant switches): names and ranges are checked, defaults are the
+    measured-best configuration."""
+    from feathercnn_b200._lib import fcuda
+    lib = fcuda()
+    assert lib.fcuda_set_tuning(b"nope", 1) == -200
+    assert lib.fcuda_set_tuning(b"igemm_cta_group", 3) == -200
+    assert lib.fcuda_set_tuning(b"gemm_cluster", 3) == -200
+    assert lib.fcuda_get_tuning(b"nope") == -200
+    assert lib.fcuda_get_tuning(b"igemm_cta_group") == 1 and lib.fcuda_get_tuning(b"gemm_cluster") == 1
+    assert lib.fcuda_get_tuning(b"igemm_slab") == 1 and lib.fcuda_get_tuning(b"gemm_tma_store") == 1
+    assert lib.fcuda_set_tuning(b"igemm_cta_group", 2) == 0 and lib.fcuda_get_tuning(b"igemm_cta_group") == 2
+    assert lib.fcuda_set_tuning(b"igemm_cta_group", 1) == 0
