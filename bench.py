@@ -203,7 +203,7 @@ def run_reference(args, rank: int, world: int) -> None:
 
 
 KERNEL_CLASS_NAMES = ["tensor_gemm_ts_kernel (tcgen05 kind::tf32, Winograd/im2col/FC GEMM)",
-                      "conv_igemm_kernel (tcgen05 kind::tf32 implicit-GEMM conv)", "wino_input_kernel",
+                      "conv_igemm_kernel (tcgen05 kind::f16 BF16x3 / kind::tf32 implicit-GEMM conv)", "wino_input_kernel",
                       "wino_output_kernel", "pooling_kernel", "depthwise kernels", "element-wise kernels"]
 
 
@@ -486,7 +486,9 @@ def main() -> None:
     ap.add_argument("--model", default=None, choices=["vgg16", "resnet50", "mobilenet_v1", "single_conv"],
                     help="one workload only (default: VGG-16 headline + ResNet-50 and MobileNet-v1 under `workloads`)")
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: BASELINE.json config)")
-    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"])
+    ap.add_argument("--precision", default="fp32split", choices=["fp32split", "tf32x3", "tf32"],
+                    help="fp32split (default): fp32-equivalent split operands, BF16x3 in the implicit GEMM + 3xTF32 in the "
+                         "TensorGEMM; tf32x3: 3xTF32 everywhere; tf32: single TF32 MMA (not fp32-equivalent)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -520,7 +522,8 @@ def main() -> None:
         if world > 1:
             dist.barrier(device_ids=[local_rank])
 
-    booster.set_precision(booster.PRECISION_TF32 if args.precision == "tf32" else booster.PRECISION_TF32X3)
+    booster.set_precision({"tf32": booster.PRECISION_TF32, "tf32x3": booster.PRECISION_TF32X3,
+                           "fp32split": booster.PRECISION_FP32_SPLIT}[args.precision])
     if args.l2_chunk_mb is not None:
         booster.set_l2_chunk_bytes(int(args.l2_chunk_mb * 1024 * 1024))
 
@@ -550,10 +553,14 @@ def main() -> None:
     line = {
         "metric": "images/sec", "value": head["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if args.precision == "tf32x3" else "tf32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
         "config": cfg,
         "details": {"parallelism": f"batch-shard x{world} (weights broadcast once over NCCL, no collective in Forward)",
-                    "tensor_core_mode": "3xTF32 split (fp32-equivalent)" if args.precision == "tf32x3" else "TF32",
+                    "tensor_core_mode": {"fp32split": "fp32-equivalent split operands, fp32 accumulation: BF16x3 (p1*q1 + p1*q2 + "
+                                                      "p2*q1, kind::f16) in the implicit GEMM, 3xTF32 in the Winograd / FC TensorGEMM; "
+                                                      "accuracy = parity_max_rel",
+                                         "tf32x3": "3xTF32 split (fp32-equivalent) in every contraction",
+                                         "tf32": "TF32"}[args.precision],
                     "algorithms": "tuned SelectAlgo (reference rule, then Winograd -> implicit GEMM when IC,OC <= 128 and OW >= 28, "
                                   "im2col -> implicit GEMM): Winograd F(6,3)+TensorGEMM / SGECONV implicit GEMM / depthwise",
                     "fusion": not args.no_fusion, "cuda_graph": not args.no_graph,

@@ -15,7 +15,7 @@ from ._lib import FcudaConvParam, fcuda
 
 NAIVE, IM2COL, SGECONV, DEPTHWISE, WINOGRADF63, WINOGRADF63FUSED, WINOGRADF23 = range(7)
 ALGO_NAMES = ["NAIVE", "IM2COL", "SGECONV", "DEPTHWISE", "WINOGRADF63", "WINOGRADF63FUSED", "WINOGRADF23"]
-PRECISION_TF32X3, PRECISION_TF32 = 0, 1
+PRECISION_TF32X3, PRECISION_TF32, PRECISION_FP32_SPLIT = 0, 1, 2
 
 
 class FcudaError(RuntimeError):

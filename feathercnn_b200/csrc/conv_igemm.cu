@@ -40,6 +40,7 @@
 
 #include <stdlib.h>
 #include "tcgen05.cuh"
+#include <cuda_bf16.h>
 
 namespace fcuda {
 
@@ -215,6 +216,19 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem], bf16 operands (two per TMEM column / 64-byte swizzled smem rows), K = 16
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // cta_group::2: one thread of the pair's leader CTA issues for both SMs (M = 256: lanes 0-127 of each CTA's tensor memory)
 __device__ __forceinline__ void umma_tf32_ts_cg2(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                                  uint32_t accumulate) {
@@ -250,16 +264,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                   const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
                   const IgemmArgs args) {
     constexpr int STAGES = kStagesIg;
+    // PLANES: 1 = TF32, 2 = 3xTF32, 3 = BF16x3 (operands split into two bf16 planes p1 = RN(x), p2 = RN(x - p1); three
+    // kind::f16 MMAs p2*q1 + p1*q2 + p1*q1 per k-step of SIXTEEN — twice the tensor throughput of 3xTF32 and half the
+    // shared-memory / tensor-memory operand bytes, dropped terms <= 3 * 2^-16 of a product)
+    constexpr bool BF = PLANES == 3;
+    constexpr int NPL = BF ? 2 : PLANES;                    // operand planes in memory
+    static_assert(!(BF && CG == 2), "pairs are a TF32 variant");
     constexpr int kBRows = BN / CG;                         // filter rows this CTA holds (CG = 2: half of the N tile)
-    constexpr int kBTile = kBRows * 32 * 4;
-    constexpr int kStage = PLANES * kBTile;                 // smem per stage: [B_hi][B_lo]
+    constexpr int kBTile = kBRows * 32 * (BF ? 2 : 4);      // 32 k-values per row: 128 B of fp32 / 64 B of bf16
+    constexpr int kStage = NPL * kBTile;                    // smem per stage: [B_hi][B_lo]
     static_assert(CG == 1 || kBRows % 8 == 0, "whole swizzle atoms per CTA");
     // accumulator ring: as deep as tensor memory allows next to the A ring (4 x 64 columns in 3xTF32 mode).  Tiles with few
     // k-blocks (IC = 3, pointwise layers) are a latency chain gather -> MMA -> epilogue; with 2 slots conv1_1 of VGG
     // spent 3.8k cycles per tile for ~1k cycles of work in any one role.
     constexpr int ACC = 4;                                  // barrier array size; args.acc_slots (<= 4) slots are in use
     constexpr uint32_t kAccCols = BN <= 64 ? 256 : 2 * BN;  // carved at run time into args.acc_slots slots of args.acc_stride
-    constexpr uint32_t kAStageCols = 32 * PLANES;           // [A_hi (32 cols)][A_lo (32 cols)]
+    constexpr uint32_t kAPlaneCols = BF ? 16 : 32;          // 32 k-values: fp32 columns, or bf16 pairs
+    constexpr uint32_t kAStageCols = kAPlaneCols * NPL;     // [A_hi][A_lo]
     constexpr uint32_t kNeedCols = kAccCols + STAGES * kAStageCols;
     constexpr uint32_t kTmemCols = kNeedCols <= 32 ? 32 : kNeedCols <= 64 ? 64 : kNeedCols <= 128 ? 128 : kNeedCols <= 256 ? 256 : 512;
     static_assert(kNeedCols <= 512, "TMEM budget");
@@ -309,7 +330,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
     if (warp == kWarpTma && lane == 0) {
         ptx::prefetch_tensormap(&tmW);
-        if (PLANES == 2) ptx::prefetch_tensormap(&tmWlo);
+        if (NPL == 2) ptx::prefetch_tensormap(&tmWlo);
         if (SLAB) ptx::prefetch_tensormap(&tmIn);
     }
     if (args.use_table == 1) {
@@ -368,9 +389,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     // barrier, which its relay warp forwards to the leader CTA's full barrier
                     uint64_t* bar = (CG == 2 && cta_rank != 0) ? &bfull_bar[stage] : &full_bar[stage];
                     const int row0 = n_blk * BN + static_cast<int>(cta_rank) * kBRows;
-                    ptx::mbar_arrive_expect_tx(bar, PLANES * kBTile);
+                    ptx::mbar_arrive_expect_tx(bar, NPL * kBTile);
                     ptx::tma_load_3d(st, &tmW, bar, kb * 32, row0, 0);
-                    if (PLANES == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, bar, kb * 32, row0, 0);
+                    if (NPL == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, bar, kb * 32, row0, 0);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -401,8 +422,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     }
             }
         } else if (ptx::elect_one()) {
-            constexpr uint32_t idesc = make_idesc_tf32(BN, 128 * CG);
-            const uint64_t dB0 = make_smem_desc_sw128(ptx::smem_u32(smem));
+            constexpr uint32_t idesc = BF ? make_idesc_bf16(BN, 128) : make_idesc_tf32(BN, 128 * CG);
+            const uint64_t dB0 = BF ? make_smem_desc_sw64(ptx::smem_u32(smem)) : make_smem_desc_sw128(ptx::smem_u32(smem));
             const uint32_t me = static_cast<uint32_t>(warp - kWarpMma);
             const uint32_t nissue = static_cast<uint32_t>(args.issuers);
             uint32_t g = me;
@@ -430,8 +451,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 }
                 IG_TRACE_T(5, g);
                 ptx::tc_fence_after();
+                if (BF) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // 8 k-values (TMEM columns / 32 smem bytes) per MMA
+                    for (int k = 0; k < 2; ++k) {  // 16 k-values (8 TMEM columns of bf16 pairs / 32 smem bytes) per MMA
+                        const uint32_t first = (first_visit && k == 0) ? 0u : 1u;
+                        umma_bf16_ts(tmem_d, ta + 16 + k * 8, dB + 2 * k, idesc, first);   // A_p2 * B_p1
+                        umma_bf16_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_p1 * B_p2
+                        umma_bf16_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);           // A_p1 * B_p1
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < (BF ? 0 : 4); ++k) {  // 8 k-values (TMEM columns / 32 smem bytes) per MMA
                     const uint32_t first = (first_visit && k == 0) ? 0u : 1u;
                     if (CG == 1) {
                         if (PLANES == 2) {
@@ -516,8 +546,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     const char* src = tb + u * (kSlabCols * 4);
                     wait_ring_slot_free<STAGES>(empty_bar, g);
                     ptx::tc_fence_after();
+                    if (BF) {
 #pragma unroll
-                    for (int part = 0; part < 4; ++part) {
+                        for (int part = 0; part < 2; ++part) {  // 16 channels -> 8 columns of bf16 pairs per plane
+                            uint32_t hi[8], lo[8];
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) {
+                                const float x0 = *reinterpret_cast<const float*>(src + (part * 16 + 2 * r) * kSlabChBytes);
+                                const float x1 = *reinterpret_cast<const float*>(src + (part * 16 + 2 * r + 1) * kSlabChBytes);
+                                split_bf16x2(x0, x1, hi[r], lo[r]);
+                            }
+                            tmem_st_32x8(ta + part * 8, hi);
+                            tmem_st_32x8(ta + 16 + part * 8, lo);
+                        }
+                    }
+#pragma unroll
+                    for (int part = 0; part < (BF ? 0 : 4); ++part) {
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
@@ -661,8 +705,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             wait_ring_slot_free<STAGES>(empty_bar, g);
             if (q == 0) IG_TRACE(1, g);
             ptx::tc_fence_after();
+            if (BF) {
 #pragma unroll
-            for (int part = 0; part < 4; ++part) {  // 8 k-values at a time keeps the live set inside 96 registers
+                for (int part = 0; part < 2; ++part) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) split_bf16x2(x[part * 16 + 2 * r], x[part * 16 + 2 * r + 1], hi[r], lo[r]);
+                    tmem_st_32x8(ta + part * 8, hi);
+                    tmem_st_32x8(ta + 16 + part * 8, lo);
+                }
+            }
+#pragma unroll
+            for (int part = 0; part < (BF ? 0 : 4); ++part) {  // 8 k-values at a time keeps the live set inside 96 registers
                 uint32_t hi[8];
                 if (PLANES == 2) {
                     uint32_t lo[8];
@@ -896,6 +950,34 @@ igemm_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, f
     }
 }
 
+// BF16x3: the same Wp[oc][Kf] order, two bf16 planes q1 = RN(w), q2 = RN(w - q1); Kf = K rounded up to 8 (16-byte rows)
+__global__ void __launch_bounds__(256)
+igemm_pack_weights_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ q1, __nv_bfloat16* __restrict__ q2,
+                               int OC, int IC, int taps, int Kf) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t total = static_cast<size_t>(OC) * Kf;
+    if (idx >= total) return;
+    const int k = static_cast<int>(idx % Kf);
+    const int oc = static_cast<int>(idx / Kf);
+    float v = 0.f;
+    if (k < IC * taps) {
+        int tap, ic;
+        if (IC % 32 == 0) {
+            const int kb = k >> 5;
+            const int cb = kb / taps;
+            tap = kb - cb * taps;
+            ic = cb * 32 + (k & 31);
+        } else {
+            tap = k / IC;
+            ic = k - tap * IC;
+        }
+        v = w[(static_cast<size_t>(oc) * IC + ic) * taps + tap];
+    }
+    const __nv_bfloat16 a = __float2bfloat16_rn(v);
+    q1[idx] = a;
+    q2[idx] = __float2bfloat16_rn(v - __bfloat162float(a));
+}
+
 template <int BN, int PLANES, bool SLAB, int CG>
 int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     EncodeTiledFn enc = encode_fn();
@@ -903,22 +985,26 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     CUtensorMap tmW, tmWlo;
     const int taps = p.KH * p.KW;
     const int K = taps * p.IC;
-    const int Kf = (K + 3) & ~3;
-    for (int pl = 0; pl < PLANES; ++pl) {
+    constexpr bool BF = PLANES == 3;
+    constexpr int NPL = BF ? 2 : PLANES;
+    constexpr int kElt = BF ? 2 : 4;
+    const int Kf = BF ? (K + 7) & ~7 : (K + 3) & ~3;
+    for (int pl = 0; pl < NPL; ++pl) {
         cuuint64_t dims[3] = {(cuuint64_t)Kf, (cuuint64_t)p.OC, 1};
-        cuuint64_t strides[2] = {(cuuint64_t)Kf * 4, (cuuint64_t)Kf * p.OC * 4};
+        cuuint64_t strides[2] = {(cuuint64_t)Kf * kElt, (cuuint64_t)Kf * p.OC * kElt};
         cuuint32_t box[3] = {32, (cuuint32_t)(BN / CG), 1};  // CG = 2: each CTA of the pair fetches half of the N tile
         cuuint32_t estr[3] = {1, 1, 1};
         const float* base = pl == 0 ? p.w_hi : p.w_lo;
-        CUresult r = enc(pl == 0 ? &tmW : &tmWlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims,
-                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+        CUresult r = enc(pl == 0 ? &tmW : &tmWlo, BF ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                         const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         BF ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             fprintf(stderr, "fcuda: igemm weight tensor map failed (%d)\n", (int)r);
             return FCUDA_ERR_CUDA;
         }
     }
-    if (PLANES == 1) tmWlo = tmW;
+    if (NPL == 1) tmWlo = tmW;
     IgemmArgs a;
     a.in = p.input; a.out = p.output; a.bias = p.bias; a.residual = p.residual;
     a.N = p.N; a.IC = p.IC; a.H = p.H; a.W = p.W; a.OC = p.OC; a.OH = p.OH; a.OW = p.OW;
@@ -958,7 +1044,7 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     if (a.acc_slots > 4) a.acc_slots = 4;
     const long long total = a.pixel_tiles * a.num_n;
     int grid = static_cast<int>(total < sm_count() ? total : sm_count());
-    constexpr int kStage = PLANES * (BN / CG) * 32 * 4;
+    constexpr int kStage = NPL * (BN / CG) * 32 * kElt;
     if (a.use_table && a.kblocks == 1) {
         a.use_table = 2;
         for (int k = 0; k < 32; ++k) {
@@ -979,7 +1065,7 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     if (int rc = ensure_dynamic_smem(kern, smem, attr_cache)) return rc;
     // algorithmic work of the layer: direct-convolution FLOPs; input + filters read once, output written once
     const double macs = static_cast<double>(p.N) * p.OC * p.OH * p.OW * p.IC * taps;
-    const double mma = 2.0 * static_cast<double>(a.pixel_tiles) * 128 * CG * (a.num_n * BN) * (a.kblocks * 32) * (PLANES == 2 ? 3 : 1);
+    const double mma = 2.0 * static_cast<double>(a.pixel_tiles) * 128 * CG * (a.num_n * BN) * (a.kblocks * 32) * (PLANES >= 2 ? 3 : 1);
     const int prof = prof_begin(stream, PROF_IGEMM, 2.0 * macs, mma,
                                 4.0 * (static_cast<double>(p.N) * p.IC * p.H * p.W + static_cast<double>(p.OC) * K +
                                        static_cast<double>(p.N) * p.OC * p.OH * p.OW * (p.residual ? 2 : 1)));
@@ -1056,7 +1142,17 @@ size_t conv_igemm_packed_floats(int OC, int IC, int taps, int planes) {
     return static_cast<size_t>(planes) * OC * ((taps * IC + 3) & ~3);
 }
 
-int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, int IC, int taps, cudaStream_t s) {
+int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, int IC, int taps, cudaStream_t s, int bf16x3) {
+    if (bf16x3) {
+        if (!w_lo) return -100;
+        const int Kf8 = (taps * IC + 7) & ~7;
+        const size_t total8 = static_cast<size_t>(OC) * Kf8;
+        igemm_pack_weights_bf16_kernel<<<static_cast<unsigned>(ceil_div_sz(total8, 256)), 256, 0, s>>>(
+            w, reinterpret_cast<__nv_bfloat16*>(w_hi), reinterpret_cast<__nv_bfloat16*>(w_lo), OC, IC, taps, Kf8);
+        FCUDA_CHECK_LAUNCH();
+        count_launch();
+        return 0;
+    }
     const int Kf = (taps * IC + 3) & ~3;
     const size_t total = static_cast<size_t>(OC) * Kf;
     igemm_pack_weights_kernel<<<static_cast<unsigned>(ceil_div_sz(total, 256)), 256, 0, s>>>(w, w_hi, w_lo, OC, IC, taps, Kf);
@@ -1087,6 +1183,11 @@ static int pick_cg(const IgemmProblem& p) {
 
 template <bool SLAB>
 static int dispatch_igemm(const IgemmProblem& p, cudaStream_t stream) {
+    if (p.planes == 3) {  // BF16x3
+        if (p.OC <= 32) return launch_igemm<32, 3, SLAB, 1>(p, stream);
+        if (p.OC <= 64) return launch_igemm<64, 3, SLAB, 1>(p, stream);
+        return launch_igemm<128, 3, SLAB, 1>(p, stream);
+    }
     const bool x3 = p.planes == 2;
     if (x3 && pick_cg(p) == 2) {
         if (p.OC <= 64) return launch_igemm<64, 2, SLAB, 2>(p, stream);

@@ -12,7 +12,7 @@ struct IgemmProblem {
     float* output;        // (N, OC, OH, OW)
     int N, IC, H, W, OC, OH, OW;
     int KH, KW, pad_top, pad_left, stride_h, stride_w;
-    int planes;           // 1 = TF32, 2 = 3xTF32
+    int planes;           // 1 = TF32, 2 = 3xTF32, 3 = BF16x3 (w_hi / w_lo then hold the two bf16 planes)
     int relu;
     const float* residual;  // optional (N, OC, OH, OW) tensor added before the activation (fused Eltwise SUM), or null
     // Extensions beyond the reference (it rejects both: conv_layer.h:43-47, avx/booster.cpp:304-308); 0 = default.
@@ -27,7 +27,10 @@ bool conv_igemm_supported(int IC, int KH, int KW);
 // Floats of the packed filter buffer ([OC][Kf] per plane, Kf = KH*KW*IC rounded up to 4).
 size_t conv_igemm_packed_floats(int OC, int IC, int taps, int planes);
 // raw (OC, IC, KH, KW) -> [OC][Kf] hi (+ lo) planes.
-int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, int IC, int taps, cudaStream_t s);
+// bf16x3 != 0: w_hi / w_lo receive the two bf16 planes q1 = RN(w), q2 = RN(w - q1), rows of Kf8 = K rounded up to 8
+// (they fit the float planes sized above).
+int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, int IC, int taps, cudaStream_t s,
+                            int bf16x3 = 0);
 // True when the launch can apply a fused 2x2 / stride-2 max pooling (the 3x3 stride-1 slab kernel without a residual).
 bool conv_igemm_can_pool(const IgemmProblem& p);
 int conv_igemm_forward(const IgemmProblem& p, cudaStream_t stream);

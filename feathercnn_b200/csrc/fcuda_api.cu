@@ -24,7 +24,8 @@ namespace {
 int env_precision() {
     const char* e = getenv("FCUDA_PRECISION");
     if (e && (!strcmp(e, "tf32") || !strcmp(e, "TF32") || !strcmp(e, "1"))) return FCUDA_PRECISION_TF32;
-    return FCUDA_PRECISION_TF32X3;
+    if (e && (!strcmp(e, "tf32x3") || !strcmp(e, "3xtf32") || !strcmp(e, "0"))) return FCUDA_PRECISION_TF32X3;
+    return FCUDA_PRECISION_FP32_SPLIT;
 }
 size_t env_chunk() {
     const char* e = getenv("FCUDA_L2_CHUNK_MB");
@@ -39,7 +40,9 @@ size_t env_chunk() {
 int g_precision = env_precision();
 size_t g_l2_chunk = env_chunk();
 
-inline int planes() { return g_precision == FCUDA_PRECISION_TF32X3 ? 2 : 1; }
+inline int planes() { return g_precision == FCUDA_PRECISION_TF32 ? 1 : 2; }
+// operand format of the implicit GEMM (IgemmProblem::planes): 3 = BF16x3 in the default fp32-split mode
+inline int igemm_planes() { return g_precision == FCUDA_PRECISION_FP32_SPLIT ? 3 : planes(); }
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
 struct ConvPlan {
@@ -185,7 +188,8 @@ int stage_to_device(const float* src, size_t n, const float** dev, float** tmp, 
 extern "C" {
 
 int fcuda_set_precision(int precision) {
-    if (precision != FCUDA_PRECISION_TF32X3 && precision != FCUDA_PRECISION_TF32) return -200;
+    if (precision != FCUDA_PRECISION_TF32X3 && precision != FCUDA_PRECISION_TF32 && precision != FCUDA_PRECISION_FP32_SPLIT)
+        return -200;
     g_precision = precision;
     return 0;
 }
@@ -299,7 +303,7 @@ int fcuda_conv_init(const FcudaConvParam* p, int algo, float* packed, const floa
             for (int g = 0; g < G && rc == 0; ++g) {  // per group: [hi plane][lo plane] of Wp[OCg][Kf]
                 float* dst = packed + static_cast<size_t>(g) * pl.np * plane;
                 rc = conv_igemm_pack_weights(d_raw + static_cast<size_t>(g) * OCg * ICg * taps, dst,
-                                             pl.np == 2 ? dst + plane : nullptr, OCg, ICg, taps, s);
+                                             pl.np == 2 ? dst + plane : nullptr, OCg, ICg, taps, s, igemm_planes() == 3);
             }
             break;
         }
@@ -437,7 +441,7 @@ static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, c
                 } else {
                     g.H = p->input_h; g.W = p->input_w; g.OH = p->output_h; g.OW = p->output_w;
                 }
-                g.planes = pl.np; g.relu = residual ? relu_after_add : relu;
+                g.planes = igemm_planes(); g.relu = residual ? relu_after_add : relu;
                 g.pool = pool;
                 if (pool) {  // pooled output planes
                     g.output = output + static_cast<size_t>(gi) * OCg * (static_cast<size_t>((p->output_h + 1) / 2) * ((p->output_w + 1) / 2));

@@ -292,6 +292,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// Same for a K-major tile whose rows are 64 bytes (32 bf16) wide, laid out by TMA with CU_TENSOR_MAP_SWIZZLE_64B:
+// 8-row groups of 512 B (SBO = 512), layout type SWIZZLE_64B (= 4 in the sm_100 descriptor).
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;
+    return d;
+}
+
 // Instruction descriptor: D=f32, A=B=tf32, both K-major, M = 128 (256 with cta_group::2), N=BN.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int bn, int m = 128) {
     return (1u << 4)                               // c_format = F32
@@ -299,6 +311,26 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int bn, int m = 128) {
            | (2u << 10)                            // b_format = TF32
            | (static_cast<uint32_t>(bn >> 3) << 17)  // N / 8
            | (static_cast<uint32_t>(m >> 4) << 24);  // M / 16
+}
+
+// kind::f16 with bf16 operands (format 1), D = f32: K = 16 per instruction.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int bn, int m = 128) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// Two fp32 values -> one register of two bf16 (round to nearest even): `lo` in bits 0-15, `hi` in bits 16-31.
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// bf16x3 operand split of a PAIR of fp32 values (k even in the low half): p1 = RN_bf16(x), p2 = RN_bf16(x - p1).
+// x - p1 is exact in fp32; |x - p1 - p2| <= 2^-16 |x|.  6 instructions per pair.
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& p1, uint32_t& p2) {
+    p1 = pack_bf16x2_rn(x0, x1);
+    const float r0 = x0 - __uint_as_float(p1 << 16);
+    const float r1 = x1 - __uint_as_float(p1 & 0xFFFF0000u);
+    p2 = pack_bf16x2_rn(r0, r1);
 }
 
 }  // namespace fcuda

@@ -57,10 +57,16 @@ typedef struct FcudaConvParam {
     int activation;          /* FcudaActivation */
 } FcudaConvParam;
 
-/* Arithmetic mode of the tensor-core contraction (global, default FCUDA_PRECISION_TF32X3).
- *   TF32X3: operands split into TF32 hi + fp32 lo planes, 3 MMAs per k-step — fp32-equivalent results.
- *   TF32  : single TF32 MMA — ~2.5e-4 relative error per layer, 3x fewer MMAs. */
-enum FcudaPrecision { FCUDA_PRECISION_TF32X3 = 0, FCUDA_PRECISION_TF32 = 1 };
+/* Arithmetic mode of the tensor-core contraction (global, default FCUDA_PRECISION_FP32_SPLIT).  The tensor cores have no
+ * fp32 MMA; every mode accumulates in fp32.
+ *   FP32_SPLIT: fp32-equivalent results from split operands, the cheapest split per kernel: the implicit GEMM (SGECONV)
+ *               uses BF16x3 — x = p1 + p2 + r with p1 = RN_bf16(x), p2 = RN_bf16(x - p1), three bf16 MMAs
+ *               p2*q1 + p1*q2 + p1*q1, dropped terms <= 3 * 2^-16 of a product (measured ~1e-5 of max|out| per layer) at
+ *               twice the tensor throughput of 3xTF32; the Winograd / im2col / InnerProduct TensorGEMM keeps 3xTF32
+ *               (F(6,3) amplifies operand rounding ~40x).
+ *   TF32X3    : every contraction as TF32 hi + fp32 lo planes, 3 TF32 MMAs per k-step (~2^-21 per product).
+ *   TF32      : single TF32 MMA — ~2.5e-4 relative error per layer, 3x fewer MMAs. */
+enum FcudaPrecision { FCUDA_PRECISION_TF32X3 = 0, FCUDA_PRECISION_TF32 = 1, FCUDA_PRECISION_FP32_SPLIT = 2 };
 int fcuda_set_precision(int precision);
 int fcuda_get_precision(void);
 

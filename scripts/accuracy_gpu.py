@@ -15,7 +15,7 @@ for name in sys.argv[1:] or ["vgg16", "resnet50", "mobilenet_v1"]:
     x = modelgen.synthetic_input(m.shape["data"], 0)
     cpu = O.ReferenceNet(param, binf) if O.reference_available() else O.OracleNet(param, binf)
     cpu.forward(x)
-    for mode, label in ((booster.PRECISION_TF32X3, "3xTF32"), (booster.PRECISION_TF32, "TF32")):
+    for mode, label in ((booster.PRECISION_FP32_SPLIT, "fp32split"), (booster.PRECISION_TF32X3, "3xTF32"), (booster.PRECISION_TF32, "TF32")):
         booster.set_precision(mode)
         net = Net()
         net.LoadParam(param); net.LoadWeights(binf)
@@ -26,6 +26,6 @@ for name in sys.argv[1:] or ["vgg16", "resnet50", "mobilenet_v1"]:
             got = net.Extract(b)[0]
             errs[b] = float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
         worst = max(errs, key=errs.get)
-        print(f"{name:14s} {label:7s} worst blob {worst:28s} {errs[worst]:.3e}   prob {errs.get('prob', float('nan')):.3e}   "
+        print(f"{name:14s} {label:9s} worst blob {worst:28s} {errs[worst]:.3e}   prob {errs.get('prob', float('nan')):.3e}   "
               f"median {np.median(list(errs.values())):.3e}", flush=True)
-    booster.set_precision(booster.PRECISION_TF32X3)
+    booster.set_precision(booster.PRECISION_FP32_SPLIT)

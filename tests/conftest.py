@@ -54,3 +54,14 @@ def cuda():
         pytest.skip("no CUDA device")
     torch.cuda.set_device(0)
     return torch
+
+
+@pytest.fixture(autouse=True)
+def _default_precision():
+    """Every test starts in the engine's default arithmetic mode (FP32_SPLIT); tests that pin a mode set it themselves."""
+    try:
+        from feathercnn_b200 import booster
+        booster.set_precision(booster.PRECISION_FP32_SPLIT)
+    except Exception:  # libraries not built (pure-oracle CPU tests)
+        pass
+    yield

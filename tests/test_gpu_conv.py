@@ -11,6 +11,13 @@ from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
 
+
+# Split modes of the fp32-equivalent contraction (include/fcuda.h): 0 = 3xTF32 everywhere, 2 = the default (BF16x3 in the
+# implicit GEMM, 3xTF32 in the TensorGEMM).  Both are held to the same 2e-4 bar.
+@pytest.fixture(params=[0, 2], ids=["tf32x3", "fp32split"])
+def mode(request):
+    return request.param
+
 # (name, oc, ic, h, w, k, stride, pad, group, bias, relu)
 CASES = [
     ("config1_64x64_56", 64, 64, 56, 56, 3, 1, 1, 1, True, False),       # BASELINE.json configs[0]
@@ -93,10 +100,10 @@ def test_conv_matches_reference_build(cuda, oracle, reference, case):
 
 
 @pytest.mark.parametrize("algo_name", ["NAIVE", "IM2COL", "SGECONV", "WINOGRADF63", "WINOGRADF23"])
-def test_forced_algorithms_agree(cuda, oracle, restatement, algo_name):
+def test_forced_algorithms_agree(cuda, oracle, restatement, algo_name, mode):
     """ForceSelectAlgo (avx/booster.cpp:313-317): every algorithm computes the same convolution."""
     from feathercnn_b200 import booster
-    booster.set_precision(booster.PRECISION_TF32X3)
+    booster.set_precision(mode)
     case = ("forced", 48, 32, 21, 28, 3, 1, 1, 1, True, True)
     p, x, wt, b = _data(oracle, case, 2, seed=3)
     got, used = _gpu_conv(cuda, case, x, wt, b, algo=getattr(booster, algo_name))
@@ -143,10 +150,10 @@ SGECONV_CASES = [
 
 @pytest.mark.parametrize("geom", SGECONV_CASES)
 @pytest.mark.parametrize("batch", [1, 3])
-def test_sgeconv_implicit_gemm(cuda, oracle, restatement, geom, batch):
+def test_sgeconv_implicit_gemm(cuda, oracle, restatement, geom, batch, mode):
     """FCUDA_SGECONV: implicit GEMM from NCHW (patches gathered inside the tcgen05 kernel), vs fp64 direct conv."""
     from feathercnn_b200 import booster
-    booster.set_precision(booster.PRECISION_TF32X3)
+    booster.set_precision(mode)
     oc, ic, h, w, k, stride, pad, bias, relu = geom
     case = ("sgeconv", oc, ic, h, w, k, stride, pad, 1, bias, relu)
     p, x, wt, b = _data(oracle, case, batch, seed=13)
@@ -171,10 +178,10 @@ def test_sgeconv_implicit_gemm(cuda, oracle, restatement, geom, batch):
     ("IM2COL", (16, 8, 10, 10, 3, 2, 1, True)),
 ])
 @pytest.mark.parametrize("relu", [False, True])
-def test_conv_forward_residual(cuda, oracle, restatement, algo_name, geom, relu):
+def test_conv_forward_residual(cuda, oracle, restatement, algo_name, geom, relu, mode):
     """fcuda_conv_forward_residual == ConvLayer::Forward then EltwiseLayer::Forward (eltwise_layer.h:68-82)."""
     from feathercnn_b200 import booster
-    booster.set_precision(booster.PRECISION_TF32X3)
+    booster.set_precision(mode)
     oc, ic, h, w, k, stride, pad, bias = geom
     case = ("residual", oc, ic, h, w, k, stride, pad, 1, bias, False)
     p, x, wt, b = _data(oracle, case, 2, seed=21)
@@ -259,12 +266,12 @@ def test_full_size_linearity_vgg_conv(cuda):
     ("SGECONV", (128, 64, 112, 112, 1)),       # BN = 128 (one issuer), VGG conv2_1 shape
     ("SGECONV", (32, 32, 30, 72, 0)),          # no padding
 ])
-def test_conv_with_fused_max_pool(cuda, algo_name, geom):
+def test_conv_with_fused_max_pool(cuda, algo_name, geom, mode):
     """fcuda_conv_forward_pool == the convolution followed by PoolingLayer (2x2 / s2 / pad 0 / max, ceil mode,
     pooling_layer.h:38-91,129-130): max commutes exactly with the per-channel bias and with ReLU, so the fused result is
     bit-identical to pooling the unfused output."""
     from feathercnn_b200 import booster
-    booster.set_precision(booster.PRECISION_TF32X3)
+    booster.set_precision(mode)
     oc, ic, h, w, pad = geom
     rng = np.random.default_rng(oc * 7 + h)
     x = cuda.from_numpy(rng.uniform(-0.5, 0.5, (3, ic, h, w)).astype(np.float32)).cuda()

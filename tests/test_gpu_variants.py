@@ -59,6 +59,27 @@ def test_implicit_gemm_variants_are_bit_identical(cuda, tuning, geom):
     np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
 
 
+@pytest.mark.parametrize("geom", IGEMM_GEOMS)
+def test_bf16x3_implicit_gemm_variants(cuda, tuning, geom):
+    """The default split mode (BF16x3 operands in the implicit GEMM): data-movement variants stay bit-identical, and the
+    result sits within 5e-5 of the 3xTF32 one (dropped terms <= 3 * 2^-16 per product, random sign)."""
+    from feathercnn_b200 import booster
+    booster.set_precision(booster.PRECISION_TF32X3)
+    tuning(igemm_cta_group=1, igemm_slab=1, igemm_issuers=2)
+    ref = _conv(cuda, booster, geom, booster.SGECONV)
+    booster.set_precision(booster.PRECISION_FP32_SPLIT)
+    base = _conv(cuda, booster, geom, booster.SGECONV)
+    assert np.abs(base - ref).max() / np.abs(ref).max() < 5e-5
+    np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)   # run to run
+    tuning(igemm_slab=0)
+    np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
+    tuning(igemm_slab=1, igemm_tma_out=0)
+    np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
+    tuning(igemm_tma_out=1, igemm_issuers=1)
+    one = _conv(cuda, booster, geom, booster.SGECONV)
+    assert np.abs(one - base).max() / np.abs(base).max() < 1e-5
+
+
 @pytest.mark.parametrize("geom", [(64, 64, 56, 56, 3, 1, 1, 4), (256, 128, 28, 28, 3, 1, 1, 8), (512, 256, 14, 14, 3, 1, 1, 16)])
 def test_tensor_gemm_variants_are_bit_identical(cuda, tuning, geom):
     from feathercnn_b200 import booster
