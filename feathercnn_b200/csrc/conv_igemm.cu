@@ -168,6 +168,18 @@ constexpr int kSlabChBytes = kSlabRows * kSlabCols * 4;       // 1,152 B per cha
 constexpr int kSlabStageBytes = 32 * kSlabChBytes;            // 36,864 B per (tile, channel block)
 __host__ __device__ constexpr int slab_stages(int bn) { return bn <= 64 ? 3 : 2; }
 
+// Pointwise slab (slab kind 2; 1x1 / stride 1 / no padding, each image addressed as one H*W-long row): the A tile of a
+// k-block — 128 pixels x 32 channels — is four {32 pixels, 32 channels} boxes of the NCHW input, one per TMEM lane quadrant
+// (a box never leaves its image; the part past the image end is zero-filled), landed by TMA as [channel][pixel] rows of
+// 128 bytes.  The producers then need no addresses, predicates or load latency: 32 conflict-free LDS.32 (lane = pixel)
+// with immediate offsets, the split, the tensor-memory stores.  Replaces the 32 LDG + IMAD.WIDE per thread and k-block of
+// the generic gather, which paced every short-K pointwise layer of ResNet-50 / MobileNet (0.08 of the tensor peak, 0.26
+// of HBM in round 1).
+constexpr int kPwBoxBytes = 32 * 32 * 4;              // one quadrant's box
+constexpr int kPwStageBytes = 4 * kPwBoxBytes;        // 16 KB per k-block
+__host__ __device__ constexpr int pw_stages(int bn, int planes) { return (planes == 2 && bn > 64) ? 3 : 6; }
+constexpr int kMaxSlabStages = 6;
+
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
@@ -258,12 +270,15 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // conv2_x) — the pair halves the first two terms per SM.  Cross-CTA hand-offs: the peer's producers and a relay warp (which
 // watches the peer's filter TMA) arrive REMOTELY on the leader's full barrier; the leader's tcgen05.commit multicasts the
 // slot-release and accumulator-ready arrivals to both CTAs; the peer's epilogue warps release the accumulator remotely.
-template <int BN, int PLANES, bool SLAB, int CG>
+template <int BN, int PLANES, int SK, int CG>
 __global__ void __launch_bounds__(kThreadsIg, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
                   const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
                   const IgemmArgs args) {
     constexpr int STAGES = kStagesIg;
+    constexpr bool SLAB = SK == 1;                          // 3x3 / stride-1 halo slabs (patch-shaped tiles)
+    constexpr bool PW = SK == 2;                            // pointwise slabs (box-shaped tiles, like the generic gather)
+    static_assert(!(PW && CG == 2), "pairs are not combined with the pointwise slab");
     // PLANES: 1 = TF32, 2 = 3xTF32, 3 = BF16x3 (operands split into two bf16 planes p1 = RN(x), p2 = RN(x - p1); three
     // kind::f16 MMAs p2*q1 + p1*q2 + p1*q1 per k-step of SIXTEEN — twice the tensor throughput of 3xTF32 and half the
     // shared-memory / tensor-memory operand bytes, dropped terms <= 3 * 2^-16 of a product)
@@ -294,8 +309,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     __shared__ uint64_t full_bar[STAGES];
     __shared__ uint64_t bfull_bar[STAGES];     // CG = 2, peer CTA: its half of the filter tile has landed (relayed to the leader)
     __shared__ uint64_t empty_bar[2][STAGES];  // MMAs that read the stage have retired; [round parity][slot], see wait_ring_slot_free
-    __shared__ uint64_t slab_full[3];    // SLAB: TMA landed the slab of an item (tile, channel block)
-    __shared__ uint64_t slab_empty[3];   // SLAB: all twelve producer warps have served the item's nine taps
+    __shared__ uint64_t slab_full[kMaxSlabStages];    // SLAB: TMA landed the slab of an item (tile, channel block); PW: of a k-block
+    __shared__ uint64_t slab_empty[kMaxSlabStages];   // SLAB: all twelve producer warps have served the item's nine taps; PW: the
+                                                      // four warps of the k-block's group have read their boxes
     __shared__ uint64_t tmem_full_bar[ACC];
     __shared__ uint64_t tmem_empty_bar[ACC];
     __shared__ uint32_t tmem_base_smem;
@@ -322,16 +338,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             ptx::mbar_init(&tmem_full_bar[s], static_cast<uint32_t>(args.issuers));  // every issuer commits its own MMAs
             ptx::mbar_init(&tmem_empty_bar[s], 4 * CG);  // CG = 2: the peer's epilogue warps arrive remotely on the leader's
         }
-        for (int s = 0; s < 3; ++s) {
+        for (int s = 0; s < kMaxSlabStages; ++s) {
             ptx::mbar_init(&slab_full[s], 1);
-            ptx::mbar_init(&slab_empty[s], 4 * kGroups);
+            ptx::mbar_init(&slab_empty[s], PW ? 4 : 4 * kGroups);
         }
         ptx::fence_barrier_init();
     }
     if (warp == kWarpTma && lane == 0) {
         ptx::prefetch_tensormap(&tmW);
         if (NPL == 2) ptx::prefetch_tensormap(&tmWlo);
-        if (SLAB) ptx::prefetch_tensormap(&tmIn);
+        if (SLAB || PW) ptx::prefetch_tensormap(&tmIn);
     }
     if (args.use_table == 1) {
         for (int k = threadIdx.x; k < kblocks * 32; k += kThreadsIg) {
@@ -346,11 +362,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
     // bias copy (zeros when the layer has none): the epilogue reads it with broadcast LDS.128
     // SLAB: the input-slab ring sits right behind the filter ring (both multiples of 1 KB), then the bias copy
-    constexpr int SST = slab_stages(BN);
+    constexpr int SST = PW ? pw_stages(BN, PLANES) : slab_stages(BN);
+    constexpr int kRingBytes = SLAB ? SST * kSlabStageBytes : PW ? SST * kPwStageBytes : 0;
     uint8_t* slab0 = smem + STAGES * kStage;
     // epilogue staging tiles of the TMA-store path: kOutBufs x 4 KB per epilogue warp, right behind the slab ring
     constexpr int kOutBufs = (SLAB && BN == 128 && CG == 1) ? 1 : 2;
-    uint8_t* stage_out = smem + STAGES * kStage + (SLAB ? SST * kSlabStageBytes : 0);
+    uint8_t* stage_out = smem + STAGES * kStage + kRingBytes;
     float* bias_s = reinterpret_cast<float*>(stage_out + 4 * kOutBufs * 4096 + (args.use_table == 1 ? kblocks * 32 * 8 : 0));
 
     for (int i = threadIdx.x; i < args.oc_pad; i += kThreadsIg)
@@ -496,6 +513,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     } else if (warp == kWarpSlab) {
         // ===================== SLAB: TMA producer of the input slabs =====================
         // one {48 x 6 x 32} box per item (tile, channel block), SST items ahead of the producers
+        if (PW) {
+            // one 16 KB stage per k-block: four {32 pixels, 32 channels} boxes, SST k-blocks ahead of the producers
+            const bool leader = ptx::elect_one();
+            uint32_t g = 0;
+            for (long long tile = tile_first; tile < total_tiles; tile += tile_step) {
+                const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+                BoxCoord bx[4];
+                int nvalid = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    bx[q] = decode_box(ptile * 4 + q, args);
+                    nvalid += bx[q].valid ? 1 : 0;
+                }
+                for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                    const uint32_t st = g % SST;
+                    ptx::mbar_wait(&slab_empty[st], ((g / SST) & 1u) ^ 1u);
+                    if (leader) {
+                        ptx::mbar_arrive_expect_tx(&slab_full[st], static_cast<uint32_t>(nvalid) * kPwBoxBytes);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (bx[q].valid)
+                                ptx::tma_load_3d(slab0 + st * kPwStageBytes + q * kPwBoxBytes, &tmIn, &slab_full[st], bx[q].ox0, kb * 32,
+                                                 bx[q].n);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
         if (SLAB) {
             const bool leader = ptx::elect_one();
             const int cblocks = args.IC >> 5;
@@ -582,6 +627,59 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 }
                 // (the __syncwarp above orders every lane's slab reads before the release)
                 if (lane == 0) ptx::mbar_arrive(&slab_empty[st]);
+            }
+        }
+    } else if (PW && warp >= 4) {
+        // ===================== A producers, pointwise slab variant =====================
+        // k-block g (running over all tiles of this CTA) belongs to group g % kGroups, ring slot g % STAGES and slab stage
+        // g % SST; this warp reads ITS quadrant's box: element (channel r, pixel lane) at r * 128 + lane * 4.
+        (void)plane;
+        const int group = (warp - 4) >> 2;
+        const int q = warp & 3;
+        const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+        long long my_tiles = 0;
+        if (tile_first < total_tiles) my_tiles = (total_tiles - tile_first + tile_step - 1) / tile_step;
+        const uint32_t total_g = static_cast<uint32_t>(my_tiles) * static_cast<uint32_t>(kblocks);
+        for (uint32_t g = static_cast<uint32_t>(group); g < total_g; g += kGroups) {
+            const uint32_t st = g % SST;
+            const int my_stage = static_cast<int>(g & (STAGES - 1));
+            const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
+            const char* src = reinterpret_cast<const char*>(slab0 + st * kPwStageBytes + q * kPwBoxBytes) + lane * 4;
+            ptx::mbar_wait(&slab_full[st], (g / SST) & 1u);
+            wait_ring_slot_free<STAGES>(empty_bar, g);
+            ptx::tc_fence_after();
+            if (BF) {
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const float x0 = *reinterpret_cast<const float*>(src + (part * 16 + 2 * r) * 128);
+                        const float x1 = *reinterpret_cast<const float*>(src + (part * 16 + 2 * r + 1) * 128);
+                        split_bf16x2(x0, x1, hi[r], lo[r]);
+                    }
+                    tmem_st_32x8(ta + part * 8, hi);
+                    tmem_st_32x8(ta + 16 + part * 8, lo);
+                }
+            }
+#pragma unroll
+            for (int part = 0; part < (BF ? 0 : 4); ++part) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float x = *reinterpret_cast<const float*>(src + (part * 8 + r) * 128);
+                    hi[r] = PLANES == 2 ? (__float_as_uint(x) & 0xFFFFE000u) : __float_as_uint(x);
+                    lo[r] = __float_as_uint(x - __uint_as_float(hi[r]));
+                }
+                tmem_st_32x8(ta + part * 8, hi);
+                if (PLANES == 2) tmem_st_32x8(ta + 32 + part * 8, lo);
+            }
+            tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();  // every lane's slab reads are done (their values went through the stores above)
+            if (lane == 0) {
+                ptx::mbar_arrive(&full_bar[my_stage]);
+                ptx::mbar_arrive(&slab_empty[st]);
             }
         }
     } else if (!SLAB && warp >= 4) {
@@ -978,8 +1076,10 @@ igemm_pack_weights_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __res
     q2[idx] = __float2bfloat16_rn(v - __bfloat162float(a));
 }
 
-template <int BN, int PLANES, bool SLAB, int CG>
+template <int BN, int PLANES, int SK, int CG>
 int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
+    constexpr bool SLAB = SK == 1;
+    constexpr bool PW = SK == 2;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return FCUDA_ERR_CUDA;
     CUtensorMap tmW, tmWlo;
@@ -1058,9 +1158,10 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     }
     const int table_bytes = a.use_table == 1 ? a.kblocks * 32 * 8 : 0;
     constexpr int kOutStage = 4 * ((SLAB && BN == 128 && CG == 1) ? 1 : 2) * 4096;
-    const int smem = kStagesIg * kStage + (SLAB ? slab_stages(BN) * kSlabStageBytes : 0) + kOutStage + table_bytes + a.oc_pad * 4 + 1024;
+    const int smem = kStagesIg * kStage + (SLAB ? slab_stages(BN) * kSlabStageBytes : PW ? pw_stages(BN, PLANES) * kPwStageBytes : 0) +
+                     kOutStage + table_bytes + a.oc_pad * 4 + 1024;
     if (smem > 227 * 1024 - 2048) return -1;
-    auto kern = conv_igemm_kernel<BN, PLANES, SLAB, CG>;
+    auto kern = conv_igemm_kernel<BN, PLANES, SK, CG>;
     static SmemAttrCache attr_cache;
     if (int rc = ensure_dynamic_smem(kern, smem, attr_cache)) return rc;
     // algorithmic work of the layer: direct-convolution FLOPs; input + filters read once, output written once
@@ -1080,6 +1181,19 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             fprintf(stderr, "fcuda: igemm input tensor map failed (%d)\n", (int)r);
+            return FCUDA_ERR_CUDA;
+        }
+    }
+    if (PW) {  // 3-D map over the input with every image as one row: {H*W, IC, N}, box {32 pixels, 32 channels, 1}
+        cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.IC, (cuuint64_t)p.N};
+        cuuint64_t strides[2] = {(cuuint64_t)p.W * 4, (cuuint64_t)a.in_img_c * p.W * 4};
+        cuuint32_t box[3] = {32, 32, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmIn, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.input), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            fprintf(stderr, "fcuda: igemm pointwise input tensor map failed (%d)\n", (int)r);
             return FCUDA_ERR_CUDA;
         }
     }
@@ -1181,7 +1295,15 @@ static int pick_cg(const IgemmProblem& p) {
     return tune_get(TUNE_IGEMM_CG);
 }
 
-template <bool SLAB>
+// 1x1, stride 1, no padding, the image addressed as one row (fcuda_api.cu does that), whole 32-channel blocks and what the
+// TMA needs (16-byte image rows / base): the pointwise slab producer (FCUDA_IGEMM_PW=0 keeps the generic gather)
+static bool pw_eligible(const IgemmProblem& p) {
+    return tune_get(TUNE_IGEMM_PW) != 0 && p.KH == 1 && p.KW == 1 && p.stride_h == 1 && p.stride_w == 1 && p.pad_top == 0 &&
+           p.pad_left == 0 && p.H == 1 && p.OH == 1 && p.IC % 32 == 0 && p.W % 4 == 0 && p.pool == 0 &&
+           (reinterpret_cast<uintptr_t>(p.input) & 15) == 0;
+}
+
+template <int SLAB>
 static int dispatch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     if (p.planes == 3) {  // BF16x3
         if (p.OC <= 32) return launch_igemm<32, 3, SLAB, 1>(p, stream);
@@ -1189,9 +1311,9 @@ static int dispatch_igemm(const IgemmProblem& p, cudaStream_t stream) {
         return launch_igemm<128, 3, SLAB, 1>(p, stream);
     }
     const bool x3 = p.planes == 2;
-    if (x3 && pick_cg(p) == 2) {
-        if (p.OC <= 64) return launch_igemm<64, 2, SLAB, 2>(p, stream);
-        return launch_igemm<128, 2, SLAB, 2>(p, stream);
+    if (x3 && SLAB != 2 && pick_cg(p) == 2) {
+        if (p.OC <= 64) return launch_igemm<64, 2, SLAB == 2 ? 0 : SLAB, 2>(p, stream);
+        return launch_igemm<128, 2, SLAB == 2 ? 0 : SLAB, 2>(p, stream);
     }
     if (p.OC <= 32) return x3 ? launch_igemm<32, 2, SLAB, 1>(p, stream) : launch_igemm<32, 1, SLAB, 1>(p, stream);
     if (p.OC <= 64) return x3 ? launch_igemm<64, 2, SLAB, 1>(p, stream) : launch_igemm<64, 1, SLAB, 1>(p, stream);
@@ -1201,7 +1323,9 @@ static int dispatch_igemm(const IgemmProblem& p, cudaStream_t stream) {
 int conv_igemm_forward(const IgemmProblem& p, cudaStream_t stream) {
     if (!conv_igemm_supported(p.IC, p.KH, p.KW)) return -1;
     if (p.pool && !conv_igemm_can_pool(p)) return -200;
-    return slab_eligible(p) ? dispatch_igemm<true>(p, stream) : dispatch_igemm<false>(p, stream);
+    if (slab_eligible(p)) return dispatch_igemm<1>(p, stream);
+    if (pw_eligible(p)) return dispatch_igemm<2>(p, stream);
+    return dispatch_igemm<0>(p, stream);
 }
 
 }  // namespace fcuda

@@ -661,9 +661,8 @@ int fcuda_from_pixels(float* output, const unsigned char* pixels, int type, int 
 
 int fcuda_set_tuning(const char* name, int value) { return tune_set(name, value); }
 int fcuda_get_tuning(const char* name) {
-    static const char* names[TUNE_COUNT] = {"igemm_issuers", "igemm_slab", "igemm_cta_group", "dw_vec", "gemm_cluster", "gemm_tma_store", "igemm_tma_out"};
     for (int k = 0; k < TUNE_COUNT; ++k)
-        if (name && !strcmp(name, names[k])) return tune_get(k);
+        if (name && !strcmp(name, tune_name(k))) return tune_get(k);
     return -200;
 }
 

@@ -669,8 +669,11 @@ TuneEntry g_tune[TUNE_COUNT] = {
     {"gemm_cluster", "FCUDA_GEMM_CLUSTER", 1, 1, 4, 0, false},       // TMA-multicast of B across a cluster: measured slower
     {"gemm_tma_store", "FCUDA_GEMM_TMA_STORE", 1, 0, 1, 0, false},   // row-major epilogue through smem + TMA stores
     {"igemm_tma_out", "FCUDA_IGEMM_TMA_OUT", 1, 0, 1, 0, false},     // implicit-GEMM epilogue through smem + TMA stores
+    {"igemm_pw", "FCUDA_IGEMM_PW", 1, 0, 1, 0, false},               // TMA-fed slab producer for 1x1 / stride-1 layers
+    {"wino_mlp", "FCUDA_WINO_MLP", 1, 0, 1, 0, false},               // Winograd transforms: asynchronous slab copies / all plane loads in flight
 };
 }  // namespace
+const char* tune_name(int key) { return key >= 0 && key < TUNE_COUNT ? g_tune[key].name : nullptr; }
 int tune_get(int key) {
     if (key < 0 || key >= TUNE_COUNT) return 0;
     TuneEntry& e = g_tune[key];

@@ -153,7 +153,15 @@ constexpr int kSegTiles = 5;   // tiles per block along x (one warp each)
 constexpr int kChBlock = 32;   // channels per block (one lane each)
 constexpr int kXformThreads = kSegTiles * 32;
 
-template <int T>
+// 4-byte asynchronous global -> shared copy (LDGSTS); ok == false writes a zero without touching global memory
+__device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gmem_src, bool ok) {
+    const unsigned sz = ok ? 4u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+                 ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src), "r"(sz)
+                 : "memory");
+}
+
+template <int T, bool ASYNC>
 __global__ void __launch_bounds__(kXformThreads)
 wino_input_kernel(const float* __restrict__ in, float* __restrict__ V, WinoGeom g, int R0, int Tc) {
     using W = Wino<T>;
@@ -184,9 +192,28 @@ wino_input_kernel(const float* __restrict__ in, float* __restrict__ V, WinoGeom 
 #pragma unroll
         for (int r = 0; r < T; ++r)
             if (static_cast<unsigned>(gy0 + r) < static_cast<unsigned>(g.H)) row_ok |= 1u << r;
+        if (ASYNC) {
+            // Every line of the slab as an asynchronous 4-byte copy: all ~52 loads of a lane are in flight at once (one
+            // memory latency per block instead of four dependent rounds of 16 register-staged loads), no staging registers,
+            // no STS; padding = zero-fill copies that do not touch global memory.
+            if (lane < COLS) {
+                for (int c = w; c < kChBlock; c += kSegTiles) {
+                    const int ic = c0 + c;
+                    const bool c_ok = x_ok && ic < g.C_in;
+                    const float* p = c_ok ? img + static_cast<size_t>(ic) * plane + static_cast<long long>(gy0) * g.W + gx : in;
+                    float* sp = slab + c * CH_STRIDE + lane;
+#pragma unroll
+                    for (int r = 0; r < T; ++r) {
+                        const bool ok = c_ok && ((row_ok >> r) & 1u);
+                        cp_async4_zfill(sp + r * COLS, ok ? p + r * g.W : in, ok);
+                    }
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
         // Channels w, w+5, ..., two per iteration: 2*T row loads are in flight per lane before the first shared-memory store
         // (ncu r02h: the kernel waits on global loads — long-scoreboard stalls, 37 % warp occupancy, 0.59 of HBM bandwidth)
-        for (int c = w; c < kChBlock; c += 2 * kSegTiles) {
+        for (int c = w; !ASYNC && c < kChBlock; c += 2 * kSegTiles) {
             float v[2][T];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -244,7 +271,7 @@ wino_input_kernel(const float* __restrict__ in, float* __restrict__ V, WinoGeom 
 // (pooling_layer.h:38-91, pad 0) is applied to the tile in registers — the 6x6 (2x2) output tile starts at an even
 // coordinate, so no window straddles two tiles — and only the pooled (OH+1)/2 x (OW+1)/2 blob is written.
 // ------------------------------------------------------------------------------------------------
-template <int T, bool POOL>
+template <int T, bool POOL, bool MLP>
 __global__ void __launch_bounds__(kXformThreads)
 wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const float* __restrict__ bias, WinoGeom g,
                    int R0, int Tc, int relu) {
@@ -274,8 +301,16 @@ wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const f
         for (int a = 0; a < T; ++a)
 #pragma unroll
             for (int b = 0; b < T; ++b)
-                mm[a][b] = __ldg(reinterpret_cast<const float*>(
-                    m + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(a * T + b)));
+                if (MLP) {
+                    // all T*T plane loads issued back to back (volatile: nvcc otherwise interleaves them column by column with
+                    // the transform to save registers — 56 registers, eight dependent rounds of memory latency per tile)
+                    asm volatile("ld.volatile.global.f32 %0, [%1];"
+                                 : "=f"(mm[a][b])
+                                 : "l"(m + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(a * T + b)));
+                } else {
+                    mm[a][b] = __ldg(reinterpret_cast<const float*>(
+                        m + static_cast<unsigned long long>(plane_bytes) * static_cast<uint32_t>(a * T + b)));
+                }
         float tmp[OT][T];
 #pragma unroll
         for (int b = 0; b < T; ++b) {
@@ -369,8 +404,14 @@ int wino_input_transform(int tile, const float* in, float* V, const WinoGeom& g,
     const double imgs = static_cast<double>(R1 - R0) / g.tilesY;  // tile-rows of the chunk, in images
     const int prof = prof_begin(s, PROF_WINO_INPUT, 0, 0,
                                 4.0 * (imgs * g.C_in * g.H * g.W + static_cast<double>(tile) * tile * Tc * g.C_in));
-    if (tile == 8) wino_input_kernel<8><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
-    else wino_input_kernel<4><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
+    const bool mlp = tune_get(TUNE_WINO_MLP) != 0;
+    if (tile == 8) {
+        if (mlp) wino_input_kernel<8, true><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
+        else wino_input_kernel<8, false><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
+    } else {
+        if (mlp) wino_input_kernel<4, true><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
+        else wino_input_kernel<4, false><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
+    }
     prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();
     count_launch();
@@ -386,12 +427,18 @@ int wino_output_transform(int tile, const float* M, float* out, const float* bia
     const double out_px = pool ? static_cast<double>((g.OH + 1) / 2) * ((g.OW + 1) / 2) : static_cast<double>(g.OH) * g.OW;
     const int prof = prof_begin(s, PROF_WINO_OUTPUT, 0, 0,
                                 4.0 * (imgs * g.C_out * out_px + static_cast<double>(tile) * tile * Tc * g.C_out));
+    const bool mlp = tune_get(TUNE_WINO_MLP) != 0;
     if (tile == 8) {
-        if (pool) wino_output_kernel<8, true><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
-        else wino_output_kernel<8, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+        if (mlp) {
+            if (pool) wino_output_kernel<8, true, true><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+            else wino_output_kernel<8, false, true><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+        } else {
+            if (pool) wino_output_kernel<8, true, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+            else wino_output_kernel<8, false, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+        }
     } else {
-        if (pool) wino_output_kernel<4, true><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
-        else wino_output_kernel<4, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+        if (pool) wino_output_kernel<4, true, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+        else wino_output_kernel<4, false, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
     }
     prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();

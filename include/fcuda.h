@@ -203,6 +203,9 @@ int fcuda_conv_forward_ext(const FcudaConvParam* param, int algo, float* output,
  *   gemm_cluster (1|2|4, 1)   TMA multicast of the B operand across a thread-block cluster in the TensorGEMM
  *   gemm_tma_store (0-1, 1)   row-major TensorGEMM epilogue through shared memory + TMA stores
  *   igemm_tma_out (0-1, 1)    implicit-GEMM epilogue through shared memory + TMA stores (0: per-thread stores)
+ *   igemm_pw (0-1, 1)         TMA-fed [32 channels][32 pixels] A boxes for 1x1 / stride-1 layers (0: generic gather)
+ *   wino_mlp (0-1, 1)         Winograd transforms with every global load of a block in flight at once (cp.async slab /
+ *                             back-to-back plane loads) instead of register-staged rounds
  * Every variant computes the same result (tests/test_gpu_variants.py).  Returns 0 / the value, -200 for an unknown name or value. */
 int fcuda_set_tuning(const char* name, int value);
 int fcuda_get_tuning(const char* name);

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 def tuning():
     from feathercnn_b200._lib import fcuda
     lib = fcuda()
-    names = ["igemm_issuers", "igemm_slab", "igemm_cta_group", "dw_vec", "gemm_cluster", "gemm_tma_store", "igemm_tma_out"]
+    names = ["igemm_issuers", "igemm_slab", "igemm_cta_group", "dw_vec", "gemm_cluster", "gemm_tma_store", "igemm_tma_out", "igemm_pw"]
     saved = {n: lib.fcuda_get_tuning(n.encode()) for n in names}
 
     def setter(**kw):
@@ -35,7 +35,10 @@ def _conv(cuda, booster, geom, algo, seed=0, group=1):
 
 
 IGEMM_GEOMS = [(64, 64, 96, 96, 3, 1, 1, 3), (128, 64, 56, 56, 3, 1, 1, 4), (256, 64, 28, 28, 1, 1, 0, 8),
-               (64, 256, 28, 28, 1, 1, 0, 8), (128, 96, 29, 31, 3, 2, 1, 3), (64, 3, 64, 64, 3, 1, 1, 2)]
+               (64, 256, 28, 28, 1, 1, 0, 8), (128, 96, 29, 31, 3, 2, 1, 3), (64, 3, 64, 64, 3, 1, 1, 2),
+               (96, 128, 14, 14, 1, 1, 0, 5),     # pointwise, 196-pixel images: boxes end inside a tile, tiles straddle images
+               (512, 2048, 7, 7, 1, 1, 0, 3),     # 49-pixel images (H*W % 4 != 0): the pointwise slab does not apply
+               (40, 32, 10, 6, 1, 1, 0, 1)]       # one partial tile (60 pixels): two of the four boxes are out of range
 
 
 @pytest.mark.parametrize("geom", IGEMM_GEOMS)
@@ -57,6 +60,8 @@ def test_implicit_gemm_variants_are_bit_identical(cuda, tuning, geom):
     np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
     tuning(igemm_cta_group=1, igemm_slab=1, igemm_tma_out=0)   # per-thread stores instead of the TMA-store epilogue
     np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
+    tuning(igemm_tma_out=1, igemm_pw=0)            # generic gather instead of the pointwise TMA boxes
+    np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
 
 
 @pytest.mark.parametrize("geom", IGEMM_GEOMS)
@@ -75,7 +80,9 @@ def test_bf16x3_implicit_gemm_variants(cuda, tuning, geom):
     np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
     tuning(igemm_slab=1, igemm_tma_out=0)
     np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
-    tuning(igemm_tma_out=1, igemm_issuers=1)
+    tuning(igemm_tma_out=1, igemm_pw=0)
+    np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
+    tuning(igemm_pw=1, igemm_issuers=1)
     one = _conv(cuda, booster, geom, booster.SGECONV)
     assert np.abs(one - base).max() / np.abs(base).max() < 1e-5
 
