@@ -139,6 +139,17 @@ def feather() -> ctypes.CDLL:
             "fnet_fuse_now": (i, [vp]),
             "fnet_layer_fused_away": (i, [vp, cp]),
             "fnet_input_name": (cp, [vp]),
+            "fgroup_create": (vp, []),
+            "fgroup_destroy": (None, [vp]),
+            "fgroup_set_options": (None, [vp, i, i]),
+            "fgroup_init_from_path": (i, [vp, cp, ip, i]),
+            "fgroup_size": (i, [vp]),
+            "fgroup_device": (i, [vp, i]),
+            "fgroup_member": (vp, [vp, i]),
+            "fgroup_broadcast_transport": (cp, [vp]),
+            "fgroup_forward_batch": (i, [vp, vp, i, cp, vp]),
+            "fgroup_shard_range": (i, [i, i, i, ip, ip]),
+            "fgroup_synchronize": (i, [vp]),
         }
         for name, (res, args) in sigs.items():
             fn = getattr(lib, name)

@@ -72,7 +72,12 @@ constexpr int kWarpMma = kWarpTma + 1;                    // then one TMA(B) war
 constexpr int kIssuers = 2;
 constexpr int kWarpSlab = kWarpMma + kIssuers;             // SLAB kernels: TMA producer of the input slabs (idle otherwise)
 constexpr int kThreadsIg = (kWarpSlab + 1) * 32;
-constexpr int kStagesIg = 4;                              // ring depth shared by the smem B tiles and the TMEM A tiles
+// Ring depth shared by the smem B tiles and the TMEM A tiles.  3xTF32: 4 (4 x 64 A columns + 256 accumulator columns fill
+// tensor memory).  BF16x3: 8 — its A stage is 32 columns and its filter stage half the bytes, and the ring was the limiter:
+// with 4 slots VGG conv1_2 ran a k-block every ~610 cycles in BOTH modes (ncu launch list r02o: 1.10 ms -> 1.04 ms although
+// the MMA time per k-block fell from 384 to 192 cycles) — a slot's cycle free -> produce -> full -> MMA -> retire -> free is a
+// ~2,400-cycle latency chain, so throughput = slots / chain.
+__host__ __device__ constexpr int igemm_stages(int planes) { return planes == 3 ? 8 : 4; }
 constexpr int kMaxTableK = 6144;                          // k-table entries that fit beside the B ring and the staging tiles
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -177,7 +182,7 @@ __host__ __device__ constexpr int slab_stages(int bn) { return bn <= 64 ? 3 : 2;
 // of HBM in round 1).
 constexpr int kPwBoxBytes = 32 * 32 * 4;              // one quadrant's box
 constexpr int kPwStageBytes = 4 * kPwBoxBytes;        // 16 KB per k-block
-__host__ __device__ constexpr int pw_stages(int bn, int planes) { return (planes == 2 && bn > 64) ? 3 : 6; }
+__host__ __device__ constexpr int pw_stages(int bn, int planes) { return bn > 64 && planes >= 2 ? 3 : 6; }
 constexpr int kMaxSlabStages = 6;
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(kThreadsIg, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
                   const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
                   const IgemmArgs args) {
-    constexpr int STAGES = kStagesIg;
+    constexpr int STAGES = igemm_stages(PLANES);
     constexpr bool SLAB = SK == 1;                          // 3x3 / stride-1 halo slabs (patch-shaped tiles)
     constexpr bool PW = SK == 2;                            // pointwise slabs (box-shaped tiles, like the generic gather)
     static_assert(!(PW && CG == 2), "pairs are not combined with the pointwise slab");
@@ -1158,7 +1163,7 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     }
     const int table_bytes = a.use_table == 1 ? a.kblocks * 32 * 8 : 0;
     constexpr int kOutStage = 4 * ((SLAB && BN == 128 && CG == 1) ? 1 : 2) * 4096;
-    const int smem = kStagesIg * kStage + (SLAB ? slab_stages(BN) * kSlabStageBytes : PW ? pw_stages(BN, PLANES) * kPwStageBytes : 0) +
+    const int smem = igemm_stages(PLANES) * kStage + (SLAB ? slab_stages(BN) * kSlabStageBytes : PW ? pw_stages(BN, PLANES) * kPwStageBytes : 0) +
                      kOutStage + table_bytes + a.oc_pad * 4 + 1024;
     if (smem > 227 * 1024 - 2048) return -1;
     auto kern = conv_igemm_kernel<BN, PLANES, SK, CG>;

@@ -4,6 +4,7 @@
 
 #include <feather/ncnn/modelbin.h>
 #include <feather/net.h>
+#include <feather/net_group.h>
 #include <string.h>
 
 #include <stdio.h>
@@ -12,6 +13,7 @@
 #include <string>
 
 using feather::Net;
+using feather::NetGroup;
 
 // No C++ exception may cross the C boundary (a corrupt model must produce an error code, not std::terminate).
 #define FNET_GUARD(expr)                                   \
@@ -103,4 +105,34 @@ size_t fnet_blob_names(void* h, char* buf, size_t cap) {
 }
 const char* fnet_input_name(void* h) { return static_cast<Net*>(h)->InputName().c_str(); }
 
+
+// ---- feather::NetGroup (include/feather/net_group.h): one model on several GPUs of one box from one process --------------
+void* fgroup_create(void) { return new NetGroup(); }
+void fgroup_destroy(void* g) { delete static_cast<NetGroup*>(g); }
+void fgroup_set_options(void* g, int fusion, int cuda_graph) {
+    static_cast<NetGroup*>(g)->SetFusion(fusion != 0);
+    static_cast<NetGroup*>(g)->SetCudaGraph(cuda_graph != 0);
+}
+int fgroup_init_from_path(void* g, const char* model_path, const int* devices, int count) {
+    FNET_GUARD(static_cast<NetGroup*>(g)->InitFromPath(model_path, devices, count))
+}
+int fgroup_size(void* g) { return static_cast<NetGroup*>(g)->Size(); }
+int fgroup_device(void* g, int i) {
+    NetGroup* grp = static_cast<NetGroup*>(g);
+    return (i >= 0 && i < grp->Size()) ? grp->Device(i) : -1;
+}
+void* fgroup_member(void* g, int i) {
+    NetGroup* grp = static_cast<NetGroup*>(g);
+    return (i >= 0 && i < grp->Size()) ? grp->Member(i) : nullptr;
+}
+const char* fgroup_broadcast_transport(void* g) { return static_cast<NetGroup*>(g)->BroadcastTransport(); }
+int fgroup_forward_batch(void* g, const float* host_nchw, int batch, const char* blob, float* host_out) {
+    FNET_GUARD(static_cast<NetGroup*>(g)->ForwardBatch(host_nchw, batch, blob, host_out))
+}
+int fgroup_shard_range(int batch, int members, int i, int* lo, int* hi) {
+    if (!lo || !hi || members < 1 || i < 0 || i >= members || batch < 0) return -1;
+    NetGroup::ShardRange(batch, members, i, lo, hi);
+    return 0;
+}
+int fgroup_synchronize(void* g) { return static_cast<NetGroup*>(g)->Synchronize(); }
 }  // extern "C"

@@ -284,6 +284,20 @@ int Net::InitFromBuffer(const void* net_buffer, size_t size) {
     return rc;
 }
 
+// Graph only (no weights): what a non-root member of a NetGroup / a non-root rank needs before PrepareWeightArena.
+int Net::InitGraphFromBuffer(const void* net_buffer, size_t size) {
+    const unsigned char* p = static_cast<const unsigned char*>(net_buffer);
+    if (size < 16 || memcmp(p, kContainerMagic, 8) != 0) {
+        LOGE("not a .feathermodel container (magic FTHRB200 missing)");
+        return -1;
+    }
+    uint64_t param_len = 0;
+    memcpy(&param_len, p + 8, 8);
+    if (param_len > size - 16) return -1;
+    std::string text(reinterpret_cast<const char*>(p + 16), static_cast<size_t>(param_len));
+    return ParseParamText(text.c_str());
+}
+
 int Net::InitFromFile(FILE* fp) {
     fseek(fp, 0, SEEK_END);
     const long len = ftell(fp);

@@ -171,3 +171,78 @@ class Net:
     @property
     def launches_per_forward(self) -> int:
         return int(self._lib.fnet_launches_per_forward(self._h))
+
+
+class NetGroup:
+    """``feather::NetGroup`` (include/feather/net_group.h): one model on several GPUs of one box from ONE process — the file
+    is read once, the weight arena reaches the other devices by one ncclBroadcast, every batch is sharded contiguously
+    over the devices, no collective in Forward."""
+
+    def __init__(self, fusion: bool = True, cuda_graph: bool = True):
+        self._lib = feather()
+        self._h = ctypes.c_void_p(self._lib.fgroup_create())
+        self._lib.fgroup_set_options(self._h, int(fusion), int(cuda_graph))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.fgroup_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def InitFromPath(self, path, devices: list[int] | None = None) -> None:
+        if devices:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self._lib.fgroup_init_from_path(self._h, str(path).encode(), arr, len(devices))
+        else:
+            rc = self._lib.fgroup_init_from_path(self._h, str(path).encode(), None, 0)
+        _check("NetGroup.InitFromPath", rc)
+
+    def Size(self) -> int:
+        return int(self._lib.fgroup_size(self._h))
+
+    def Device(self, member: int) -> int:
+        return int(self._lib.fgroup_device(self._h, member))
+
+    def BroadcastTransport(self) -> str:
+        return self._lib.fgroup_broadcast_transport(self._h).decode()
+
+    def Member(self, member: int) -> Net:
+        """A non-owning view of a member Net (Extract / BlobShape / ... on that device)."""
+        h = self._lib.fgroup_member(self._h, member)
+        if not h:
+            raise FeatherError("NetGroup.Member", -1)
+        return _BorrowedNet(self._lib, ctypes.c_void_p(h), self)
+
+    def ForwardBatch(self, x: np.ndarray, blob: str, out_shape_per_image: tuple[int, ...]) -> np.ndarray:
+        """Shards the host batch `x` (N, C, H, W) over the members; returns `blob` of every image, in input order."""
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty((x.shape[0],) + tuple(out_shape_per_image), np.float32)
+        _check("NetGroup.ForwardBatch", self._lib.fgroup_forward_batch(
+            self._h, x.ctypes.data_as(ctypes.c_void_p), x.shape[0], blob.encode(), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def ForwardBatchPtr(self, host_ptr: int, batch: int, blob: str | None, host_out_ptr: int = 0) -> None:
+        _check("NetGroup.ForwardBatch", self._lib.fgroup_forward_batch(
+            self._h, ctypes.c_void_p(host_ptr), batch, blob.encode() if blob else None, ctypes.c_void_p(host_out_ptr)))
+
+    def ShardRange(self, batch: int, member: int) -> tuple[int, int]:
+        lo, hi = ctypes.c_int(), ctypes.c_int()
+        _check("NetGroup.ShardRange", self._lib.fgroup_shard_range(batch, self.Size(), member, ctypes.byref(lo), ctypes.byref(hi)))
+        return lo.value, hi.value
+
+    def Synchronize(self) -> None:
+        _check("NetGroup.Synchronize", self._lib.fgroup_synchronize(self._h))
+
+
+class _BorrowedNet(Net):
+    """Net methods on a handle owned by a NetGroup."""
+
+    def __init__(self, lib, handle, owner):
+        self._lib = lib
+        self._h = handle
+        self._owner = owner
+
+    def __del__(self):
+        self._h = None

@@ -49,6 +49,7 @@ public:
     int InitFromPath(const char* model_path);
     int InitFromFile(FILE* fp);
     int InitFromBuffer(const void* net_buffer, size_t size);
+    int InitGraphFromBuffer(const void* net_buffer, size_t size);  // the container's graph only; weights via the arena calls below
     int Forward(const float* input);                 // one image shaped like the model's Input layer
     int Forward(const float* input, int height, int width);
     int ExtractBlob(float* output_ptr, std::string blob_name);

@@ -50,6 +50,23 @@ int fnet_input_shape(void* net, int* c, int* h, int* w);
 size_t fnet_blob_names(void* net, char* buf, size_t cap);
 const char* fnet_input_name(void* net);
 
+
+/* ---- feather::NetGroup (include/feather/net_group.h): one model replicated on several GPUs of one box from ONE process:
+ * the file is read once, the weight arena reaches the other devices by one ncclBroadcast (dlopen'ed libnccl; peer copies
+ * when absent), every batch is sharded contiguously over the devices; no collective in Forward. */
+void* fgroup_create(void);
+void fgroup_destroy(void* group);
+void fgroup_set_options(void* group, int fusion, int cuda_graph);          /* before fgroup_init_from_path */
+int fgroup_init_from_path(void* group, const char* model_path, const int* devices, int count); /* NULL / 0: all devices */
+int fgroup_size(void* group);
+int fgroup_device(void* group, int member);
+void* fgroup_member(void* group, int member);                              /* the member's Net handle (fnet_* calls) */
+const char* fgroup_broadcast_transport(void* group);                       /* "nccl" | "cudaMemcpyPeer" | "" */
+/* shards `batch` host images over the members, gathers `blob` of every image in input order into host_out (may be NULL) */
+int fgroup_forward_batch(void* group, const float* host_nchw, int batch, const char* blob, float* host_out);
+int fgroup_shard_range(int batch, int members, int member, int* lo, int* hi);  /* rows [lo, hi) of a batch run on `member` */
+int fgroup_synchronize(void* group);
+
 #ifdef __cplusplus
 }
 #endif

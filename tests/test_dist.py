@@ -46,6 +46,27 @@ def test_shard_range_partitions_exactly():
     assert shard_range(1024, 3, 8) == (384, 512)  # BASELINE.json configs[4]: 1024 images over 8 GPUs
 
 
+def test_net_group_shards_like_the_process_per_gpu_path():
+    """feather::NetGroup (one process, N devices) splits a batch exactly like dist.shard_range (one process per device)."""
+    import ctypes
+    from feathercnn_b200._lib import feather
+    from feathercnn_b200.dist import shard_range
+    lib = feather()
+    lo, hi = ctypes.c_int(), ctypes.c_int()
+    for total in (0, 1, 7, 64, 1000, 1024):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                assert lib.fgroup_shard_range(total, world, r, ctypes.byref(lo), ctypes.byref(hi)) == 0
+                assert (lo.value, hi.value) == shard_range(total, r, world)
+    assert lib.fgroup_shard_range(8, 2, 2, ctypes.byref(lo), ctypes.byref(hi)) == -1   # member out of range
+    g = lib.fgroup_create()
+    try:
+        assert lib.fgroup_size(g) == 0 and lib.fgroup_broadcast_transport(g) == b""
+        assert lib.fgroup_forward_batch(g, None, 1, None, None) == -1                  # not initialised
+    finally:
+        lib.fgroup_destroy(g)
+
+
 def test_two_rank_broadcast_and_gather_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -271,3 +271,36 @@ def test_graph_cache_survives_growth_and_equal_sized_shapes(cuda, model_dir):
             plain.Forward(t)
             assert net.BlobShape(out_name) == plain.BlobShape(out_name)
             np.testing.assert_array_equal(net.Extract(out_name), plain.Extract(out_name))
+
+
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_net_group_one_process_many_devices(cuda, model_dir, ndev):
+    """feather::NetGroup: the model is read once, the weight arena is broadcast (NCCL) to the other devices, one host
+    batch is sharded over them; outputs are bit-identical to a single Net forwarding the whole batch."""
+    from feathercnn_b200.net import NetGroup
+    from feathercnn_b200.tools import feathermodel, modelgen
+    if cuda.cuda.device_count() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    m, (param, binf) = _save(model_dir, "mini")
+    x = np.stack([modelgen.synthetic_input(m.shape["data"], i) for i in range(5)])
+    single = _gpu_net(param, binf, fusion=True, cuda_graph=True)
+    single.Forward(x)
+    want = single.Extract("prob")
+    for path in (str(param)[:-len(".param")], None):       # <stem>.param/.bin, then the single-file container
+        if path is None:
+            path = str(model_dir / "mini_group.feathermodel")
+            feathermodel.pack(param, binf, path)
+        g = NetGroup(fusion=True, cuda_graph=True)
+        g.InitFromPath(path, devices=list(range(ndev)))
+        assert g.Size() == ndev and [g.Device(i) for i in range(ndev)] == list(range(ndev))
+        assert g.BroadcastTransport() == ("" if ndev == 1 else "nccl")
+        got = g.ForwardBatch(x, "prob", want.shape[1:])
+        np.testing.assert_array_equal(got, want)
+        got2 = g.ForwardBatch(x[:3], "prob", want.shape[1:])    # a second batch: smaller than the first, uneven shards
+        np.testing.assert_array_equal(got2, want[:3])
+        spans = [g.ShardRange(3, i) for i in range(ndev)]
+        assert spans[0][0] == 0 and spans[-1][1] == 3
+        for i, (lo, hi) in enumerate(spans):                    # every member holds exactly its shard of the last batch
+            assert g.Member(i).BlobShape("prob")[0] == hi - lo
+        del g
+    cuda.cuda.set_device(0)
