@@ -122,6 +122,7 @@ struct IgemmArgs {
     int tma_out;             // epilogue stores through shared memory + TMA (tmOut is valid); pooled tiles keep direct stores
     int pool;                // SLAB only: fuse a following 2x2 / stride-2 max pooling; `out` is the pooled blob
     int2 ktab1[32];          // use_table == 2 (K <= 32, e.g. IC = 3 first layers): the k-table in the kernel parameters
+    unsigned suspend_ns;     // suspend hint of the ring / slab / accumulator waits (0 = poll), see ptx::mbar_try_wait_ns
     int taps;                // KH*KW
     unsigned tap_inv;        // ceil(65536 / KW): tap / KW == (tap * tap_inv) >> 16 for tap < 64
 };
@@ -213,10 +214,10 @@ __device__ __forceinline__ uint64_t* ring_release_bar(uint64_t (*empty_bar)[STAG
     return &empty_bar[(g / STAGES) & 1u][g & (STAGES - 1)];
 }
 template <int STAGES>
-__device__ __forceinline__ void wait_ring_slot_free(uint64_t (*empty_bar)[STAGES], uint32_t g) {
+__device__ __forceinline__ void wait_ring_slot_free(uint64_t (*empty_bar)[STAGES], uint32_t g, uint32_t ns) {
     if (g >= STAGES) {
         const uint32_t gg = g - STAGES;  // the k-block that used this slot one round earlier
-        ptx::mbar_wait(ring_release_bar<STAGES>(empty_bar, gg), ((gg / STAGES) >> 1) & 1u);
+        ptx::mbar_wait(ring_release_bar<STAGES>(empty_bar, gg), ((gg / STAGES) >> 1) & 1u, ns);
     }
 }
 
@@ -264,6 +265,21 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
         "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
         : "memory");
+}
+// Explicit shared-memory load: through a generic pointer derived from the dynamic shared array nvcc emitted LD.E (generic
+// address path, long-scoreboard latency) for every slab read of the producers (profiles/r02r source page).
+__device__ __forceinline__ float lds_f32(uint32_t smem_addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t smem_addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t smem_addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -403,7 +419,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const uint32_t pt = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
             const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - pt * static_cast<uint32_t>(args.num_n));
             for (int kb = 0; kb < kblocks; ++kb, ++gb) {
-                wait_ring_slot_free<STAGES>(empty_bar, gb);
+                wait_ring_slot_free<STAGES>(empty_bar, gb, args.suspend_ns);
                 IG_TRACE(8, gb);
                 if (leader) {
                     uint8_t* st = smem + stage * kStage;
@@ -465,8 +481,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 const uint32_t ta = tmem_a0 + stage * kAStageCols;
                 const bool first_visit = kb < static_cast<int>(nissue);  // this thread's first k-block of the tile
                 if (CG == 1) {
-                    if (first_visit) ptx::mbar_wait(&tmem_empty_bar[as], ((it / static_cast<uint32_t>(args.acc_slots)) & 1u) ^ 1u);
-                    ptx::mbar_wait(&full_bar[stage], phase);
+                    if (first_visit) ptx::mbar_wait(&tmem_empty_bar[as], ((it / static_cast<uint32_t>(args.acc_slots)) & 1u) ^ 1u, args.suspend_ns);
+                    ptx::mbar_wait(&full_bar[stage], phase, args.suspend_ns);
                 } else {  // arrivals from the peer CTA: acquire at cluster scope
                     if (first_visit) ptx::mbar_wait_cluster(&tmem_empty_bar[as], ((it / static_cast<uint32_t>(args.acc_slots)) & 1u) ^ 1u);
                     ptx::mbar_wait_cluster(&full_bar[stage], phase);
@@ -533,7 +549,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 }
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
                     const uint32_t st = g % SST;
-                    ptx::mbar_wait(&slab_empty[st], ((g / SST) & 1u) ^ 1u);
+                    ptx::mbar_wait(&slab_empty[st], ((g / SST) & 1u) ^ 1u, args.suspend_ns);
                     if (leader) {
                         ptx::mbar_arrive_expect_tx(&slab_full[st], static_cast<uint32_t>(nvalid) * kPwBoxBytes);
 #pragma unroll
@@ -556,7 +572,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 const BoxCoord bx = decode_patch(ptile, args);
                 for (int cb = 0; cb < cblocks; ++cb, ++j) {
                     const uint32_t st = j % SST;
-                    ptx::mbar_wait(&slab_empty[st], ((j / SST) & 1u) ^ 1u);
+                    ptx::mbar_wait(&slab_empty[st], ((j / SST) & 1u) ^ 1u, args.suspend_ns);
                     if (leader) {
                         ptx::mbar_arrive_expect_tx(&slab_full[st], kSlabStageBytes);
                         tma_load_4d(slab0 + st * kSlabStageBytes, &tmIn, &slab_full[st], bx.ox0 - kSlabShift,
@@ -586,15 +602,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         for (long long tile = tile_first; tile < total_tiles; tile += tile_step) {
             for (int cb = 0; cb < cblocks; ++cb, ++j) {
                 const uint32_t st = j % SST;
-                ptx::mbar_wait(&slab_full[st], (j / SST) & 1u);
-                const char* tb = reinterpret_cast<const char*>(slab0 + st * kSlabStageBytes) + lane_off;
+                ptx::mbar_wait(&slab_full[st], (j / SST) & 1u, args.suspend_ns);
+                const uint32_t tb = ptx::smem_u32(slab0 + st * kSlabStageBytes) + static_cast<uint32_t>(lane_off);
 #pragma unroll 1
                 for (int u = 0; u < 3; ++u) {
                     const uint32_t g = j * 9u + static_cast<uint32_t>(3 * u + group);
                     const int my_stage = static_cast<int>(g & (STAGES - 1));
                     const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
-                    const char* src = tb + u * (kSlabCols * 4);
-                    wait_ring_slot_free<STAGES>(empty_bar, g);
+                    const uint32_t src = tb + static_cast<uint32_t>(u * (kSlabCols * 4));
+                    if (q == 0) IG_TRACE(0, g);
+                    wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
+                    if (q == 0) IG_TRACE(1, g);
                     ptx::tc_fence_after();
                     if (BF) {
 #pragma unroll
@@ -602,8 +620,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                             uint32_t hi[8], lo[8];
 #pragma unroll
                             for (int r = 0; r < 8; ++r) {
-                                const float x0 = *reinterpret_cast<const float*>(src + (part * 16 + 2 * r) * kSlabChBytes);
-                                const float x1 = *reinterpret_cast<const float*>(src + (part * 16 + 2 * r + 1) * kSlabChBytes);
+                                const float x0 = lds_f32(src + (part * 16 + 2 * r) * kSlabChBytes);
+                                const float x1 = lds_f32(src + (part * 16 + 2 * r + 1) * kSlabChBytes);
                                 split_bf16x2(x0, x1, hi[r], lo[r]);
                             }
                             tmem_st_32x8(ta + part * 8, hi);
@@ -615,14 +633,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
-                            const float x = *reinterpret_cast<const float*>(src + (part * 8 + r) * kSlabChBytes);
+                            const float x = lds_f32(src + (part * 8 + r) * kSlabChBytes);
                             hi[r] = PLANES == 2 ? (__float_as_uint(x) & 0xFFFFE000u) : __float_as_uint(x);
                             lo[r] = __float_as_uint(x - __uint_as_float(hi[r]));
                         }
                         tmem_st_32x8(ta + part * 8, hi);
                         if (PLANES == 2) tmem_st_32x8(ta + 32 + part * 8, lo);
                     }
+                    if (q == 0) IG_TRACE(2, g);
                     tmem_st_wait();
+                    if (q == 0) IG_TRACE(4, g);
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -649,9 +669,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const uint32_t st = g % SST;
             const int my_stage = static_cast<int>(g & (STAGES - 1));
             const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
-            const char* src = reinterpret_cast<const char*>(slab0 + st * kPwStageBytes + q * kPwBoxBytes) + lane * 4;
-            ptx::mbar_wait(&slab_full[st], (g / SST) & 1u);
-            wait_ring_slot_free<STAGES>(empty_bar, g);
+            const uint32_t src = ptx::smem_u32(slab0 + st * kPwStageBytes + q * kPwBoxBytes) + static_cast<uint32_t>(lane * 4);
+            ptx::mbar_wait(&slab_full[st], (g / SST) & 1u, args.suspend_ns);
+            wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
             ptx::tc_fence_after();
             if (BF) {
 #pragma unroll
@@ -659,8 +679,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        const float x0 = *reinterpret_cast<const float*>(src + (part * 16 + 2 * r) * 128);
-                        const float x1 = *reinterpret_cast<const float*>(src + (part * 16 + 2 * r + 1) * 128);
+                        const float x0 = lds_f32(src + (part * 16 + 2 * r) * 128);
+                        const float x1 = lds_f32(src + (part * 16 + 2 * r + 1) * 128);
                         split_bf16x2(x0, x1, hi[r], lo[r]);
                     }
                     tmem_st_32x8(ta + part * 8, hi);
@@ -672,7 +692,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const float x = *reinterpret_cast<const float*>(src + (part * 8 + r) * 128);
+                    const float x = lds_f32(src + (part * 8 + r) * 128);
                     hi[r] = PLANES == 2 ? (__float_as_uint(x) & 0xFFFFE000u) : __float_as_uint(x);
                     lo[r] = __float_as_uint(x - __uint_as_float(hi[r]));
                 }
@@ -805,7 +825,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const int my_stage = static_cast<int>(g & (STAGES - 1));
             const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
             if (q == 0) IG_TRACE(0, g);
-            wait_ring_slot_free<STAGES>(empty_bar, g);
+            wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
             if (q == 0) IG_TRACE(1, g);
             ptx::tc_fence_after();
             if (BF) {
@@ -908,7 +928,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 asm volatile("" : "+l"(dst));  // one IMAD.WIDE per store off an opaque base
                 // fused Eltwise SUM: the other addend sits at the same NCHW position
                 const long long res_off = args.residual ? reinterpret_cast<const char*>(args.residual) - reinterpret_cast<const char*>(args.out) : 0;
-                const float4* b4 = reinterpret_cast<const float4*>(bias_s + oc0);
+                const uint32_t b4 = ptx::smem_u32(bias_s + oc0);  // bias_s is padded with zeros up to oc_pad
                 // all addend loads first (32 in flight), then the accumulator wait: a load placed next to its store
                 // is serialised behind the previous store by the aliasing rules (measured 2.4x slower epilogue)
                 float res[32];
@@ -940,15 +960,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     // 2x2 / stride-2 max pooling of the sub-patch (pooling_layer.h:38-91, pad 0): the window of the pixel at
                     // an even (row, column) is lanes {l, l^1, l^16, l^17}; pixels outside the image hold -inf.  max commutes
                     // with the per-channel bias and with ReLU, so both are applied to the pooled value.
+                    // The bias comes in ahead of the stores, 16 channels at a time: read through a generic pointer next to its
+                    // store (round 2 until r02r) every channel paid a full generic-load latency behind the previous store —
+                    // ~10k cycles per tile, the whole pooled layer was paced by this loop (ncu source page r02r).
                     const bool writer = ok && (lane & 17) == 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float v = ok ? __uint_as_float(r[j]) + res[j] : -INFINITY;
-                        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
-                        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-                        if (writer && oc0 + j < args.OC)
-                            *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(j)) =
-                                fmaxf(v + bias_s[oc0 + j], floor_v);
+                    for (int h = 0; h < 2; ++h) {
+                        float bb[16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 bv = lds_f32x4(b4 + 64 * h + 16 * i);
+                            bb[4 * i] = bv.x; bb[4 * i + 1] = bv.y; bb[4 * i + 2] = bv.z; bb[4 * i + 3] = bv.w;
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const int j = h * 16 + jj;
+                            float v = ok ? __uint_as_float(r[j]) + res[j] : -INFINITY;
+                            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+                            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+                            if (writer && oc0 + j < args.OC)
+                                *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(j)) =
+                                    fmaxf(v + bb[jj], floor_v);
+                        }
                     }
                 } else if (tma_out) {
                     // Per-thread STG moved ~15 B/clk per SM here (igemm trace of VGG conv1_1: 2,250 cycles of epilogue per
@@ -958,15 +991,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     uint8_t* stg = stage_out + (q * kOutBufs + (kOutBufs == 2 ? (ebuf & 1u) : 0u)) * 4096;
                     if (lane == 0) ptx::tma_store_wait_read<kOutBufs - 1>();  // the store that last read this tile is done with it
                     __syncwarp();
-                    float* sp = reinterpret_cast<float*>(stg) + lane;
+                    const uint32_t sp = ptx::smem_u32(stg) + static_cast<uint32_t>(lane * 4);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 bv = b4[j4];  // bias_s is padded with zeros up to oc_pad
+                        const float4 bv = lds_f32x4(b4 + 16 * j4);
                         const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int j = j4 * 4 + e;
-                            sp[j * 32] = fmaxf(__uint_as_float(r[j]) + res[j] + bb[e], floor_v);
+                            sts_f32(sp + j * 128, fmaxf(__uint_as_float(r[j]) + res[j] + bb[e], floor_v));
                         }
                     }
                     ptx::fence_proxy_async_smem();
@@ -981,7 +1014,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     if (oc0 + 32 <= args.OC) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 bv = b4[j4];
+                            const float4 bv = lds_f32x4(b4 + 16 * j4);
                             const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -995,7 +1028,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         for (int j = 0; j < 32; ++j)
                             if (oc0 + j < args.OC)
                                 *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(j)) =
-                                    fmaxf(__uint_as_float(r[j]) + res[j] + bias_s[oc0 + j], floor_v);
+                                    fmaxf(__uint_as_float(r[j]) + res[j] + lds_f32(b4 + 4 * j), floor_v);
                     }
                 }
             }
@@ -1139,6 +1172,7 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
         static_cast<long long>(p.H) * p.W >= (1ll << 30) || static_cast<long long>(p.OH) * p.OW >= (1ll << 30))
         return -1;
     a.relu = p.relu;
+    a.suspend_ns = static_cast<unsigned>(tune_get(TUNE_MBAR_SUSPEND_NS));
     // two issuers (one accumulator each) where one thread cannot keep the pipe fed: N <= 64 and at least four k-blocks
     // per tile (short-K tiles are epilogue-bound and would only pay the second accumulator read); BN = 128 has 768 cycles of MMA work per k-block against ~350 of issue work, and only 256 accumulator
     // columns.  FCUDA_IGEMM_ISSUERS=1 forces one issuer (diagnostic).

@@ -62,6 +62,35 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Same with a run-time suspend hint; ns == 0: no hint at all (the hardware's short default time limit — the caller spins).
+// Why: a warp parked by a long hint (SASS: NANOSLEEP.SYNCS) comes back several hundred cycles after the arrive that
+// completed the phase; on the operand-ring hand-offs that wake-up sits on a latency chain (profiles/r02r: 21 % of the
+// implicit GEMM's stall samples on one such instruction), so those waits poll instead.
+__device__ __forceinline__ bool mbar_try_wait_ns(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    if (ns) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must fail the launch (trap) instead of hanging the GPU.  The clock is only read every
 // 64th failed poll: the polls themselves park in the hardware (suspend hint), and in the producer-bound kernels the
 // wait loops of the idle roles were 10% of all issued instructions when they read the clock every time.
@@ -77,6 +106,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 4000000000LL) mbar_timeout_trap();  // ~2 s at 2 GHz
+        }
+    }
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    if (mbar_try_wait_ns(bar, parity, ns)) return;
+    long long t0 = 0;
+    for (uint32_t spins = 1; !mbar_try_wait_ns(bar, parity, ns); ++spins) {
+        if ((spins & 1023u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) mbar_timeout_trap();
         }
     }
 }

@@ -47,6 +47,7 @@ struct GemmKernelArgs {
     long long m_offset;
     long long split_stride;
     int tma_store;   // EPI_ROWMAJOR through shared memory + cp.async.bulk.tensor stores (tmD is valid)
+    unsigned suspend_ns;  // suspend hint of the operand-ring waits (0 = poll), see ptx::mbar_try_wait_ns
 };
 
 template <int BN, int PLANES>
@@ -399,7 +400,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int kb0 = ks * kb_per_split;
             const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
             for (int kb = kb0; kb < kb1; ++kb) {
-                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1, args.suspend_ns);
                 if (CL > 1) {
                     // my copy of the slot is free: tell the peers, then wait until theirs are (their multicast lands in
                     // my slot, mine in theirs)
@@ -487,13 +488,13 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int kb1 = min(kb0 + kb_per_split, args.k_blocks_total);
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+            ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1, args.suspend_ns);
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * BN;
             for (int kb = kb0; kb < kb1; ++kb) {
                 // a_ready implies full_bar (the splitters waited on it).  The tensor pipe's queue is shallow, so the
                 // NEXT slot's barrier is probed between this slot's MMAs; the blocking wait is the fallback.
-                if (!ready) ptx::mbar_wait(&a_ready_bar[stage], phase);
+                if (!ready) ptx::mbar_wait(&a_ready_bar[stage], phase, args.suspend_ns);
                 ptx::tc_fence_after();
                 const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
                 const uint32_t nphase = nstage == 0 ? phase ^ 1u : phase;
@@ -539,8 +540,8 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 g_par ^= 1;
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 if (!mine) continue;
-                ptx::mbar_wait(&full_bar[my_stage], my_phase);
-                const uint8_t* a = smem + my_stage * kStage + row_off;
+                ptx::mbar_wait(&full_bar[my_stage], my_phase, args.suspend_ns);
+                const uint32_t a = ptx::smem_u32(smem + my_stage * kStage) + row_off;
                 const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -548,8 +549,8 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t chunk = static_cast<uint32_t>(half * 4 + c) ^ sw;
-                        const float4 v = *reinterpret_cast<const float4*>(a + (chunk << 4));
-                        const float x[4] = {v.x, v.y, v.z, v.w};
+                        float x[4];  // explicit ld.shared: through the generic pointer nvcc emitted LD.E.128 (generic address path)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(a + (chunk << 4)));
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             hi[c * 4 + j] = __float_as_uint(x[j]) & 0xFFFFE000u;   // what the tensor core would read
@@ -601,10 +602,11 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (lane == 0) ptx::tma_store_wait_read<1>();  // the store issued two chunks ago has read this tile
                     __syncwarp();
                     ptx::tmem_ld_wait();
-                    uint8_t* rowp = stg + lane * 128;
+                    const uint32_t rowp = ptx::smem_u32(stg) + static_cast<uint32_t>(lane * 128);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + ((j ^ (lane & 7)) << 4)), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                                     "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -670,7 +672,8 @@ TuneEntry g_tune[TUNE_COUNT] = {
     {"gemm_tma_store", "FCUDA_GEMM_TMA_STORE", 1, 0, 1, 0, false},   // row-major epilogue through smem + TMA stores
     {"igemm_tma_out", "FCUDA_IGEMM_TMA_OUT", 1, 0, 1, 0, false},     // implicit-GEMM epilogue through smem + TMA stores
     {"igemm_pw", "FCUDA_IGEMM_PW", 1, 0, 1, 0, false},               // TMA-fed slab producer for 1x1 / stride-1 layers
-    {"wino_mlp", "FCUDA_WINO_MLP", 1, 0, 1, 0, false},               // Winograd transforms: asynchronous slab copies / all plane loads in flight
+    {"wino_mlp", "FCUDA_WINO_MLP", 2, 0, 2, 0, false},
+    {"mbar_suspend_ns", "FCUDA_MBAR_SUSPEND_NS", 100000, 0, 1000000, 0, false},  // suspend hint of the implicit GEMM's hand-off waits (0 = poll)               // Winograd transforms: asynchronous slab copies / all plane loads in flight
 };
 }  // namespace
 const char* tune_name(int key) { return key >= 0 && key < TUNE_COUNT ? g_tune[key].name : nullptr; }
@@ -912,6 +915,7 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
     const bool tma_store_off = tune_get(TUNE_GEMM_TMA_STORE) == 0;
     CUtensorMap tmD = tmA;
     a.tma_store = 0;
+    a.suspend_ns = static_cast<unsigned>(tune_get(TUNE_MBAR_SUSPEND_NS));
     if (p.epilogue == EPI_ROWMAJOR && !tma_store_off && p.ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0) {
         if ((rc = make_map_2(&tmD, p.D, p.N, p.M, p.G, p.ldd, static_cast<long long>(p.M) * p.ldd, 32, 32))) return rc;
         a.tma_store = 1;

@@ -163,20 +163,23 @@ __device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gm
 
 template <int T, bool ASYNC>
 __global__ void __launch_bounds__(kXformThreads)
-wino_input_kernel(const float* __restrict__ in, float* __restrict__ V, WinoGeom g, int R0, int Tc) {
+wino_input_kernel(const float* __restrict__ in, float* __restrict__ V, WinoGeom g, int R0, int Tc, int ncb) {
     using W = Wino<T>;
     constexpr int OT = W::kOut;
     constexpr int COLS = OT * kSegTiles + (T - OT);  // 32 for F(6,3)
     constexpr int CH_STRIDE = T * COLS + 1;          // odd => conflict-free when lanes index channels
     __shared__ float slab[kChBlock * CH_STRIDE];
 
+    // ncb > 0: 1-D grid with the channel block as the FASTEST index — the blocks that write the eight 128-byte pieces of the
+    // same 1 KB row V[e][tile][0..IC) run at the same time, so DRAM sees whole rows instead of 128 B at a 1 KB stride
     const int segs = (g.tilesX + kSegTiles - 1) / kSegTiles;
-    const int seg = blockIdx.x % segs;
-    const int Rl = blockIdx.x / segs;  // chunk-local tile-row
+    const unsigned bx = ncb > 0 ? blockIdx.x / static_cast<unsigned>(ncb) : blockIdx.x;
+    const int seg = bx % segs;
+    const int Rl = bx / segs;  // chunk-local tile-row
     const int R = R0 + Rl;
     const int n = R / g.tilesY, ty = R - n * g.tilesY;
     const int tx0 = seg * kSegTiles;
-    const int c0 = blockIdx.y * kChBlock;
+    const int c0 = (ncb > 0 ? blockIdx.x % static_cast<unsigned>(ncb) : blockIdx.y) * kChBlock;
     const int gy0 = ty * OT - g.pad_top, gx0 = tx0 * OT - g.pad_left;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -274,7 +277,7 @@ wino_input_kernel(const float* __restrict__ in, float* __restrict__ V, WinoGeom 
 template <int T, bool POOL, bool MLP>
 __global__ void __launch_bounds__(kXformThreads)
 wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const float* __restrict__ bias, WinoGeom g,
-                   int R0, int Tc, int relu) {
+                   int R0, int Tc, int relu, int ncb) {
     using W = Wino<T>;
     constexpr int OT = W::kOut;
     constexpr int ST = POOL ? OT / 2 : OT;     // rows / columns of the tile as stored
@@ -283,12 +286,13 @@ wino_output_kernel(const float* __restrict__ M, float* __restrict__ out, const f
     __shared__ float slab[kChBlock * CH_STRIDE];
 
     const int segs = (g.tilesX + kSegTiles - 1) / kSegTiles;
-    const int seg = blockIdx.x % segs;
-    const int Rl = blockIdx.x / segs;
+    const unsigned bx = ncb > 0 ? blockIdx.x / static_cast<unsigned>(ncb) : blockIdx.x;  // ncb > 0: channel block fastest (see above)
+    const int seg = bx % segs;
+    const int Rl = bx / segs;
     const int R = R0 + Rl;
     const int n = R / g.tilesY, ty = R - n * g.tilesY;
     const int tx0 = seg * kSegTiles;
-    const int c0 = blockIdx.y * kChBlock;
+    const int c0 = (ncb > 0 ? blockIdx.x % static_cast<unsigned>(ncb) : blockIdx.y) * kChBlock;
 
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = tx0 + w, oc = c0 + lane;
@@ -400,17 +404,22 @@ int wino_input_transform(int tile, const float* in, float* V, const WinoGeom& g,
     const int segs = ceil_div(g.tilesX, kSegTiles);
     const int Tc = (R1 - R0) * g.tilesX;
     dim3 grid(static_cast<unsigned>(segs) * (R1 - R0), ceil_div(g.C_in, kChBlock));
+    int ncb = 0;
+    if (tune_get(TUNE_WINO_MLP) >= 2 && static_cast<unsigned long long>(grid.x) * grid.y < 0x7fffffffULL) {
+        ncb = static_cast<int>(grid.y);
+        grid = dim3(grid.x * grid.y, 1);
+    }
     // algorithmic bytes: the rows of the input the chunk covers, read once, + V written once
     const double imgs = static_cast<double>(R1 - R0) / g.tilesY;  // tile-rows of the chunk, in images
     const int prof = prof_begin(s, PROF_WINO_INPUT, 0, 0,
                                 4.0 * (imgs * g.C_in * g.H * g.W + static_cast<double>(tile) * tile * Tc * g.C_in));
     const bool mlp = tune_get(TUNE_WINO_MLP) != 0;
     if (tile == 8) {
-        if (mlp) wino_input_kernel<8, true><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
-        else wino_input_kernel<8, false><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
+        if (mlp) wino_input_kernel<8, true><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc, ncb);
+        else wino_input_kernel<8, false><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc, ncb);
     } else {
-        if (mlp) wino_input_kernel<4, true><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
-        else wino_input_kernel<4, false><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc);
+        if (mlp) wino_input_kernel<4, true><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc, ncb);
+        else wino_input_kernel<4, false><<<grid, kXformThreads, 0, s>>>(in, V, g, R0, Tc, ncb);
     }
     prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();
@@ -423,6 +432,11 @@ int wino_output_transform(int tile, const float* M, float* out, const float* bia
     const int segs = ceil_div(g.tilesX, kSegTiles);
     const int Tc = (R1 - R0) * g.tilesX;
     dim3 grid(static_cast<unsigned>(segs) * (R1 - R0), ceil_div(g.C_out, kChBlock));
+    int ncb = 0;
+    if (tune_get(TUNE_WINO_MLP) >= 2 && static_cast<unsigned long long>(grid.x) * grid.y < 0x7fffffffULL) {
+        ncb = static_cast<int>(grid.y);
+        grid = dim3(grid.x * grid.y, 1);
+    }
     const double imgs = static_cast<double>(R1 - R0) / g.tilesY;  // tile-rows of the chunk, in images
     const double out_px = pool ? static_cast<double>((g.OH + 1) / 2) * ((g.OW + 1) / 2) : static_cast<double>(g.OH) * g.OW;
     const int prof = prof_begin(s, PROF_WINO_OUTPUT, 0, 0,
@@ -430,15 +444,15 @@ int wino_output_transform(int tile, const float* M, float* out, const float* bia
     const bool mlp = tune_get(TUNE_WINO_MLP) != 0;
     if (tile == 8) {
         if (mlp) {
-            if (pool) wino_output_kernel<8, true, true><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
-            else wino_output_kernel<8, false, true><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+            if (pool) wino_output_kernel<8, true, true><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu, ncb);
+            else wino_output_kernel<8, false, true><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu, ncb);
         } else {
-            if (pool) wino_output_kernel<8, true, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
-            else wino_output_kernel<8, false, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+            if (pool) wino_output_kernel<8, true, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu, ncb);
+            else wino_output_kernel<8, false, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu, ncb);
         }
     } else {
-        if (pool) wino_output_kernel<4, true, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
-        else wino_output_kernel<4, false, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu);
+        if (pool) wino_output_kernel<4, true, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu, ncb);
+        else wino_output_kernel<4, false, false><<<grid, kXformThreads, 0, s>>>(M, out, bias, g, R0, Tc, relu, ncb);
     }
     prof_end(prof, s);
     FCUDA_CHECK_LAUNCH();

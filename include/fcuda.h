@@ -204,8 +204,9 @@ int fcuda_conv_forward_ext(const FcudaConvParam* param, int algo, float* output,
  *   gemm_tma_store (0-1, 1)   row-major TensorGEMM epilogue through shared memory + TMA stores
  *   igemm_tma_out (0-1, 1)    implicit-GEMM epilogue through shared memory + TMA stores (0: per-thread stores)
  *   igemm_pw (0-1, 1)         TMA-fed [32 channels][32 pixels] A boxes for 1x1 / stride-1 layers (0: generic gather)
- *   wino_mlp (0-1, 1)         Winograd transforms with every global load of a block in flight at once (cp.async slab /
- *                             back-to-back plane loads) instead of register-staged rounds
+ *   wino_mlp (0-2, 2)         Winograd transforms: 1 = every global load of a block in flight at once (cp.async slab /
+ *                             back-to-back plane loads) instead of register-staged rounds; 2 = also launch the channel
+ *                             blocks of a tile group next to each other (whole 1 KB rows of V / M in flight together)
  * Every variant computes the same result (tests/test_gpu_variants.py).  Returns 0 / the value, -200 for an unknown name or value. */
 int fcuda_set_tuning(const char* name, int value);
 int fcuda_get_tuning(const char* name);

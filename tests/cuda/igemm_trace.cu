@@ -1,5 +1,6 @@
 // Timeline of the implicit-GEMM conv's hand-offs (needs a B200; diagnostic, not a test).
-//   build: make -C feathercnn_b200/csrc igemm_trace      run: build/igemm_trace [IC OC HW batch]
+//   build: make -C feathercnn_b200/csrc igemm_trace      run: build/igemm_trace [IC OC HW batch [planes pool]]
+//   planes: 2 = 3xTF32 (default), 3 = BF16x3; pool: 1 = fused 2x2 max pooling epilogue
 // Compiles conv_igemm.cu with -DFCUDA_IGEMM_TRACE: CTA 0 records clock64() at every producer / MMA / epilogue hand-off
 // of its first 64 k-blocks; printed relative to the first event, one line per k-block.
 #include <cstdio>
@@ -16,6 +17,7 @@ using namespace fcuda;
 int main(int argc, char** argv) {
     const int IC = argc > 1 ? atoi(argv[1]) : 64, OC = argc > 2 ? atoi(argv[2]) : 64;
     const int HW = argc > 3 ? atoi(argv[3]) : 224, N = argc > 4 ? atoi(argv[4]) : 16;
+    const int planes = argc > 5 ? atoi(argv[5]) : 2, pool = argc > 6 ? atoi(argv[6]) : 0;
     const size_t nin = (size_t)N * IC * HW * HW, nout = (size_t)N * OC * HW * HW, nw = (size_t)OC * IC * 9;
     float *in, *out, *w, *whi, *wlo, *bias;
     CK(cudaMalloc(&in, nin * 4)); CK(cudaMalloc(&out, nout * 4)); CK(cudaMalloc(&w, nw * 4));
@@ -25,8 +27,9 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(in, h.data(), nin * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w, h.data(), nw * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(bias, 0, OC * 4));
-    if (conv_igemm_pack_weights(w, whi, wlo, OC, IC, 9, 0)) return 1;
-    IgemmProblem p{in, whi, wlo, bias, out, N, IC, HW, HW, OC, HW, HW, 3, 3, 1, 1, 1, 1, 2, 1};
+    if (conv_igemm_pack_weights(w, whi, wlo, OC, IC, 9, 0, planes == 3)) return 1;
+    IgemmProblem p{in, whi, wlo, bias, out, N, IC, HW, HW, OC, HW, HW, 3, 3, 1, 1, 1, 1, planes, 1};
+    p.pool = pool;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int i = 0; i < 2; ++i) if (conv_igemm_forward(p, 0)) return 1;
@@ -36,7 +39,8 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     const int kblocks = 9 * IC / 32;
-    printf("IC=%d OC=%d %dx%d batch %d: %.3f ms (trace build), %d k-blocks per tile\n", IC, OC, HW, HW, N, ms, kblocks);
+    printf("IC=%d OC=%d %dx%d batch %d planes %d pool %d: %.3f ms (trace build), %d k-blocks per tile\n", IC, OC, HW, HW, N, planes,
+           pool, ms, kblocks);
     std::vector<long long> t(16 * 64);
     if (igemm_trace_read(t.data())) return 1;
     long long t0 = t[0];
