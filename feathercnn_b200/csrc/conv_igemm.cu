@@ -122,6 +122,10 @@ struct IgemmArgs {
     int tma_out;             // epilogue stores through shared memory + TMA (tmOut is valid); pooled tiles keep direct stores
     int pool;                // SLAB only: fuse a following 2x2 / stride-2 max pooling; `out` is the pooled blob
     int2 ktab1[32];          // use_table == 2 (K <= 32, e.g. IC = 3 first layers): the k-table in the kernel parameters
+    const unsigned char* wbf;  // BF16x3: pre-tiled filter planes (see igemm_pack_weights_bf16_kernel)
+    unsigned wbf_plane_bytes;  // bytes of one plane: kblocks * ocpad * 64
+    unsigned wbf_kb_bytes;     // bytes of one k-block of one plane: ocpad * 64
+    unsigned desc_swap;      // debug: exchange the two byte offsets of the un-swizzled filter descriptor
     unsigned suspend_ns;     // suspend hint of the ring / slab / accumulator waits (0 = poll), see ptx::mbar_try_wait_ns
     int taps;                // KH*KW
     unsigned tap_inv;        // ceil(65536 / KW): tap / KW == (tap * tap_inv) >> 16 for tap < 64
@@ -281,6 +285,12 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t smem_addr) {
 __device__ __forceinline__ void sts_f32(uint32_t smem_addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_addr), "f"(v) : "memory");
 }
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ptx::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(ptx::smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // CG = 2: a CTA PAIR (thread-block cluster of 2, cta_group::2) works on 256 output pixels x BN channels: each CTA gathers /
@@ -428,8 +438,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     uint64_t* bar = (CG == 2 && cta_rank != 0) ? &bfull_bar[stage] : &full_bar[stage];
                     const int row0 = n_blk * BN + static_cast<int>(cta_rank) * kBRows;
                     ptx::mbar_arrive_expect_tx(bar, NPL * kBTile);
-                    ptx::tma_load_3d(st, &tmW, bar, kb * 32, row0, 0);
-                    if (NPL == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, bar, kb * 32, row0, 0);
+                    if (BF) {
+                        // BF16x3: the tile of a k-block is ONE contiguous run per plane in global memory, already in the
+                        // shared-memory (core-matrix) order -> two 1-D bulk copies of whole 128-byte lines.  As a tensor box it
+                        // was BN rows of 64 bytes = BN half-used L2 lines per plane, and the SM's L2 read port (~2.2 cycles per
+                        // line, tests/cuda/store_rate.cu) paced the whole kernel (profiles/r02s trace: the filter TMA of a
+                        // k-block issued ~3,000 cycles after its A tile was ready).
+                        const unsigned char* src = args.wbf + static_cast<size_t>(kb) * args.wbf_kb_bytes + static_cast<size_t>(row0) * 64;
+                        bulk_load_1d(st, src, kBTile, bar);
+                        bulk_load_1d(st + kBTile, src + args.wbf_plane_bytes, kBTile, bar);
+                    } else {
+                        ptx::tma_load_3d(st, &tmW, bar, kb * 32, row0, 0);
+                        if (NPL == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, bar, kb * 32, row0, 0);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -461,7 +482,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             }
         } else if (ptx::elect_one()) {
             constexpr uint32_t idesc = BF ? make_idesc_bf16(BN, 128) : make_idesc_tf32(BN, 128 * CG);
-            const uint64_t dB0 = BF ? make_smem_desc_sw64(ptx::smem_u32(smem)) : make_smem_desc_sw128(ptx::smem_u32(smem));
+            // BF16x3: un-swizzled core-matrix layout [row / 8][16-byte k chunk (4)][row % 8][8 bf16]: 128 bytes between the
+            // core matrices of consecutive k chunks (LBO), 512 bytes between 8-row groups (SBO)
+            const uint64_t dB0 = BF ? make_smem_desc_none(ptx::smem_u32(smem), args.desc_swap ? 512 : 128, args.desc_swap ? 128 : 512) : make_smem_desc_sw128(ptx::smem_u32(smem));
             const uint32_t me = static_cast<uint32_t>(warp - kWarpMma);
             const uint32_t nissue = static_cast<uint32_t>(args.issuers);
             uint32_t g = me;
@@ -493,9 +516,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {  // 16 k-values (8 TMEM columns of bf16 pairs / 32 smem bytes) per MMA
                         const uint32_t first = (first_visit && k == 0) ? 0u : 1u;
-                        umma_bf16_ts(tmem_d, ta + 16 + k * 8, dB + 2 * k, idesc, first);   // A_p2 * B_p1
-                        umma_bf16_ts(tmem_d, ta + k * 8, dBlo + 2 * k, idesc, 1u);         // A_p1 * B_p2
-                        umma_bf16_ts(tmem_d, ta + k * 8, dB + 2 * k, idesc, 1u);           // A_p1 * B_p1
+                        // a k-step of 16 = two 16-byte chunks = two core matrices = 256 bytes further
+                        umma_bf16_ts(tmem_d, ta + 16 + k * 8, dB + 16 * k, idesc, first);   // A_p2 * B_p1
+                        umma_bf16_ts(tmem_d, ta + k * 8, dBlo + 16 * k, idesc, 1u);         // A_p1 * B_p2
+                        umma_bf16_ts(tmem_d, ta + k * 8, dB + 16 * k, idesc, 1u);           // A_p1 * B_p1
                     }
                 }
 #pragma unroll
@@ -775,6 +799,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             }
         };
         // issue the 32 loads of the cursor's k-block
+        const uint32_t ktab_s = ptx::smem_u32(ktab);
         auto gather = [&](float (&x)[32]) {
             if (!args.use_table) {
                 // IC % 32 == 0: the whole k-block is one tap -> one predicate; the 32 channel addresses are
@@ -811,7 +836,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             } else {
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
-                    const int2 e = ktab[kb * 32 + r];
+                    int2 e;  // explicit ld.shared (the table pointer is generic to nvcc)
+                    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(ktab_s + static_cast<uint32_t>((kb * 32 + r) * 8)));
                     x[r] = ((tapmask >> e.y) & 1ull) ? __ldg(base + e.x) : 0.f;
                 }
             }
@@ -1086,23 +1112,29 @@ igemm_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, f
     }
 }
 
-// BF16x3: the same Wp[oc][Kf] order, two bf16 planes q1 = RN(w), q2 = RN(w - q1); Kf = K rounded up to 8 (16-byte rows)
+// BF16x3: two bf16 planes q1 = RN(w), q2 = RN(w - q1), PRE-TILED for the kernel's filter ring: plane p, k-block kb
+// (32 k-values, same k order as above) and output channel oc live at
+//     ((p * KB + kb) * OCpad + (oc / 8) * 8) * 32  +  (kk / 8) * 64 + (oc % 8) * 8 + kk % 8        (bf16 elements)
+// i.e. per k-block the rows of an N tile are one contiguous run of 8-row x 16-byte core matrices — the un-swizzled K-major
+// shared-memory layout of tcgen05 — so the kernel fetches a tile with one 1-D bulk copy per plane.  Rows >= OC and
+// k >= K are zeros; OCpad = OC rounded up to the N tile the dispatcher picks for this OC.
 __global__ void __launch_bounds__(256)
-igemm_pack_weights_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ q1, __nv_bfloat16* __restrict__ q2,
-                               int OC, int IC, int taps, int Kf) {
-    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const size_t total = static_cast<size_t>(OC) * Kf;
+igemm_pack_weights_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ q, int OC, int IC, int taps, int KB,
+                               int OCpad) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // over [kb][oc][kk]
+    const size_t total = static_cast<size_t>(KB) * OCpad * 32;
     if (idx >= total) return;
-    const int k = static_cast<int>(idx % Kf);
-    const int oc = static_cast<int>(idx / Kf);
+    const int kk = static_cast<int>(idx & 31);
+    const int oc = static_cast<int>((idx >> 5) % OCpad);
+    const int kb = static_cast<int>((idx >> 5) / OCpad);
+    const int k = kb * 32 + kk;
     float v = 0.f;
-    if (k < IC * taps) {
+    if (oc < OC && k < IC * taps) {
         int tap, ic;
         if (IC % 32 == 0) {
-            const int kb = k >> 5;
             const int cb = kb / taps;
             tap = kb - cb * taps;
-            ic = cb * 32 + (k & 31);
+            ic = cb * 32 + kk;
         } else {
             tap = k / IC;
             ic = k - tap * IC;
@@ -1110,9 +1142,14 @@ igemm_pack_weights_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __res
         v = w[(static_cast<size_t>(oc) * IC + ic) * taps + tap];
     }
     const __nv_bfloat16 a = __float2bfloat16_rn(v);
-    q1[idx] = a;
-    q2[idx] = __float2bfloat16_rn(v - __bfloat162float(a));
+    const size_t dst = (static_cast<size_t>(kb) * OCpad + (oc & ~7)) * 32 + (kk >> 3) * 64 + (oc & 7) * 8 + (kk & 7);
+    q[dst] = a;
+    q[dst + total] = __float2bfloat16_rn(v - __bfloat162float(a));
 }
+
+// N tile the dispatcher uses for a layer with OC output channels (dispatch_igemm) and the padded row count of the tiled planes
+static int igemm_bn_for(int OC) { return OC <= 32 ? 32 : OC <= 64 ? 64 : 128; }
+static int igemm_ocpad(int OC) { const int bn = igemm_bn_for(OC); return (OC + bn - 1) / bn * bn; }
 
 template <int BN, int PLANES, int SK, int CG>
 int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
@@ -1127,7 +1164,7 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     constexpr int NPL = BF ? 2 : PLANES;
     constexpr int kElt = BF ? 2 : 4;
     const int Kf = BF ? (K + 7) & ~7 : (K + 3) & ~3;
-    for (int pl = 0; pl < NPL; ++pl) {
+    for (int pl = 0; pl < (BF ? 0 : NPL); ++pl) {
         cuuint64_t dims[3] = {(cuuint64_t)Kf, (cuuint64_t)p.OC, 1};
         cuuint64_t strides[2] = {(cuuint64_t)Kf * kElt, (cuuint64_t)Kf * p.OC * kElt};
         cuuint32_t box[3] = {32, (cuuint32_t)(BN / CG), 1};  // CG = 2: each CTA of the pair fetches half of the N tile
@@ -1142,8 +1179,16 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
             return FCUDA_ERR_CUDA;
         }
     }
+    if (BF) {  // no tensor map: the planes are pre-tiled, fetched by 1-D bulk copies
+        memset(&tmW, 0, sizeof(tmW));
+        tmWlo = tmW;
+    }
     if (NPL == 1) tmWlo = tmW;
     IgemmArgs a;
+    a.wbf = reinterpret_cast<const unsigned char*>(p.w_hi);
+    a.wbf_kb_bytes = static_cast<unsigned>(igemm_ocpad(p.OC)) * 64u;
+    a.wbf_plane_bytes = static_cast<unsigned>(ceil_div(K, 32)) * a.wbf_kb_bytes;
+    if (BF && (igemm_bn_for(p.OC) != BN || static_cast<unsigned long long>(ceil_div(K, 32)) * igemm_ocpad(p.OC) * 64ull >= (1ull << 31))) return -1;
     a.in = p.input; a.out = p.output; a.bias = p.bias; a.residual = p.residual;
     a.N = p.N; a.IC = p.IC; a.H = p.H; a.W = p.W; a.OC = p.OC; a.OH = p.OH; a.OW = p.OW;
     a.KH = p.KH; a.KW = p.KW; a.pad_top = p.pad_top; a.pad_left = p.pad_left;
@@ -1173,6 +1218,10 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
         return -1;
     a.relu = p.relu;
     a.suspend_ns = static_cast<unsigned>(tune_get(TUNE_MBAR_SUSPEND_NS));
+    {
+        static const int swap = getenv("FCUDA_DEBUG_DESC_SWAP") ? atoi(getenv("FCUDA_DEBUG_DESC_SWAP")) : 0;
+        a.desc_swap = static_cast<unsigned>(swap);
+    }
     // two issuers (one accumulator each) where one thread cannot keep the pipe fed: N <= 64 and at least four k-blocks
     // per tile (short-K tiles are epilogue-bound and would only pay the second accumulator read); BN = 128 has 768 cycles of MMA work per k-block against ~350 of issue work, and only 256 accumulator
     // columns.  FCUDA_IGEMM_ISSUERS=1 forces one issuer (diagnostic).
@@ -1292,16 +1341,19 @@ bool conv_igemm_supported(int IC, int KH, int KW) {
 }
 
 size_t conv_igemm_packed_floats(int OC, int IC, int taps, int planes) {
-    return static_cast<size_t>(planes) * OC * ((taps * IC + 3) & ~3);
+    const size_t rows = static_cast<size_t>(planes) * OC * ((taps * IC + 3) & ~3);
+    if (planes < 2) return rows;
+    // the pre-tiled BF16x3 planes (2 planes x k-blocks x OCpad x 64 bytes) must fit the same buffer
+    const size_t tiled = (2 * static_cast<size_t>(ceil_div(taps * IC, 32)) * igemm_ocpad(OC) * 64 + 3) / 4;
+    return rows > tiled ? rows : tiled;
 }
 
 int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, int IC, int taps, cudaStream_t s, int bf16x3) {
     if (bf16x3) {
-        if (!w_lo) return -100;
-        const int Kf8 = (taps * IC + 7) & ~7;
-        const size_t total8 = static_cast<size_t>(OC) * Kf8;
+        const int KB = ceil_div(taps * IC, 32), OCpad = igemm_ocpad(OC);
+        const size_t total8 = static_cast<size_t>(KB) * OCpad * 32;
         igemm_pack_weights_bf16_kernel<<<static_cast<unsigned>(ceil_div_sz(total8, 256)), 256, 0, s>>>(
-            w, reinterpret_cast<__nv_bfloat16*>(w_hi), reinterpret_cast<__nv_bfloat16*>(w_lo), OC, IC, taps, Kf8);
+            w, reinterpret_cast<__nv_bfloat16*>(w_hi), OC, IC, taps, KB, OCpad);
         FCUDA_CHECK_LAUNCH();
         count_launch();
         return 0;

@@ -300,8 +300,9 @@ int fcuda_conv_init(const FcudaConvParam* p, int algo, float* packed, const floa
             const int G = p->group > 0 ? p->group : 1;
             const int ICg = IC / G, OCg = OC / G;
             const size_t plane = conv_igemm_packed_floats(OCg, ICg, taps, 1);
+            const size_t group_stride = conv_igemm_packed_floats(OCg, ICg, taps, pl.np);  // (the BF16x3 planes are pre-tiled and padded)
             for (int g = 0; g < G && rc == 0; ++g) {  // per group: [hi plane][lo plane] of Wp[OCg][Kf]
-                float* dst = packed + static_cast<size_t>(g) * pl.np * plane;
+                float* dst = packed + static_cast<size_t>(g) * group_stride;
                 rc = conv_igemm_pack_weights(d_raw + static_cast<size_t>(g) * OCg * ICg * taps, dst,
                                              pl.np == 2 ? dst + plane : nullptr, OCg, ICg, taps, s, igemm_planes() == 3);
             }
@@ -419,11 +420,12 @@ static int conv_forward_impl(const FcudaConvParam* p, int algo, float* output, c
             const int G = p->group > 0 ? p->group : 1;
             const int ICg = IC / G, OCg = OC / G;
             const size_t wplane = conv_igemm_packed_floats(OCg, ICg, taps, 1);
+            const size_t wgroup = conv_igemm_packed_floats(OCg, ICg, taps, pl.np);
             const size_t in_plane = static_cast<size_t>(p->input_h) * p->input_w;
             const size_t out_plane = static_cast<size_t>(p->output_h) * p->output_w;
             for (int gi = 0; gi < G; ++gi) {  // one launch per group on channel slices (G == 1: the whole tensor)
                 IgemmProblem g{};
-                const float* wg = packed + static_cast<size_t>(gi) * pl.np * wplane;
+                const float* wg = packed + static_cast<size_t>(gi) * wgroup;
                 g.input = input + static_cast<size_t>(gi) * ICg * in_plane;
                 g.w_hi = wg;
                 g.w_lo = pl.np == 2 ? wg + wplane : nullptr;

@@ -345,6 +345,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
     return d;
 }
 
+// Un-swizzled K-major tile: 8-row x 16-byte core matrices of 128 contiguous bytes; lbo = bytes between the core matrices of
+// consecutive 16-byte k chunks, sbo = bytes between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t make_smem_desc_none(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
+
 // Instruction descriptor: D=f32, A=B=tf32, both K-major, M = 128 (256 with cta_group::2), N=BN.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int bn, int m = 128) {
     return (1u << 4)                               // c_format = F32
