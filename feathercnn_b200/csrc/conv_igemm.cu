@@ -123,8 +123,7 @@ struct IgemmArgs {
     int pool;                // SLAB only: fuse a following 2x2 / stride-2 max pooling; `out` is the pooled blob
     int2 ktab1[32];          // use_table == 2 (K <= 32, e.g. IC = 3 first layers): the k-table in the kernel parameters
     const unsigned char* wbf;  // BF16x3: pre-tiled filter planes (see igemm_pack_weights_bf16_kernel)
-    unsigned wbf_plane_bytes;  // bytes of one plane: kblocks * ocpad * 64
-    unsigned wbf_kb_bytes;     // bytes of one k-block of one plane: ocpad * 64
+    unsigned wbf_kb_bytes;     // bytes of one k-block (both planes, every N tile): 2 * ocpad * 64
     unsigned desc_swap;      // debug: exchange the two byte offsets of the un-swizzled filter descriptor
     unsigned suspend_ns;     // suspend hint of the ring / slab / accumulator waits (0 = poll), see ptx::mbar_try_wait_ns
     int taps;                // KH*KW
@@ -421,39 +420,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
     if (warp == kWarpTma) {
         // ===================== TMA producer for the filter tiles =====================
-        const bool leader = ptx::elect_one();
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t gb = 0;
-        for (long long tile = tile_first; tile < total_tiles; tile += tile_step) {
-            const uint32_t pt = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
-            const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - pt * static_cast<uint32_t>(args.num_n));
-            for (int kb = 0; kb < kblocks; ++kb, ++gb) {
+        // One thread can start a TMA operation only every ~280 cycles (tests/cuda/store_rate.cu: 276 cycles per bulk copy and
+        // issuing thread whatever its size, throughput scaling with the number of issuing threads), and the slot wait, the
+        // expect_tx arrive and the copy are a chain of long-latency SYNCS / UTMA instructions: ~560 cycles per k-block when
+        // ONE thread walked the k-blocks (igemm trace r02v) — that chain, not the tensor pipe or any bandwidth, paced every
+        // implicit-GEMM layer (VGG conv1_2 took 1.04-1.10 ms whatever the MMA mode, ring depth or filter layout was).
+        // So kTmaLanes lanes of this warp each take every kTmaLanes-th k-block and run the chain in lockstep: one
+        // instruction issue starts kTmaLanes copies.  (Lane j of a round needs the slot k-block g+j-STAGES used, whose filters
+        // were requested one or two rounds earlier: no cycle as long as kTmaLanes <= STAGES.)
+        constexpr int kTmaLanes = 4;
+        static_assert(kTmaLanes <= STAGES, "a round must not wait for its own copies");
+        if (lane < kTmaLanes) {
+            long long tile = tile_first;
+            int kb = lane;
+            uint32_t gb = static_cast<uint32_t>(lane);
+            for (;;) {
+                while (kb >= kblocks && tile < total_tiles) { kb -= kblocks; tile += tile_step; }
+                if (tile >= total_tiles) break;
+                const uint32_t pt = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+                const int n_blk = static_cast<int>(static_cast<uint32_t>(tile) - pt * static_cast<uint32_t>(args.num_n));
+                const int stage = static_cast<int>(gb & (STAGES - 1));
+                if (lane == 0) IG_TRACE_T(11, gb);
                 wait_ring_slot_free<STAGES>(empty_bar, gb, args.suspend_ns);
-                IG_TRACE(8, gb);
-                if (leader) {
-                    uint8_t* st = smem + stage * kStage;
-                    // CG = 2: rows [rank * BN/2, (rank+1) * BN/2) of the N tile; the peer CTA's copy completes on ITS bfull
-                    // barrier, which its relay warp forwards to the leader CTA's full barrier
-                    uint64_t* bar = (CG == 2 && cta_rank != 0) ? &bfull_bar[stage] : &full_bar[stage];
-                    const int row0 = n_blk * BN + static_cast<int>(cta_rank) * kBRows;
-                    ptx::mbar_arrive_expect_tx(bar, NPL * kBTile);
-                    if (BF) {
-                        // BF16x3: the tile of a k-block is ONE contiguous run per plane in global memory, already in the
-                        // shared-memory (core-matrix) order -> two 1-D bulk copies of whole 128-byte lines.  As a tensor box it
-                        // was BN rows of 64 bytes = BN half-used L2 lines per plane, and the SM's L2 read port (~2.2 cycles per
-                        // line, tests/cuda/store_rate.cu) paced the whole kernel (profiles/r02s trace: the filter TMA of a
-                        // k-block issued ~3,000 cycles after its A tile was ready).
-                        const unsigned char* src = args.wbf + static_cast<size_t>(kb) * args.wbf_kb_bytes + static_cast<size_t>(row0) * 64;
-                        bulk_load_1d(st, src, kBTile, bar);
-                        bulk_load_1d(st + kBTile, src + args.wbf_plane_bytes, kBTile, bar);
-                    } else {
-                        ptx::tma_load_3d(st, &tmW, bar, kb * 32, row0, 0);
-                        if (NPL == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, bar, kb * 32, row0, 0);
-                    }
+                if (lane == 0) IG_TRACE_T(8, gb);
+                uint8_t* st = smem + stage * kStage;
+                // CG = 2: rows [rank * BN/2, (rank+1) * BN/2) of the N tile; the peer CTA's copy completes on ITS bfull
+                // barrier, which its relay warp forwards to the leader CTA's full barrier
+                uint64_t* bar = (CG == 2 && cta_rank != 0) ? &bfull_bar[stage] : &full_bar[stage];
+                const int row0 = n_blk * BN + static_cast<int>(cta_rank) * kBRows;
+                ptx::mbar_arrive_expect_tx(bar, NPL * kBTile);
+                if (BF) {
+                    // BF16x3: [k-block][N tile][plane][BN rows x 64 B] in global memory, already in the shared-memory
+                    // (core-matrix) order: both planes of the tile are ONE run of whole 128-byte lines -> one 1-D bulk copy
+                    // (as a tensor box it was BN rows of 64 bytes per plane: half-used L2 lines, two operations)
+                    const unsigned char* src = args.wbf + static_cast<size_t>(kb) * args.wbf_kb_bytes + static_cast<size_t>(n_blk) * (2 * kBTile);
+                    bulk_load_1d(st, src, 2 * kBTile, bar);
+                } else {
+                    ptx::tma_load_3d(st, &tmW, bar, kb * 32, row0, 0);
+                    if (NPL == 2) ptx::tma_load_3d(st + kBTile, &tmWlo, bar, kb * 32, row0, 0);
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (lane == 0) IG_TRACE_T(12, gb);
+                gb += kTmaLanes;
+                kb += kTmaLanes;
             }
         }
     } else if (warp >= kWarpMma && warp < kWarpSlab) {
@@ -1112,15 +1120,14 @@ igemm_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, f
     }
 }
 
-// BF16x3: two bf16 planes q1 = RN(w), q2 = RN(w - q1), PRE-TILED for the kernel's filter ring: plane p, k-block kb
-// (32 k-values, same k order as above) and output channel oc live at
-//     ((p * KB + kb) * OCpad + (oc / 8) * 8) * 32  +  (kk / 8) * 64 + (oc % 8) * 8 + kk % 8        (bf16 elements)
-// i.e. per k-block the rows of an N tile are one contiguous run of 8-row x 16-byte core matrices — the un-swizzled K-major
-// shared-memory layout of tcgen05 — so the kernel fetches a tile with one 1-D bulk copy per plane.  Rows >= OC and
-// k >= K are zeros; OCpad = OC rounded up to the N tile the dispatcher picks for this OC.
+// BF16x3: two bf16 planes q1 = RN(w), q2 = RN(w - q1), PRE-TILED for the kernel's filter ring, ordered
+//     [k-block kb (32 k-values, same k order as above)][N tile nb (BN rows)][plane][row / 8][16-byte k chunk (4)][row % 8][8 bf16]
+// i.e. per (k-block, N tile) both planes are ONE contiguous run of 8-row x 16-byte core matrices — the un-swizzled K-major
+// shared-memory layout of tcgen05 — so the kernel fetches a ring stage with one 1-D bulk copy.  Rows >= OC and k >= K are
+// zeros; BN = the N tile the dispatcher picks for this OC, OCpad = OC rounded up to it.
 __global__ void __launch_bounds__(256)
 igemm_pack_weights_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ q, int OC, int IC, int taps, int KB,
-                               int OCpad) {
+                               int OCpad, int BN) {
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // over [kb][oc][kk]
     const size_t total = static_cast<size_t>(KB) * OCpad * 32;
     if (idx >= total) return;
@@ -1142,9 +1149,11 @@ igemm_pack_weights_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __res
         v = w[(static_cast<size_t>(oc) * IC + ic) * taps + tap];
     }
     const __nv_bfloat16 a = __float2bfloat16_rn(v);
-    const size_t dst = (static_cast<size_t>(kb) * OCpad + (oc & ~7)) * 32 + (kk >> 3) * 64 + (oc & 7) * 8 + (kk & 7);
+    const int nb = oc / BN, r = oc - nb * BN;
+    const size_t tile = (static_cast<size_t>(kb) * (OCpad / BN) + nb) * 2 * BN * 32;  // elements before this (k-block, N tile)
+    const size_t dst = tile + static_cast<size_t>(r & ~7) * 32 + (kk >> 3) * 64 + (r & 7) * 8 + (kk & 7);
     q[dst] = a;
-    q[dst + total] = __float2bfloat16_rn(v - __bfloat162float(a));
+    q[dst + static_cast<size_t>(BN) * 32] = __float2bfloat16_rn(v - __bfloat162float(a));
 }
 
 // N tile the dispatcher uses for a layer with OC output channels (dispatch_igemm) and the padded row count of the tiled planes
@@ -1186,9 +1195,8 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     if (NPL == 1) tmWlo = tmW;
     IgemmArgs a;
     a.wbf = reinterpret_cast<const unsigned char*>(p.w_hi);
-    a.wbf_kb_bytes = static_cast<unsigned>(igemm_ocpad(p.OC)) * 64u;
-    a.wbf_plane_bytes = static_cast<unsigned>(ceil_div(K, 32)) * a.wbf_kb_bytes;
-    if (BF && (igemm_bn_for(p.OC) != BN || static_cast<unsigned long long>(ceil_div(K, 32)) * igemm_ocpad(p.OC) * 64ull >= (1ull << 31))) return -1;
+    a.wbf_kb_bytes = 2u * static_cast<unsigned>(igemm_ocpad(p.OC)) * 64u;
+    if (BF && (igemm_bn_for(p.OC) != BN || static_cast<unsigned long long>(ceil_div(K, 32)) * igemm_ocpad(p.OC) * 128ull >= (1ull << 31))) return -1;
     a.in = p.input; a.out = p.output; a.bias = p.bias; a.residual = p.residual;
     a.N = p.N; a.IC = p.IC; a.H = p.H; a.W = p.W; a.OC = p.OC; a.OH = p.OH; a.OW = p.OW;
     a.KH = p.KH; a.KW = p.KW; a.pad_top = p.pad_top; a.pad_left = p.pad_left;
@@ -1353,7 +1361,7 @@ int conv_igemm_pack_weights(const float* w, float* w_hi, float* w_lo, int OC, in
         const int KB = ceil_div(taps * IC, 32), OCpad = igemm_ocpad(OC);
         const size_t total8 = static_cast<size_t>(KB) * OCpad * 32;
         igemm_pack_weights_bf16_kernel<<<static_cast<unsigned>(ceil_div_sz(total8, 256)), 256, 0, s>>>(
-            w, reinterpret_cast<__nv_bfloat16*>(w_hi), OC, IC, taps, KB, OCpad);
+            w, reinterpret_cast<__nv_bfloat16*>(w_hi), OC, IC, taps, KB, OCpad, igemm_bn_for(OC));
         FCUDA_CHECK_LAUNCH();
         count_launch();
         return 0;

@@ -384,8 +384,48 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t tmem_base = tmem_base_smem;
     const uint32_t tmem_a0 = tmem_base + kAccCols;
 
-    if (warp == 0) {
+    if (warp == 0 && CL == 1) {
         // ===================== TMA producer =====================
+        // A thread can start a TMA operation only every ~280 cycles and the slot wait -> expect_tx -> three loads of a k-block are
+        // a chain of long-latency instructions: ~700 cycles per k-block when one thread walked them, against 768 cycles of
+        // MMAs at N = 128 — the reason this kernel sat at 60-72 % tensor pipe (tests/cuda/store_rate.cu, igemm trace r02v).
+        // Now kKG k-blocks x 3 operands are issued in lockstep by 3 * kKG lanes: lane = group * 3 + operand, group j takes
+        // every kKG-th k-block of this CTA's k-block sequence; one instruction issue starts 3 * kKG loads.
+        constexpr int kKG = 2;
+        static_assert(kKG <= STAGES, "a round must not wait for its own loads");
+        if (lane < 3 * kKG) {
+            const int grp = lane / 3, op = lane - grp * 3;
+            const CUtensorMap* map = op == 0 ? &tmA : op == 1 ? &tmB : &tmBlo;
+            const uint32_t dst_off = op == 0 ? 0u : op == 1 ? static_cast<uint32_t>(kATile) : static_cast<uint32_t>(kATile + kBTile);
+            int tile = t_first;
+            int kb_off = grp;                          // offset inside the current tile's k range
+            uint32_t gi = static_cast<uint32_t>(grp);  // running k-block index of this CTA
+            int dec_tile = -1, g = 0, row = 0, kb0 = 0, nk = 0;
+            while (tile < total_tiles) {
+                if (tile != dec_tile) {
+                    const int ks = tile / (tiles_per_g * args.G);
+                    const int rem = tile - ks * (tiles_per_g * args.G);
+                    g = rem / tiles_per_g;
+                    const int mn = rem - g * tiles_per_g;
+                    const int m_grp = mn / args.num_n;
+                    const int n_blk = mn - m_grp * args.num_n;
+                    row = op == 0 ? m_grp * kBM : n_blk * BN;   // CL == 1: m_blk == m_grp
+                    kb0 = ks * kb_per_split;
+                    nk = min(kb0 + kb_per_split, args.k_blocks_total) - kb0;
+                    dec_tile = tile;
+                }
+                if (kb_off >= nk) { kb_off -= nk; tile += t_step; continue; }
+                const int stage = static_cast<int>(gi % STAGES);
+                const uint32_t phase = (gi / STAGES) & 1u;
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1, args.suspend_ns);
+                if (op == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], kStage);  // A + B_hi + B_lo
+                ptx::tma_load_3d(smem + stage * kStage + dst_off, map, &full_bar[stage], (kb0 + kb_off) * kBK, row, g);
+                gi += kKG;
+                kb_off += kKG;
+            }
+        }
+    } else if (warp == 0) {
+        // ===================== TMA producer, cluster-multicast variant =====================
         const bool leader = ptx::elect_one();
         int stage = 0;
         uint32_t phase = 0;

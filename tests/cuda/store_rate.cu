@@ -133,6 +133,50 @@ __global__ void __launch_bounds__(128, 1) tma_load_kernel(const __grid_constant_
     }
 }
 
+// Small 1-D bulk copies from an L2-resident buffer (the implicit GEMM's filter tiles): `issuers` threads (one per warp) each
+// stream `copies` copies of `bytes` into their own ring of `ring` stages.  Cycles per copy -> per-instruction cost of the TMA unit.
+__global__ void __launch_bounds__(128, 1) bulk_copy_kernel(const unsigned char* src, int src_bytes, int bytes, int ring, int issuers,
+                                                           int copies, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar[4][16];
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < 4; ++w)
+            for (int i = 0; i < 16; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[w][i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) != 0 || warp >= issuers) return;
+    uint8_t* my = smem + warp * ring * bytes;
+    const long long t0 = clock64();
+    for (int it = 0; it < copies; ++it) {
+        const int st = it % ring;
+        if (it >= ring) {
+            const uint32_t parity = ((it / ring) - 1) & 1u;
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_u32(&bar[warp][st])), "r"(parity) : "memory");
+        }
+        const unsigned char* g = src + ((static_cast<unsigned>(it * 4 + warp + blockIdx.x * 7) * 4096u) & static_cast<unsigned>(src_bytes / 2 - 1));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[warp][st])), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(my + st * bytes)), "l"(g), "r"(bytes), "r"(smem_u32(&bar[warp][st]))
+                     : "memory");
+    }
+    for (int k = 0; k < ring && k < copies; ++k) {
+        const int j = copies - 1 - k;
+        const int st = j % ring;
+        const uint32_t parity = (j / ring) & 1u;
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(smem_u32(&bar[warp][st])), "r"(parity) : "memory");
+    }
+    if (blockIdx.x == 0 && warp == 0) *out = clock64() - t0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -188,6 +232,30 @@ int main() {
         }
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         report(mode == 0 ? "tma 32ch x 32px (4 KB)" : mode == 1 ? "tma 64ch x 32px (8 KB)" : "tma 64ch x 128px (32KB)", ms);
+    }
+    // ---- small bulk copies from L2
+    {
+        unsigned char* src;
+        const int src_bytes = 1 << 20;
+        CK(cudaMalloc(&src, src_bytes));
+        CK(cudaMemset(src, 1, src_bytes));
+        long long* d_out;
+        CK(cudaMalloc(&d_out, 8));
+        CK(cudaFuncSetAttribute(bulk_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (int bytes : {2048, 4096, 8192, 16384})
+            for (int issuers : {1, 2, 4})
+                for (int ring : {2, 8}) {
+                    if (issuers * ring * bytes > 196 * 1024 || ring > 16) continue;
+                    const int copies = 2000;
+                    for (int rep = 0; rep < 2; ++rep) {
+                        bulk_copy_kernel<<<148, 128, 200 * 1024>>>(src, src_bytes, bytes, ring, issuers, copies, d_out);
+                        CK(cudaDeviceSynchronize());
+                    }
+                    long long c;
+                    CK(cudaMemcpy(&c, d_out, 8, cudaMemcpyDeviceToHost));
+                    printf("bulk copy %5d B x %d issuers, ring %d: %7.1f cycles per copy per issuer, %6.1f B/clk/SM\n", bytes, issuers, ring,
+                           static_cast<double>(c) / copies, static_cast<double>(bytes) * issuers * copies / c);
+                }
     }
     // ---- TMA loads of slab-shaped boxes
     CK(cudaFuncSetAttribute(tma_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 49152 + 1024));
