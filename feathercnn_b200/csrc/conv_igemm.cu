@@ -224,6 +224,16 @@ __device__ __forceinline__ void wait_ring_slot_free(uint64_t (*empty_bar)[STAGES
     }
 }
 
+// Non-blocking look at the same condition: lets a role ask about its NEXT k-block before it starts the work of the current
+// one, so the ~200-cycle latency of the barrier probe (SYNCS.PHASECHK) hides under that work instead of heading the next
+// iteration's dependency chain.
+template <int STAGES>
+__device__ __forceinline__ bool probe_ring_slot_free(uint64_t (*empty_bar)[STAGES], uint32_t g) {
+    if (g < STAGES) return true;
+    const uint32_t gg = g - STAGES;
+    return ptx::mbar_test(ring_release_bar<STAGES>(empty_bar, gg), ((gg / STAGES) >> 1) & 1u);
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -499,6 +509,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             long long tile = tile_first;
             int kb = static_cast<int>(me);
             uint32_t it = 0;
+            bool next_full = false;  // full_bar of this thread's next k-block already seen complete (probed during the MMAs)
             if (me >= nissue) tile = total_tiles;  // single-issuer launch: the second issuer idles
             for (;;) {
                 while (kb >= kblocks && tile < total_tiles) { kb -= kblocks; tile += tile_step; ++it; }
@@ -511,15 +522,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 const uint64_t dBlo = dB + static_cast<uint64_t>(kBTile >> 4);
                 const uint32_t ta = tmem_a0 + stage * kAStageCols;
                 const bool first_visit = kb < static_cast<int>(nissue);  // this thread's first k-block of the tile
+                IG_TRACE_T(6, g);
                 if (CG == 1) {
                     if (first_visit) ptx::mbar_wait(&tmem_empty_bar[as], ((it / static_cast<uint32_t>(args.acc_slots)) & 1u) ^ 1u, args.suspend_ns);
-                    ptx::mbar_wait(&full_bar[stage], phase, args.suspend_ns);
+                    if (!next_full) ptx::mbar_wait(&full_bar[stage], phase, args.suspend_ns);
                 } else {  // arrivals from the peer CTA: acquire at cluster scope
                     if (first_visit) ptx::mbar_wait_cluster(&tmem_empty_bar[as], ((it / static_cast<uint32_t>(args.acc_slots)) & 1u) ^ 1u);
                     ptx::mbar_wait_cluster(&full_bar[stage], phase);
                 }
                 IG_TRACE_T(5, g);
                 ptx::tc_fence_after();
+                if (CG == 1) {  // my next k-block's operands: asked now, looked at after the MMAs below are issued
+                    const uint32_t gn = g + nissue;
+                    next_full = ptx::mbar_test(&full_bar[gn & (STAGES - 1)], (gn / STAGES) & 1u);
+                }
                 if (BF) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {  // 16 k-values (8 TMEM columns of bf16 pairs / 32 smem bytes) per MMA
@@ -551,6 +567,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         }
                     }
                 }
+                IG_TRACE_T(14, g);
                 if (CG == 1) {
                     ptx::umma_commit(ring_release_bar<STAGES>(empty_bar, g));
                     if (kb + static_cast<int>(nissue) >= kblocks) ptx::umma_commit(&tmem_full_bar[as]);  // my last k-block here
@@ -631,6 +648,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // this lane's pixel inside the patch (2 x 16 sub-patch per warp) and its first slab element for tap row 0
         const int lane_off = (patch_row(q, lane) * kSlabCols + patch_col(q, lane) + group - args.pad_left + kSlabShift) * 4;
         uint32_t j = 0;  // running item index of this CTA; its k-blocks are 9j .. 9j+8
+        bool slot_free = false;  // ring slot of this warp's next k-block already seen released (probed one k-block ahead)
         for (long long tile = tile_first; tile < total_tiles; tile += tile_step) {
             for (int cb = 0; cb < cblocks; ++cb, ++j) {
                 const uint32_t st = j % SST;
@@ -643,8 +661,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
                     const uint32_t src = tb + static_cast<uint32_t>(u * (kSlabCols * 4));
                     if (q == 0) IG_TRACE(0, g);
-                    wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
+                    if (!slot_free) wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
                     if (q == 0) IG_TRACE(1, g);
+                    // this warp's next k-block: 3 further on inside the item, else the first one of the next item
+                    slot_free = probe_ring_slot_free<STAGES>(empty_bar, u < 2 ? g + 3u : (j + 1u) * 9u + static_cast<uint32_t>(group));
                     ptx::tc_fence_after();
                     if (BF) {
 #pragma unroll
@@ -675,6 +695,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     if (q == 0) IG_TRACE(2, g);
                     tmem_st_wait();
                     if (q == 0) IG_TRACE(4, g);
+                    if (q == 3) IG_TRACE(3, g);
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -697,13 +718,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         long long my_tiles = 0;
         if (tile_first < total_tiles) my_tiles = (total_tiles - tile_first + tile_step - 1) / tile_step;
         const uint32_t total_g = static_cast<uint32_t>(my_tiles) * static_cast<uint32_t>(kblocks);
+        bool slot_free = false;
         for (uint32_t g = static_cast<uint32_t>(group); g < total_g; g += kGroups) {
             const uint32_t st = g % SST;
             const int my_stage = static_cast<int>(g & (STAGES - 1));
             const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
             const uint32_t src = ptx::smem_u32(slab0 + st * kPwStageBytes + q * kPwBoxBytes) + static_cast<uint32_t>(lane * 4);
             ptx::mbar_wait(&slab_full[st], (g / SST) & 1u, args.suspend_ns);
-            wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
+            if (!slot_free) wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
+            slot_free = probe_ring_slot_free<STAGES>(empty_bar, g + kGroups);
             ptx::tc_fence_after();
             if (BF) {
 #pragma unroll

@@ -51,6 +51,11 @@ int main(int argc, char** argv) {
         printf("%3d  %d  | %10lld %9lld %10lld %14lld %8lld | %9lld %7lld(%lld) %7lld | %8lld | %lld\n", g, g % 3, r(0), r(1), r(2),
                r(3), r(4), r(5), r(6), 0LL, r(7), r(8), g ? r(5) - (t[5 * 64 + g - 1] - t0) : 0LL);
     }
+    printf("  g | M: loop_top  full_ok  mma_issued  committed | P(q3) st_done\n");
+    for (int g = 24; g < 44; ++g) {
+        auto r = [&](int slot) { return t[slot * 64 + g] ? (long long)(t[slot * 64 + g] - t0) : -1LL; };
+        printf("%3d | %10lld %10lld %10lld %10lld | %10lld\n", g, r(6), r(5), r(14), r(7), r(3));
+    }
     printf("  g | T: loop_top  slot_free  copy_issued  after_syncwarp\n");
     for (int g = 24; g < 44; ++g) {
         auto r = [&](int slot) { return t[slot * 64 + g] ? (long long)(t[slot * 64 + g] - t0) : -1LL; };
