@@ -1020,24 +1020,44 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     // The bias comes in ahead of the stores, 16 channels at a time: read through a generic pointer next to its
                     // store (round 2 until r02r) every channel paid a full generic-load latency behind the previous store —
                     // ~10k cycles per tile, the whole pooled layer was paced by this loop (ncu source page r02r).
-                    const bool writer = ok && (lane & 17) == 0;
+                    // Through shared memory instead of shuffles: the chunk is laid out [channel][pixel] (lane = pixel, 16-byte
+                    // pieces XOR-swizzled by the channel: conflict-free both ways), then lane c owns CHANNEL c: eight LDS.128
+                    // bring its 2 x 16 pixels, the four window members of a pooled pixel sit in its own registers, and the 8
+                    // pooled values leave as two 16-byte stores.  ~90 instructions per lane and chunk instead of ~230 (two
+                    // shuffles + a 4-byte store of 8 active lanes per channel): the pooled layers were epilogue-bound
+                    // (igemm trace r02x: 7.5k cycles per 128 x 64 tile against 3.5k cycles of MMAs).
+                    uint8_t* stg = stage_out + (q * kOutBufs) * 4096;
+                    const uint32_t sbase = ptx::smem_u32(stg);
+                    __syncwarp();  // the previous chunk's reads of this tile are done
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float bb[16];
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = ok ? __uint_as_float(r[j]) + res[j] : -INFINITY;
+                        sts_f32(sbase + static_cast<uint32_t>(j * 128 + ((((lane >> 2) ^ (j & 7)) << 4) | ((lane & 3) << 2))), v);
+                    }
+                    __syncwarp();
+                    float v[32];  // channel `lane`: v[0..15] = row 0, v[16..31] = row 1 of the 2 x 16 sub-patch
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 bv = lds_f32x4(b4 + 64 * h + 16 * i);
-                            bb[4 * i] = bv.x; bb[4 * i + 1] = bv.y; bb[4 * i + 2] = bv.z; bb[4 * i + 3] = bv.w;
-                        }
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 t = lds_f32x4(sbase + static_cast<uint32_t>(lane * 128 + ((k ^ (lane & 7)) << 4)));
+                        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+                    }
+                    const int oc = oc0 + lane;
+                    const float bj = lds_f32(b4 + 4 * lane);
+                    float pv[8];
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            const int j = h * 16 + jj;
-                            float v = ok ? __uint_as_float(r[j]) + res[j] : -INFINITY;
-                            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
-                            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-                            if (writer && oc0 + j < args.OC)
-                                *reinterpret_cast<float*>(dst + static_cast<unsigned long long>(oplane_bytes) * static_cast<uint32_t>(j)) =
-                                    fmaxf(v + bb[jj], floor_v);
+                    for (int pp = 0; pp < 8; ++pp)
+                        pv[pp] = fmaxf(fmaxf(fmaxf(v[2 * pp], v[2 * pp + 1]), fmaxf(v[16 + 2 * pp], v[17 + 2 * pp])) + bj, floor_v);
+                    // where the sub-patch's pooled row starts in the stored blob (the same for every lane of the warp)
+                    const int py = (bx.oy + 2 * (q >> 1)) >> 1, px0 = (bx.ox0 + 16 * (q & 1)) >> 1;
+                    if (bx.valid && oc < args.OC && py < SH && px0 < SW) {
+                        float* pd = args.out + (static_cast<size_t>(bx.n) * args.out_img_c + oc) * oplane + static_cast<size_t>(py) * SW + px0;
+                        if (px0 + 8 <= SW && (reinterpret_cast<uintptr_t>(pd) & 15) == 0) {
+                            *reinterpret_cast<float4*>(pd) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                            *reinterpret_cast<float4*>(pd + 4) = make_float4(pv[4], pv[5], pv[6], pv[7]);
+                        } else {
+#pragma unroll
+                            for (int pp = 0; pp < 8; ++pp)
+                                if (px0 + pp < SW) pd[pp] = pv[pp];
                         }
                     }
                 } else if (tma_out) {
