@@ -124,6 +124,9 @@ struct IgemmArgs {
     int2 ktab1[32];          // use_table == 2 (K <= 32, e.g. IC = 3 first layers): the k-table in the kernel parameters
     const unsigned char* wbf;  // BF16x3: pre-tiled filter planes (see igemm_pack_weights_bf16_kernel)
     unsigned wbf_kb_bytes;     // bytes of one k-block (both planes, every N tile): 2 * ocpad * 64
+    int flat_ow;             // > 0: output pixels are boxed along the FLATTENED index oy * OW + ox (OH = 1, OW = OH*OW in this
+                             // struct) and flat_ow is the real output width the producers divide by (small images)
+    unsigned long long m_flat_ow;
     unsigned desc_swap;      // debug: exchange the two byte offsets of the un-swizzled filter descriptor
     unsigned suspend_ns;     // suspend hint of the ring / slab / accumulator waits (0 = poll), see ptx::mbar_try_wait_ns
     int taps;                // KH*KW
@@ -803,8 +806,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const BoxCoord bx = decode_box(ptile * 4 + q, args);
             const int ox = bx.ox0 + lane;
             const bool pix_ok = bx.valid && ox < args.OW;
-            const int iy0 = bx.oy * args.stride_h - args.pad_top;
-            const int ix0 = ox * args.stride_w - args.pad_left;
+            int py = bx.oy, px = ox;
+            if (args.flat_ow > 0) {  // flattened boxes: this lane's pixel index -> (row, column) of the real output image
+                py = static_cast<int>(fast_div(static_cast<uint32_t>(ox), args.m_flat_ow, args.flat_ow));
+                px = ox - py * args.flat_ow;
+            }
+            const int iy0 = py * args.stride_h - args.pad_top;
+            const int ix0 = px * args.stride_w - args.pad_left;
             tapmask = 0;
             if (pix_ok) {  // row mask x column mask instead of KH*KW tests
                 unsigned long long cols = 0;
@@ -1241,7 +1249,13 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     a.wbf_kb_bytes = 2u * static_cast<unsigned>(igemm_ocpad(p.OC)) * 64u;
     if (BF && (igemm_bn_for(p.OC) != BN || static_cast<unsigned long long>(ceil_div(K, 32)) * igemm_ocpad(p.OC) * 128ull >= (1ull << 31))) return -1;
     a.in = p.input; a.out = p.output; a.bias = p.bias; a.residual = p.residual;
-    a.N = p.N; a.IC = p.IC; a.H = p.H; a.W = p.W; a.OC = p.OC; a.OH = p.OH; a.OW = p.OW;
+    // Small images on the generic path: a 32-pixel box along ONE output row is mostly padding when OW < 32 (7x7: 7 of 32
+    // lanes, 4.6x the tiles — ResNet-50's stage-5 3x3 / strided 1x1 layers ran 385 us each).  Box the flattened pixel index
+    // oy * OW + ox instead (the epilogue then sees a 1 x OH*OW image, like the pointwise remap of fcuda_api.cu).
+    const bool flat = !SLAB && !PW && p.OH > 1 && p.OW < 28 && p.pool == 0;
+    const int OHe = flat ? 1 : p.OH, OWe = flat ? p.OH * p.OW : p.OW;   // what the boxes / the epilogue see
+    a.flat_ow = flat ? p.OW : 0;
+    a.N = p.N; a.IC = p.IC; a.H = p.H; a.W = p.W; a.OC = p.OC; a.OH = OHe; a.OW = OWe;
     a.KH = p.KH; a.KW = p.KW; a.pad_top = p.pad_top; a.pad_left = p.pad_left;
     a.stride_h = p.stride_h; a.stride_w = p.stride_w;
     a.dil_h = p.dil_h > 1 ? p.dil_h : 1; a.dil_w = p.dil_w > 1 ? p.dil_w : 1;
@@ -1250,13 +1264,14 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     a.K = K;
     a.kblocks = ceil_div(K, 32);
     a.use_table = (p.IC % 32 == 0) ? 0 : 1;
-    a.bpr = ceil_div(p.OW, 32);
-    a.per_img = (SLAB ? ceil_div(p.OH, 4) : p.OH) * a.bpr;  // SLAB: tiles (4 x 32 patches) per image, else boxes per image
+    a.bpr = ceil_div(OWe, 32);
+    a.per_img = (SLAB ? ceil_div(p.OH, 4) : OHe) * a.bpr;  // SLAB: tiles (4 x 32 patches) per image, else boxes per image
     a.total_boxes = static_cast<long long>(p.N) * a.per_img * (SLAB ? 4 : 1);
     a.pool = SLAB ? p.pool : 0;
     a.taps = taps;
     a.tap_inv = (65536u + static_cast<unsigned>(p.KW) - 1u) / static_cast<unsigned>(p.KW);
     auto magic = [](int d) { return d > 1 ? ~0ull / static_cast<unsigned long long>(d) + 1ull : 0ull; };
+    a.m_flat_ow = magic(p.OW);
     a.m_per_img = magic(a.per_img);
     a.m_bpr = magic(a.bpr);
     a.num_n = ceil_div(p.OC, BN);
@@ -1340,9 +1355,9 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
     // (32 pixels of a row | a 2 x 16 sub-patch in SLAB mode).  Needs 16-byte rows; pooled launches keep direct stores.
     CUtensorMap tmOut = tmW;
     a.tma_out = 0;
-    if (tune_get(TUNE_IGEMM_TMA_OUT) && !a.pool && p.OW % 4 == 0 && (reinterpret_cast<uintptr_t>(p.output) & 15) == 0) {
-        cuuint64_t dims[4] = {(cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.OC, (cuuint64_t)p.N};
-        cuuint64_t strides[3] = {(cuuint64_t)p.OW * 4, (cuuint64_t)p.OW * p.OH * 4, (cuuint64_t)a.out_img_c * p.OW * p.OH * 4};
+    if (tune_get(TUNE_IGEMM_TMA_OUT) && !a.pool && OWe % 4 == 0 && (reinterpret_cast<uintptr_t>(p.output) & 15) == 0) {
+        cuuint64_t dims[4] = {(cuuint64_t)OWe, (cuuint64_t)OHe, (cuuint64_t)p.OC, (cuuint64_t)p.N};
+        cuuint64_t strides[3] = {(cuuint64_t)OWe * 4, (cuuint64_t)OWe * OHe * 4, (cuuint64_t)a.out_img_c * OWe * OHe * 4};
         cuuint32_t box[4] = {SLAB ? 16u : 32u, SLAB ? 2u : 1u, 32, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.output, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
