@@ -127,7 +127,6 @@ struct IgemmArgs {
     int flat_ow;             // > 0: output pixels are boxed along the FLATTENED index oy * OW + ox (OH = 1, OW = OH*OW in this
                              // struct) and flat_ow is the real output width the producers divide by (small images)
     unsigned long long m_flat_ow;
-    unsigned desc_swap;      // debug: exchange the two byte offsets of the un-swizzled filter descriptor
     unsigned suspend_ns;     // suspend hint of the ring / slab / accumulator waits (0 = poll), see ptx::mbar_try_wait_ns
     int taps;                // KH*KW
     unsigned tap_inv;        // ceil(65536 / KW): tap / KW == (tap * tap_inv) >> 16 for tap < 64
@@ -505,7 +504,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             constexpr uint32_t idesc = BF ? make_idesc_bf16(BN, 128) : make_idesc_tf32(BN, 128 * CG);
             // BF16x3: un-swizzled core-matrix layout [row / 8][16-byte k chunk (4)][row % 8][8 bf16]: 128 bytes between the
             // core matrices of consecutive k chunks (LBO), 512 bytes between 8-row groups (SBO)
-            const uint64_t dB0 = BF ? make_smem_desc_none(ptx::smem_u32(smem), args.desc_swap ? 512 : 128, args.desc_swap ? 128 : 512) : make_smem_desc_sw128(ptx::smem_u32(smem));
+            const uint64_t dB0 = BF ? make_smem_desc_none(ptx::smem_u32(smem), 128, 512) : make_smem_desc_sw128(ptx::smem_u32(smem));
             const uint32_t me = static_cast<uint32_t>(warp - kWarpMma);
             const uint32_t nissue = static_cast<uint32_t>(args.issuers);
             uint32_t g = me;
@@ -587,30 +586,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // ===================== SLAB: TMA producer of the input slabs =====================
         // one {48 x 6 x 32} box per item (tile, channel block), SST items ahead of the producers
         if (PW) {
-            // one 16 KB stage per k-block: four {32 pixels, 32 channels} boxes, SST k-blocks ahead of the producers
-            const bool leader = ptx::elect_one();
-            uint32_t g = 0;
-            for (long long tile = tile_first; tile < total_tiles; tile += tile_step) {
-                const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
-                BoxCoord bx[4];
-                int nvalid = 0;
+            // one 16 KB stage per k-block: four {32 pixels, 32 channels} boxes, SST k-blocks ahead of the producers.  Like the
+            // filter ring (see there) the boxes are issued in lockstep: lane = k-block slot * 4 + box, kPwK k-blocks per round —
+            // one thread needed ~280 cycles per TMA operation, four boxes a k-block, against 384 cycles of MMAs at N = 128.
+            constexpr int kPwK = 2;
+            static_assert(kPwK <= SST, "a round must not wait for its own stages");
+            if (lane < 4 * kPwK) {
+                const int ks = lane >> 2, q = lane & 3;
+                long long tile = tile_first;
+                int kb = ks;
+                uint32_t g = static_cast<uint32_t>(ks);
+                long long dec_tile = -1;
+                BoxCoord bx{};
+                uint32_t nvalid = 0;
+                for (;;) {
+                    while (kb >= kblocks && tile < total_tiles) { kb -= kblocks; tile += tile_step; }
+                    if (tile >= total_tiles) break;
+                    if (tile != dec_tile) {
+                        const uint32_t ptile = fast_div(static_cast<uint32_t>(tile), args.m_num_n, args.num_n);
+                        bx = decode_box(ptile * 4 + q, args);
+                        nvalid = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    bx[q] = decode_box(ptile * 4 + q, args);
-                    nvalid += bx[q].valid ? 1 : 0;
-                }
-                for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                        for (int qq = 0; qq < 4; ++qq) nvalid += (ptile * 4 + qq) < static_cast<uint32_t>(args.total_boxes) ? 1u : 0u;
+                        dec_tile = tile;
+                    }
                     const uint32_t st = g % SST;
                     ptx::mbar_wait(&slab_empty[st], ((g / SST) & 1u) ^ 1u, args.suspend_ns);
-                    if (leader) {
-                        ptx::mbar_arrive_expect_tx(&slab_full[st], static_cast<uint32_t>(nvalid) * kPwBoxBytes);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (bx[q].valid)
-                                ptx::tma_load_3d(slab0 + st * kPwStageBytes + q * kPwBoxBytes, &tmIn, &slab_full[st], bx[q].ox0, kb * 32,
-                                                 bx[q].n);
-                    }
-                    __syncwarp();
+                    if (q == 0) ptx::mbar_arrive_expect_tx(&slab_full[st], nvalid * kPwBoxBytes);
+                    if (bx.valid)
+                        ptx::tma_load_3d(slab0 + st * kPwStageBytes + q * kPwBoxBytes, &tmIn, &slab_full[st], bx.ox0, kb * 32, bx.n);
+                    g += kPwK;
+                    kb += kPwK;
                 }
             }
         }
@@ -883,6 +889,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         };
 
         float x[32];
+        bool gslot_free = false;  // ring slot of the cursor's k-block already seen released
         enter_tile();
         if (have) gather(x);
         while (have) {
@@ -890,7 +897,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const int my_stage = static_cast<int>(g & (STAGES - 1));
             const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
             if (q == 0) IG_TRACE(0, g);
-            wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
+            if (!gslot_free) wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
             if (q == 0) IG_TRACE(1, g);
             ptx::tc_fence_after();
             if (BF) {
@@ -926,6 +933,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             }
             if (q == 0) IG_TRACE(2, g);
             advance();
+            gslot_free = have && probe_ring_slot_free<STAGES>(empty_bar, g0 + static_cast<uint32_t>(kb));  // asked early, used next round
             if (have) gather(x);  // in flight across the store drain, the arrive and the next slot wait
             if (q == 0) IG_TRACE(3, g);
             tmem_st_wait();
@@ -1284,10 +1292,6 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
         return -1;
     a.relu = p.relu;
     a.suspend_ns = static_cast<unsigned>(tune_get(TUNE_MBAR_SUSPEND_NS));
-    {
-        static const int swap = getenv("FCUDA_DEBUG_DESC_SWAP") ? atoi(getenv("FCUDA_DEBUG_DESC_SWAP")) : 0;
-        a.desc_swap = static_cast<unsigned>(swap);
-    }
     // two issuers (one accumulator each) where one thread cannot keep the pipe fed: N <= 64 and at least four k-blocks
     // per tile (short-K tiles are epilogue-bound and would only pay the second accumulator read); BN = 128 has 768 cycles of MMA work per k-block against ~350 of issue work, and only 256 accumulator
     // columns.  FCUDA_IGEMM_ISSUERS=1 forces one issuer (diagnostic).

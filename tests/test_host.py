@@ -272,9 +272,17 @@ def test_hot_kernels_are_tcgen05_and_tma_in_sass():
         c = ops[k]
         assert c["UTCHMMA"] == 12 and c["STTM"] >= 4 and c["LDTM"] >= 1 and c["UTMALDG"] >= 2 and c["UTCBAR"] >= 2, (k, dict(c))
         assert c["HMMA"] == 0 and c["FFMA"] == 0, k              # no tensor-core-less inner product hiding in there
+    for k in only(r"conv_igemm_kernelILi(32|64|128)ELi3ELi[012]ELi1E"):   # BF16x3 implicit-GEMM conv (the default mode)
+        c = ops[k]
+        # three kind::f16 MMAs per 16-k step, two steps per k-block; filters by ONE 1-D bulk copy (UBLKCP) per k-block
+        assert c["UTCHMMA"] == 6 and c["STTM"] >= 4 and c["LDTM"] >= 1 and c["UBLKCP"] >= 1 and c["UTCBAR"] >= 2, (k, dict(c))
+        assert c["F2FP"] >= 16 and c["HMMA"] == 0 and c["FFMA"] == 0, (k, dict(c))   # on-chip bf16 RN split, no CUDA-core GEMM
+        if "ELi3ELi0ELi1E" not in k:                            # slab variants: operands arrive by TMA tensor loads
+            assert c["UTMALDG"] >= 1, (k, dict(c))
     for k in only(r"tensor_gemm_ts_kernelILi(32|64|128)E"):      # TensorGEMM, A split on chip into tensor memory
         c = ops[k]
-        assert c["UTCHMMA"] == 12 and c["STTM"] >= 4 and c["LDTM"] >= 1 and c["UTMALDG"] >= 3, (k, dict(c))
+        # (one UTMALDG in the single-CTA variants: the three operand loads of a k-block are ONE instruction over three lanes)
+        assert c["UTCHMMA"] == 12 and c["STTM"] >= 4 and c["LDTM"] >= 1 and c["UTMALDG"] >= 1, (k, dict(c))
         assert c["HMMA"] == 0
     for k in only(r"wino_(in|out)put_kernelILi8E"):              # transforms stay on CUDA cores, as designed
         assert ops[k]["UTCHMMA"] == 0 and ops[k]["FFMA"] + ops[k]["FADD"] > 100
