@@ -441,7 +441,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // instruction issue starts kTmaLanes copies.  (Lane j of a round needs the slot k-block g+j-STAGES used, whose filters
         // were requested one or two rounds earlier: no cycle as long as kTmaLanes <= STAGES.)
         constexpr int kTmaLanes = 4;
-        static_assert(kTmaLanes <= STAGES, "a round must not wait for its own copies");
+        static_assert(kTmaLanes <= STAGES && STAGES % kTmaLanes == 0, "a round must not wait for its own copies; one lane per ring slot, so a lane meets every phase of its slots' barriers");
         if (lane < kTmaLanes) {
             long long tile = tile_first;
             int kb = lane;
@@ -589,8 +589,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             // one 16 KB stage per k-block: four {32 pixels, 32 channels} boxes, SST k-blocks ahead of the producers.  Like the
             // filter ring (see there) the boxes are issued in lockstep: lane = k-block slot * 4 + box, kPwK k-blocks per round —
             // one thread needed ~280 cycles per TMA operation, four boxes a k-block, against 384 cycles of MMAs at N = 128.
-            constexpr int kPwK = 2;
-            static_assert(kPwK <= SST, "a round must not wait for its own stages");
+            // kPwK must DIVIDE the stage count: then a stage is always visited by the same lane group, in consecutive phases of
+            // its barriers.  (With 2 groups over 3 stages a group met a stage only every other phase, where a parity wait cannot
+            // tell "one phase behind" from "one ahead": a group that ran ahead of its twin after a divergent branch re-armed a
+            // barrier whose phase was still open — a dead-lock at bench batch sizes, profiles/r02aa.)
+            constexpr int kPwK = SST % 2 == 0 ? 2 : 3;
+            static_assert(SST % kPwK == 0 && kPwK <= SST, "one lane group per stage, and a round must not wait for its own stages");
             if (lane < 4 * kPwK) {
                 const int ks = lane >> 2, q = lane & 3;
                 long long tile = tile_first;
@@ -889,7 +893,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         };
 
         float x[32];
-        bool gslot_free = false;  // ring slot of the cursor's k-block already seen released
         enter_tile();
         if (have) gather(x);
         while (have) {
@@ -897,7 +900,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const int my_stage = static_cast<int>(g & (STAGES - 1));
             const uint32_t ta = tmem_a0 + lane_base + my_stage * kAStageCols;
             if (q == 0) IG_TRACE(0, g);
-            if (!gslot_free) wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
+            wait_ring_slot_free<STAGES>(empty_bar, g, args.suspend_ns);
             if (q == 0) IG_TRACE(1, g);
             ptx::tc_fence_after();
             if (BF) {
@@ -933,7 +936,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             }
             if (q == 0) IG_TRACE(2, g);
             advance();
-            gslot_free = have && probe_ring_slot_free<STAGES>(empty_bar, g0 + static_cast<uint32_t>(kb));  // asked early, used next round
             if (have) gather(x);  // in flight across the store drain, the arrive and the next slot wait
             if (q == 0) IG_TRACE(3, g);
             tmem_st_wait();

@@ -392,7 +392,7 @@ tensor_gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // Now kKG k-blocks x 3 operands are issued in lockstep by 3 * kKG lanes: lane = group * 3 + operand, group j takes
         // every kKG-th k-block of this CTA's k-block sequence; one instruction issue starts 3 * kKG loads.
         constexpr int kKG = 2;
-        static_assert(kKG <= STAGES, "a round must not wait for its own loads");
+        static_assert(kKG <= STAGES && STAGES % kKG == 0, "a round must not wait for its own loads; one lane group per ring slot (consecutive barrier phases)");
         if (lane < 3 * kKG) {
             const int grp = lane / 3, op = lane - grp * 3;
             const CUtensorMap* map = op == 0 ? &tmA : op == 1 ? &tmB : &tmBlo;
