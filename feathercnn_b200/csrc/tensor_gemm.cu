@@ -47,6 +47,7 @@ struct GemmKernelArgs {
     long long m_offset;
     long long split_stride;
     int tma_store;   // EPI_ROWMAJOR through shared memory + cp.async.bulk.tensor stores (tmD is valid)
+    int st256;       // EPI_ROWMAJOR direct stores as 32-byte st.global.v8 (whole sectors per lane; gemm_tma_store = 2)
     unsigned suspend_ns;  // suspend hint of the operand-ring waits (0 = poll), see ptx::mbar_try_wait_ns
 };
 
@@ -86,7 +87,14 @@ __device__ __forceinline__ void epilogue_store(const GemmKernelArgs& args, uint3
         if (m_ok) {
             if (args.epilogue == EPI_ROWMAJOR) {
                 float* dst = args.D + row_base + n0;
-                if (n0 + 32 <= args.N && (args.ldd & 3) == 0) {
+                if (args.st256 && n0 + 32 <= args.N && (args.ldd & 7) == 0) {
+                    // a lane owns a 128-byte row piece: four 32-byte stores = four whole sectors, no shared-memory staging
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8)
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + j), "r"(r[j]), "r"(r[j + 1]),
+                                     "r"(r[j + 2]), "r"(r[j + 3]), "r"(r[j + 4]), "r"(r[j + 5]), "r"(r[j + 6]), "r"(r[j + 7])
+                                     : "memory");
+                } else if (n0 + 32 <= args.N && (args.ldd & 3) == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
@@ -709,7 +717,7 @@ TuneEntry g_tune[TUNE_COUNT] = {
     {"igemm_cta_group", "FCUDA_IGEMM_CG", 1, 1, 2, 0, false},        // 2 = CTA pairs (cta_group::2, M = 256): correct, measured slower
     {"dw_vec", "FCUDA_DW_VEC", 1, 0, 1, 0, false},                   // vectorised depthwise kernel on wide planes
     {"gemm_cluster", "FCUDA_GEMM_CLUSTER", 1, 1, 4, 0, false},       // TMA-multicast of B across a cluster: measured slower
-    {"gemm_tma_store", "FCUDA_GEMM_TMA_STORE", 1, 0, 1, 0, false},   // row-major epilogue through smem + TMA stores
+    {"gemm_tma_store", "FCUDA_GEMM_TMA_STORE", 1, 0, 2, 0, false},   // row-major epilogue through smem + TMA stores
     {"igemm_tma_out", "FCUDA_IGEMM_TMA_OUT", 1, 0, 1, 0, false},     // implicit-GEMM epilogue through smem + TMA stores
     {"igemm_pw", "FCUDA_IGEMM_PW", 1, 0, 1, 0, false},               // TMA-fed slab producer for 1x1 / stride-1 layers
     {"wino_mlp", "FCUDA_WINO_MLP", 2, 0, 2, 0, false},
@@ -952,7 +960,8 @@ static int launch_ts(const GemmProblem& p, cudaStream_t stream) {
     fill_kernel_args(p, BN, &a);
     if (CL > 1) a.num_m = ceil_div(a.num_m, CL);  // work items = groups of CL consecutive M tiles
     // row-major D leaves through shared memory + TMA (see the epilogue); needs 16-byte rows
-    const bool tma_store_off = tune_get(TUNE_GEMM_TMA_STORE) == 0;
+    const bool tma_store_off = tune_get(TUNE_GEMM_TMA_STORE) != 1;
+    a.st256 = tune_get(TUNE_GEMM_TMA_STORE) == 2 && (reinterpret_cast<uintptr_t>(p.D) & 31) == 0 ? 1 : 0;
     CUtensorMap tmD = tmA;
     a.tma_store = 0;
     a.suspend_ns = static_cast<unsigned>(tune_get(TUNE_MBAR_SUSPEND_NS));

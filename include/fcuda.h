@@ -201,7 +201,8 @@ int fcuda_conv_forward_ext(const FcudaConvParam* param, int algo, float* output,
  *   igemm_cta_group (1-2, 1)  2: CTA pairs with tcgen05 cta_group::2 (M = 256, half of the filter tile per SM)
  *   dw_vec (0-1, 1)           vectorised depthwise kernel on wide planes
  *   gemm_cluster (1|2|4, 1)   TMA multicast of the B operand across a thread-block cluster in the TensorGEMM
- *   gemm_tma_store (0-1, 1)   row-major TensorGEMM epilogue through shared memory + TMA stores
+ *   gemm_tma_store (0-2, 1)   row-major TensorGEMM epilogue: 1 = through shared memory + TMA stores, 0 = direct 16-byte
+ *                             stores, 2 = direct 32-byte stores (st.global.v8: whole sectors, no shared-memory staging)
  *   igemm_tma_out (0-1, 1)    implicit-GEMM epilogue through shared memory + TMA stores (0: per-thread stores)
  *   igemm_pw (0-1, 1)         TMA-fed [32 channels][32 pixels] A boxes for 1x1 / stride-1 layers (0: generic gather)
  *   wino_mlp (0-2, 2)         Winograd transforms: 1 = every global load of a block in flight at once (cp.async slab /

@@ -145,6 +145,9 @@ SGECONV_CASES = [
     (32, 32, 17, 19, 3, 2, 1, True, True),      # 3x3 stride 2, odd sizes
     (128, 64, 28, 28, 1, 2, 0, False, False),   # strided pointwise (ResNet downsample)
     (16, 2048, 7, 7, 1, 1, 0, True, False),     # deep K (64 channel blocks), 49-pixel images
+    (64, 64, 7, 7, 3, 1, 1, True, True),        # ResNet stage-5 3x3 class: W % 4 != 0 -> generic gather, flattened pixel boxes
+    (160, 64, 14, 14, 1, 2, 0, False, True),    # strided pointwise onto 7x7 (flattened boxes, two N tiles)
+    (32, 40, 9, 9, 3, 2, 1, True, False),       # table gather (IC % 32 != 0) + stride 2 + flattened boxes (5x5 output)
 ]
 
 

@@ -95,7 +95,7 @@ def test_tensor_gemm_variants_are_bit_identical(cuda, tuning, geom):
     base = _conv(cuda, booster, geom, booster.WINOGRADF63)
     naive = _conv(cuda, booster, geom, booster.NAIVE)
     assert np.abs(base - naive).max() / np.abs(naive).max() < 2e-4
-    for cluster, store in ((1, 0), (2, 1), (4, 1), (2, 0)):
+    for cluster, store in ((1, 0), (1, 2), (2, 1), (4, 1), (2, 0)):   # store 2: direct 32-byte st.global.v8 epilogue
         tuning(gemm_cluster=cluster, gemm_tma_store=store)
         np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.WINOGRADF63), base)
 
