@@ -63,6 +63,10 @@ def test_net_group_shards_like_the_process_per_gpu_path():
     try:
         assert lib.fgroup_size(g) == 0 and lib.fgroup_broadcast_transport(g) == b""
         assert lib.fgroup_forward_batch(g, None, 1, None, None) == -1                  # not initialised
+        import torch
+        if not torch.cuda.is_available():   # no device: a clean error code, not a crash (the product has no CPU path)
+            assert lib.fgroup_init_from_path(g, b"/nonexistent/model", None, 0) == -700
+            assert lib.fgroup_size(g) == 0
     finally:
         lib.fgroup_destroy(g)
 
