@@ -127,6 +127,7 @@ struct IgemmArgs {
     int flat_ow;             // > 0: output pixels are boxed along the FLATTENED index oy * OW + ox (OH = 1, OW = OH*OW in this
                              // struct) and flat_ow is the real output width the producers divide by (small images)
     unsigned long long m_flat_ow;
+    int tma_lanes;           // lanes of the filter-TMA warp that issue in lockstep (1, 2 or 4)
     unsigned suspend_ns;     // suspend hint of the ring / slab / accumulator waits (0 = poll), see ptx::mbar_try_wait_ns
     int taps;                // KH*KW
     unsigned tap_inv;        // ceil(65536 / KW): tap / KW == (tap * tap_inv) >> 16 for tap < 64
@@ -440,8 +441,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // So kTmaLanes lanes of this warp each take every kTmaLanes-th k-block and run the chain in lockstep: one
         // instruction issue starts kTmaLanes copies.  (Lane j of a round needs the slot k-block g+j-STAGES used, whose filters
         // were requested one or two rounds earlier: no cycle as long as kTmaLanes <= STAGES.)
-        constexpr int kTmaLanes = 4;
-        static_assert(kTmaLanes <= STAGES && STAGES % kTmaLanes == 0, "a round must not wait for its own copies; one lane per ring slot, so a lane meets every phase of its slots' barriers");
+        // kTmaLanes (1, 2 or 4: divides the ring depth, so a lane owns its slots and meets every phase of their barriers) trades
+        // issue rate against prefetch distance: a round starts when the slot of its LAST k-block is free, so STAGES -
+        // kTmaLanes + 1 k-blocks of filters can be in flight ahead of the MMAs.
+        const int kTmaLanes = args.tma_lanes;
+        static_assert(STAGES % 4 == 0, "1, 2 or 4 lanes own whole ring slots");
         if (lane < kTmaLanes) {
             long long tile = tile_first;
             int kb = lane;
@@ -1294,6 +1298,8 @@ int launch_igemm(const IgemmProblem& p, cudaStream_t stream) {
         return -1;
     a.relu = p.relu;
     a.suspend_ns = static_cast<unsigned>(tune_get(TUNE_MBAR_SUSPEND_NS));
+    a.tma_lanes = tune_get(TUNE_IGEMM_TMA_LANES);
+    if (a.tma_lanes != 1 && a.tma_lanes != 2) a.tma_lanes = 4;
     // two issuers (one accumulator each) where one thread cannot keep the pipe fed: N <= 64 and at least four k-blocks
     // per tile (short-K tiles are epilogue-bound and would only pay the second accumulator read); BN = 128 has 768 cycles of MMA work per k-block against ~350 of issue work, and only 256 accumulator
     // columns.  FCUDA_IGEMM_ISSUERS=1 forces one issuer (diagnostic).

@@ -721,7 +721,8 @@ TuneEntry g_tune[TUNE_COUNT] = {
     {"igemm_tma_out", "FCUDA_IGEMM_TMA_OUT", 1, 0, 1, 0, false},     // implicit-GEMM epilogue through smem + TMA stores
     {"igemm_pw", "FCUDA_IGEMM_PW", 1, 0, 1, 0, false},               // TMA-fed slab producer for 1x1 / stride-1 layers
     {"wino_mlp", "FCUDA_WINO_MLP", 2, 0, 2, 0, false},
-    {"mbar_suspend_ns", "FCUDA_MBAR_SUSPEND_NS", 100000, 0, 1000000, 0, false},  // suspend hint of the implicit GEMM's hand-off waits (0 = poll)               // Winograd transforms: asynchronous slab copies / all plane loads in flight
+    {"mbar_suspend_ns", "FCUDA_MBAR_SUSPEND_NS", 100000, 0, 1000000, 0, false},  // suspend hint of the implicit GEMM's hand-off waits (0 = poll)
+    {"igemm_tma_lanes", "FCUDA_IGEMM_TMA_LANES", 4, 1, 4, 0, false},  // lanes of the implicit GEMM's filter-TMA warp issuing in lockstep (1, 2, 4)               // Winograd transforms: asynchronous slab copies / all plane loads in flight
 };
 }  // namespace
 const char* tune_name(int key) { return key >= 0 && key < TUNE_COUNT ? g_tune[key].name : nullptr; }

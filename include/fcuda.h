@@ -208,6 +208,9 @@ int fcuda_conv_forward_ext(const FcudaConvParam* param, int algo, float* output,
  *   wino_mlp (0-2, 2)         Winograd transforms: 1 = every global load of a block in flight at once (cp.async slab /
  *                             back-to-back plane loads) instead of register-staged rounds; 2 = also launch the channel
  *                             blocks of a tile group next to each other (whole 1 KB rows of V / M in flight together)
+ *   igemm_tma_lanes (1|2|4, 4) lanes of the implicit GEMM's filter-TMA warp that issue in lockstep (a thread starts a TMA
+ *                             operation only every ~280 cycles; VGG-16 5.45 / 5.05 / 5.05 ms with 1 / 2 / 4 lanes)
+ *   mbar_suspend_ns (0-1000000, 100000) suspend hint of the operand-ring barrier waits, 0 = poll (no measurable difference)
  * Every variant computes the same result (tests/test_gpu_variants.py).  Returns 0 / the value, -200 for an unknown name or value. */
 int fcuda_set_tuning(const char* name, int value);
 int fcuda_get_tuning(const char* name);

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 def tuning():
     from feathercnn_b200._lib import fcuda
     lib = fcuda()
-    names = ["igemm_issuers", "igemm_slab", "igemm_cta_group", "dw_vec", "gemm_cluster", "gemm_tma_store", "igemm_tma_out", "igemm_pw"]
+    names = ["igemm_issuers", "igemm_slab", "igemm_cta_group", "dw_vec", "gemm_cluster", "gemm_tma_store", "igemm_tma_out", "igemm_pw", "igemm_tma_lanes", "mbar_suspend_ns"]
     saved = {n: lib.fcuda_get_tuning(n.encode()) for n in names}
 
     def setter(**kw):
@@ -82,7 +82,11 @@ def test_bf16x3_implicit_gemm_variants(cuda, tuning, geom):
     np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
     tuning(igemm_tma_out=1, igemm_pw=0)
     np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
-    tuning(igemm_pw=1, igemm_issuers=1)
+    tuning(igemm_pw=1, igemm_tma_lanes=1, mbar_suspend_ns=0)   # one filter-TMA lane, polling barrier waits
+    np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
+    tuning(igemm_tma_lanes=2, mbar_suspend_ns=100000)
+    np.testing.assert_array_equal(_conv(cuda, booster, geom, booster.SGECONV), base)
+    tuning(igemm_tma_lanes=4, igemm_issuers=1)
     one = _conv(cuda, booster, geom, booster.SGECONV)
     assert np.abs(one - base).max() / np.abs(base).max() < 1e-5
 
