@@ -11,29 +11,46 @@
 //                                                      producer below serves all nine taps of a channel block from one slab)
 //   A[pixel][k]  = X[n][ic][oy*s+u-pad][ox*s+v-pad]   (0 outside the image: the im2col rule, generic_kernels.cpp:66-67)
 //
-//   M tile     = 128 output pixels = four 32-pixel row segments ("boxes", consecutive in (n, oy, ox/32) order);
+//   M tile     = 128 output pixels = four 32-pixel row segments ("boxes", consecutive in (n, oy, ox/32) order; along the
+//                FLATTENED pixel index when the image is narrower than a box, and a 4 x 32 patch in the 3x3 slab kernel);
 //                pixel <-> TMEM lane.
 //   A operand  = lives in TENSOR MEMORY.  Twelve producer warps (3 groups x 4; group g serves every third k-block) each
-//                own 32 pixels (= their TMEM lane quadrant): a thread gathers the 32 k-values of its pixel (loads
-//                coalesced across lanes along x, the NEXT k-block's 32 loads in flight while the current one is split),
-//                splits them into TF32 hi + fp32 lo (2 instructions per element) and writes them with tcgen05.st into a
-//                4-deep ring.  IC % 32 == 0: a k-block is one tap x 32 channels -> one predicate, one IMAD.WIDE per
-//                address; otherwise offsets and taps come from a small shared-memory table and a per-pixel tap mask.
-//                (TMA cannot gather: its innermost box coordinate must be 16-byte aligned — a +-1 pixel tap shift
-//                traps; an A tile in shared memory costs 3x the instructions and +33 cycles per MMA.)
-//   B operand  = filters re-packed once at Init to Wp[oc][k] (K-major), TF32 hi / fp32 lo planes, loaded by TMA into a
-//                4-deep shared-memory ring; one barrier per ring slot counts the 4 producer arrivals and the TMA bytes.
-//   MMA        = tcgen05.mma kind::tf32 with A from TMEM ("TS" form), 3 MMAs per k-step in 3xTF32 mode, issued by TWO
-//                elected threads that alternate k-blocks (the pipe holds ~6 MMAs and issue blocks beyond that; one
-//                thread's barrier wait / descriptor arithmetic / commit overlaps the other's blocking issue); fp32
-//                accumulators in a 2- (BN = 128) or 4-deep (BN <= 64) TMEM ring next to the A ring.
-//   epilogue   = tcgen05.ld -> +bias (staged in smem) [-> + residual, prefetched: fused Eltwise SUM] -> ReLU -> NCHW
-//                store; lanes hold consecutive pixels -> 128-byte coalesced rows.
-//   roles      = 19 warps: 0-3 epilogue, 4-15 producers (TMEM quadrant = warp % 4), 16 TMA, 17-18 MMA issuers.
+//                own 32 pixels (= their TMEM lane quadrant) and write the split operand with tcgen05.st into the ring.
+//                Where the 32 k-values of a pixel come from (template parameter SK):
+//                  1  3x3 / stride 1, IC % 32 == 0: the fp32 halo of the patch for 32 channels arrives ONCE by TMA (a
+//                     {48 columns, 6 rows, 32 channels} box, OOB zero fill = the padding); a k-block = one tap = 32 LDS.32
+//                     with immediate offsets.
+//                  2  1x1 / stride 1: four TMA boxes {32 pixels, 32 channels} per k-block, laid [channel][pixel].
+//                  0  everything else: gathered from global memory (coalesced across lanes along x, the NEXT k-block's
+//                     loads in flight while the current one is split); IC % 32 == 0: a k-block is one tap x 32 channels
+//                     -> one predicate, one IMAD.WIDE per address, otherwise offsets / taps from a small k-table.
+//                (TMA cannot gather a shifted tap: its innermost box coordinate must be 16-byte aligned; an A tile in
+//                shared memory costs 3x the instructions and +33 cycles per MMA.)
+//   arithmetic = template parameter PLANES: 3 (default) BF16x3 — x = p1 + p2 + r with p1 = RN_bf16(x), p2 = RN_bf16(x - p1),
+//                three kind::f16 MMAs p2*q1 + p1*q2 + p1*q1 per k-step of 16 (two values per TMEM column, 32 columns per
+//                ring stage, 8 stages); 2 = 3xTF32 (hi = x & 0xFFFFE000, lo = x - hi, three kind::tf32 MMAs per k-step of
+//                8, 64 columns per stage, 4 stages); 1 = plain TF32.
+//   B operand  = filters re-packed once at Init, K-major.  BF16x3: two bf16 planes PRE-TILED in global memory in the
+//                un-swizzled core-matrix order of tcgen05, [k-block][N tile][plane][row/8][16-byte k chunk][row%8][8]:
+//                a ring stage is one contiguous run, fetched by ONE cp.async.bulk.  3xTF32 / TF32: Wp[oc][k] fp32 rows
+//                (hi / lo planes), TMA tensor loads with the 128-byte swizzle.  One barrier per ring slot counts the 4
+//                producer arrivals and the copy's bytes.
+//   MMA        = tcgen05.mma with A from TMEM ("TS" form), issued by TWO elected threads that alternate k-blocks at
+//                N <= 64 (one accumulator each, folded in a fixed order by the epilogue: deterministic), one at N = 128;
+//                fp32 accumulators in a ring next to the A ring.
+//   epilogue   = tcgen05.ld -> +bias (staged in smem) [-> + residual, prefetched: fused Eltwise SUM] -> ReLU -> NCHW through
+//                a [channel][pixel] staging tile and one TMA store per 32-channel chunk; the fused 2x2 max-pool goes through
+//                swizzled shared memory (lane = channel).
+//   roles      = 20 warps: 0-3 epilogue, 4-15 producers (TMEM quadrant = warp % 4), 16 filter TMA, 17-18 MMA issuers, 19 slab TMA.
+//   hand-offs  = every role's loop is a chain of long-latency instructions (a barrier probe answers after ~200 cycles, a
+//                thread starts a TMA operation every ~280): TMA is issued by several lanes in lockstep, each owning its
+//                ring slots; issuers and slab producers probe the barrier of their NEXT k-block before working on the
+//                current one; every shared-memory access is an explicit ld/st.shared (a pointer into the dynamic array is
+//                generic to nvcc).  DESIGN.md section 3 has the measurements.
 //
 // Used where non-fused Winograd is bandwidth-bound (large images, <= 128 channels) and for every layer the reference
-// sends to im2col + SGEMM (1x1, strided, 7x7, IC = 3).  Measurements behind these choices: DESIGN.md section 3,
-// tests/cuda/mma_rate.cu, tests/cuda/igemm_trace.cu.
+// sends to im2col + SGEMM (1x1, strided, 7x7, IC = 3, small images).  Measurements behind these choices: DESIGN.md section 3,
+// tests/cuda/mma_rate.cu, tests/cuda/igemm_trace.cu, tests/cuda/store_rate.cu.
 #include "conv_igemm.cuh"
 
 #include "common.cuh"
