@@ -99,6 +99,16 @@ def test_workspace_planning_is_host_only_and_consistent():
     assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), booster.WINOGRADF63FUSED, 1, ctypes.byref(s), ctypes.byref(k)) == -1
     assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), booster.SGECONV, 1, ctypes.byref(s), ctypes.byref(k)) == 0
     assert s.value == 0 and k.value == 2 * 9 * 64 * 64   # implicit GEMM: no scratch, [tap][OC][IC] hi+lo
+    # the same buffer holds the pre-tiled BF16x3 planes of the default mode: 2 planes x k-blocks x OCpad x 64 bytes, where OCpad
+    # is OC rounded up to the N tile (32 / 64 / 128) — larger than the fp32 rows for short K or few output channels
+    for oc, ic, kk in ((64, 3, 3), (40, 64, 1), (200, 32, 1), (8, 8, 3)):
+        q = booster.ConvParam.make(oc, ic, 16, 16, kk, pad=kk // 2)
+        assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(q), booster.SGECONV, 1, ctypes.byref(s), ctypes.byref(k)) == 0
+        K = ic * kk * kk
+        bn = 32 if oc <= 32 else 64 if oc <= 64 else 128
+        ocpad = -(-oc // bn) * bn
+        tiled_floats = (2 * -(-K // 32) * ocpad * 64 + 3) // 4
+        assert k.value == max(2 * oc * ((K + 3) // 4 * 4), tiled_floats), (oc, ic, kk, k.value)
     assert fcuda().fcuda_conv_get_buffer_size(ctypes.byref(p), booster.WINOGRADF63, 0, ctypes.byref(s), ctypes.byref(k)) == -100
     assert fcuda().fcuda_pooling_out_dim(112, 0, 0, 3, 2) == 56
 
