@@ -1027,6 +1027,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 const uint32_t b4 = ptx::smem_u32(bias_s + oc0);  // bias_s is padded with zeros up to oc_pad
                 // all addend loads first (32 in flight), then the accumulator wait: a load placed next to its store
                 // is serialised behind the previous store by the aliasing rules (measured 2.4x slower epilogue)
+                // plain = one accumulator, no fused addend: the common case of the short-K layers, whose epilogue is the
+                // critical role — it skips the 32 zero-fills and 32 additions of `res` (warp-uniform branch)
+                const bool plain = !dual && args.residual == nullptr;
                 float res[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) res[j] = 0.f;
@@ -1108,14 +1111,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     if (lane == 0) ptx::tma_store_wait_read<kOutBufs - 1>();  // the store that last read this tile is done with it
                     __syncwarp();
                     const uint32_t sp = ptx::smem_u32(stg) + static_cast<uint32_t>(lane * 4);
+                    if (plain) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 bv = lds_f32x4(b4 + 16 * j4);
-                        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 bv = lds_f32x4(b4 + 16 * j4);
+                            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int j = j4 * 4 + e;
-                            sts_f32(sp + j * 128, fmaxf(__uint_as_float(r[j]) + res[j] + bb[e], floor_v));
+                            for (int e = 0; e < 4; ++e) {
+                                const int j = j4 * 4 + e;
+                                sts_f32(sp + j * 128, fmaxf(__uint_as_float(r[j]) + bb[e], floor_v));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 bv = lds_f32x4(b4 + 16 * j4);
+                            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int j = j4 * 4 + e;
+                                sts_f32(sp + j * 128, fmaxf(__uint_as_float(r[j]) + res[j] + bb[e], floor_v));
+                            }
                         }
                     }
                     ptx::fence_proxy_async_smem();
