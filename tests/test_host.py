@@ -496,3 +496,27 @@ def test_tuning_switches_are_validated_on_the_host():
     assert lib.fcuda_get_tuning(b"igemm_slab") == 1 and lib.fcuda_get_tuning(b"gemm_tma_store") == 1
     assert lib.fcuda_set_tuning(b"igemm_cta_group", 2) == 0 and lib.fcuda_get_tuning(b"igemm_cta_group") == 2
     assert lib.fcuda_set_tuning(b"igemm_cta_group", 1) == 0
+
+
+def test_every_documented_tuning_switch_and_precision_mode_exists():
+    """include/fcuda.h documents the kernel-variant switches as `name (range, default)` and the three arithmetic modes; the
+    registry in libfcuda.so must know each name, report the documented default and reject out-of-range values."""
+    from feathercnn_b200 import booster
+    from feathercnn_b200._lib import fcuda
+    lib = fcuda()
+    text = (ROOT / "include" / "fcuda.h").read_text()
+    found = re.findall(r"^ \*   (\w+) \(([0-9|\-]+), (\d+)\)", text, flags=re.M)
+    assert len(found) >= 11, found
+    for name, rng, default in found:
+        assert lib.fcuda_get_tuning(name.encode()) == int(default), (name, default)
+        hi = int(re.split(r"[|\-]", rng)[-1])
+        assert lib.fcuda_set_tuning(name.encode(), hi + 1) == -200, name
+        assert lib.fcuda_set_tuning(name.encode(), int(default)) == 0, name
+    saved = booster.get_precision()
+    try:
+        for mode in (booster.PRECISION_TF32X3, booster.PRECISION_TF32, booster.PRECISION_FP32_SPLIT):
+            booster.set_precision(mode)
+            assert booster.get_precision() == mode
+        assert lib.fcuda_set_precision(3) == -200 and lib.fcuda_set_precision(-1) == -200
+    finally:
+        booster.set_precision(saved)
